@@ -1,0 +1,207 @@
+/*
+ * simudo_b200.h -- C ABI of the B200 assembly hot path.
+ *
+ * The reference (simudo 0.6.5) has no FFI for this path: its seam is the
+ * Python duck-typed one between simudo.fem.NewtonSolver and
+ * dolfin.SystemAssembler / PETScLUSolver.  Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the ctypes binding a Simudo maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures;
+ *   - "h_" = host pointer, "d_" = device pointer (cudaMalloc'ed, e.g. a
+ *     torch tensor's data_ptr()); all device work is enqueued on `stream`
+ *     (a cudaStream_t cast to void*, NULL = legacy default stream) and is
+ *     stream-ordered, nothing synchronises unless stated;
+ *   - return 0 on success, negative sb_status on failure; the Python host maps
+ *     failures to RuntimeError exactly like dolfin/PETSc errors surface in the
+ *     reference (simudo/fem/adaptive_stepper.py:212-217);
+ *   - every number is in "form units": length in mesh_unit (um), potential V,
+ *     energy eV, current A, time s, charge C, densities 1/um^3
+ *     (simudo/fem/delayed_form.py:80-94 folds pint units into the same
+ *     dimensionless form values).
+ */
+#ifndef SIMUDO_B200_H
+#define SIMUDO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_MAX_BANDS   4
+#define SB_MAX_PROCS   8
+#define SB_MAX_FIELDS  4
+#define SB_MAX_QUAD_M  11      /* collapsed Gauss-Jacobi points per axis    */
+
+/* band statistics: simudo/physics/poisson_drift_diffusion1.py1:170-245 */
+enum { SB_BAND_NONDEGENERATE = 0, SB_BAND_INTERMEDIATE = 1 };
+
+/* generation / recombination processes: simudo/physics/electro_optical_process.py */
+enum {
+  SB_PROC_SRH      = 0,  /* SRHRecombination                 :495-536 */
+  SB_PROC_SR_TRAP  = 1,  /* NonRadiativeTrap                 :539-562 */
+  SB_PROC_RAD_BB   = 2,  /* NonOverlappingTopHatBeerLambert  :398-431 */
+  SB_PROC_RAD_IB   = 3   /* NonOverlappingTopHatBeerLambertIB:434-492 */
+};
+
+typedef enum {
+  SB_OK = 0,
+  SB_ERR_ARG = -1,
+  SB_ERR_CUDA = -2,
+  SB_ERR_ALLOC = -3,
+  SB_ERR_NOT_FINITE = -4,
+  SB_ERR_UNSUPPORTED = -5
+} sb_status;
+
+/* Per cell-tag parameter row (doubles).  One row per distinct cell value of
+ * MeshData.cell_function; replaces the conditional tree that Spatial.get()
+ * builds on the DG0 tag function (simudo/fem/spatial.py:350-376,
+ * simudo/fem/expr.py:106-153; missing rule => 0.0). */
+#define SB_TP_KT          0   /* k T / e                                [eV]        */
+#define SB_TP_EPS         1   /* permittivity                [e / (V um)]           */
+#define SB_TP_RHO_STATIC  2   /* poisson/static_rho          [e / um^3]             */
+#define SB_TP_BAND0       3   /* + 5*b : band b                                     */
+#define   SB_TPB_IN_SUBDOMAIN 0 /* 1 inside band.subdomain, 0 in subdomain_inv     */
+#define   SB_TPB_N            1 /* eff. DOS or number_of_states [1/um^3]           */
+#define   SB_TPB_E            2 /* (effective) energy level     [eV]               */
+#define   SB_TPB_MOBILITY     3 /* mobility / mobility0         [um^2/(V s)]       */
+#define   SB_TPB_SPARE        4
+#define SB_TP_PROC0       (SB_TP_BAND0 + 5 * SB_MAX_BANDS)  /* + 8*p : process p   */
+#define   SB_TPP_P0           0 /* SRH tau(dst)  | trap capture coeff [um^3/s]     */
+                                /* RAD_BB alpha*I_strandberg [1/(um^3 s)]          */
+                                /* RAD_IB pseudo capture coeff sigma_opt*I/u1      */
+#define   SB_TPP_P1           1 /* SRH tau(src) [s]                                */
+#define   SB_TPP_P2           2 /* SRH u1(dst) [1/um^3]                            */
+#define   SB_TPP_P3           3 /* SRH u1(src) [1/um^3]                            */
+#define   SB_TPP_FIELD0       4 /* + f : absorption of optical field f inside its  */
+                                /* window: RAD_BB alpha [1/um]; RAD_IB sigma [um^2]*/
+#define SB_TAG_STRIDE     (SB_TP_PROC0 + 8 * SB_MAX_PROCS)
+
+/* Physics description (what PoissonDriftDiffusion + bands + processes lower to). */
+typedef struct sb_model {
+  int32_t n_bands;          /* bands entering rho, in pdd.bands order               */
+  int32_t bands_have_dofs;  /* 1: goal 'full' (MixedQfl unknowns, P = 1 + n_bands); */
+                            /* 0: goal 'thermal equilibrium' (qfl == 0, P = 1)      */
+  int32_t n_procs;
+  int32_t n_fields;         /* optical fields feeding g (Phi_pddproj, CG2 per cell) */
+  int32_t n_tags;
+  int32_t quad_m_rho;       /* (mixed_debug_quad_degree_rho   + 2)/2, default 11    */
+  int32_t quad_m_super;     /* (mixedqfl_debug_quad_degree_super + 2)/2, default 11 */
+  int32_t quad_m_g;         /* (mixedqfl_debug_quad_degree_g  + 2)/2, default 5     */
+  int32_t band_kind[SB_MAX_BANDS];
+  int32_t band_sign[SB_MAX_BANDS];            /* -1 electrons, +1 holes            */
+  int32_t band_const_mobility[SB_MAX_BANDS];  /* IB: use_constant_mobility         */
+  int32_t proc_kind[SB_MAX_PROCS];
+  int32_t proc_dst[SB_MAX_PROCS];             /* band indices, -1 = none           */
+  int32_t proc_src[SB_MAX_PROCS];
+  int32_t proc_trap[SB_MAX_PROCS];
+  int32_t proc_radiative[SB_MAX_PROCS];       /* enable_radiative_recombination    */
+  double  e_charge;         /* elementary charge [C]: -s e <v g> factor            */
+  double  dd_scale;         /* unit factor of <xi.j/(mu u)>  (= 1/e_charge)        */
+  double  ext_w_coef;       /* external_qfl_term constant  (poisson_drift_diffusion1.py1:285-286) */
+  double  ext_j_coef;       /* external_j_term constant    (:288-289)              */
+} sb_model;
+
+/* Mesh + space + boundary description handed to sb_plan_create (host pointers,
+ * copied to the device).  Replaces dolfin Mesh/DofMap/SparsityPattern/
+ * DirichletBC construction inside SystemAssembler(J, F, bcs)
+ * (simudo/fem/newton_solver.py:293-304). */
+typedef struct sb_problem {
+  int64_t n_cells;
+  int64_t n_dofs;              /* N                                                */
+  int32_t P;                   /* sub-problems; L = 15 P local dofs                */
+  const double*  h_cell_vertices; /* [n_cells][3][2] vertex-sorted cell geometry   */
+  const int32_t* h_cell_tag;      /* [n_cells] row index into tag_params           */
+  const int32_t* h_cell_dofs;     /* [n_cells][L]                                  */
+  const int32_t* h_cell_neighbors;/* [n_cells][3] cell across local facet f, -1    */
+  const uint8_t* h_cell_jump_mask;/* [n_cells][3] bit b set: base_w jump term of   */
+                                  /* band b on this (interior) facet, and this     */
+                                  /* cell is its '+' side                          */
+  const int64_t* h_rowptr;        /* [N+1] dolfin-pattern CSR row pointers         */
+  const uint8_t* h_rank_own;      /* [n_cells][L]                                  */
+  const uint8_t* h_rank_fac;      /* [n_cells][3][L]                               */
+  const double*  h_tag_params;    /* [n_tags][SB_TAG_STRIDE]                       */
+  /* essential (Dirichlet) conditions: constrained global dofs, sorted ascending   */
+  int64_t n_bc;
+  const int32_t* h_bc_dofs;       /* [n_bc]                                        */
+  /* cell-local right-hand-side additions (natural BC terms): static sparsity      */
+  int64_t n_natbc;
+  const int32_t* h_natbc_cell;    /* [n_natbc]                                     */
+  const int32_t* h_natbc_row;     /* [n_natbc] local dof index 0..L-1              */
+  /* reference-element constant tables, see simudo_b200/fem/reference_element.py   */
+  const double* h_tables;         /* packed; layout = sb_tables_layout()           */
+  int64_t n_tables;
+} sb_problem;
+
+typedef struct sb_plan sb_plan;   /* opaque */
+
+/* Per-assembly inputs (device pointers). */
+typedef struct sb_state {
+  const double* d_u;          /* [N] current solution u_ (mixed function vector)    */
+  const double* d_base_w;     /* [n_bands][n_cells] mixedqfl_base_w (DG0), or NULL  */
+  const double* d_thmeq_phi;  /* [n_cells][6] thermal_equilibrium_phi (DG2), or NULL*/
+  const double* d_phi_opt;    /* [n_fields][n_cells][6] Phi_pddproj per cell (P2)   */
+  const double* d_bc_values;  /* [n_bc] Dirichlet value per constrained dof         */
+  const double* d_natbc_values;/* [n_natbc] values added to the local residual      */
+} sb_state;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+int  sb_plan_create(const sb_model* model, const sb_problem* problem, sb_plan** out);
+void sb_plan_destroy(sb_plan* plan);
+const char* sb_last_error(void);
+int  sb_version(void);
+/* number of kernel launches issued through this library since load */
+int64_t sb_launch_count(void);
+
+/* ---- a1 + a2: Jacobian and residual in one traversal ---------------------------
+ * Replaces NewtonSolution.A / .b, i.e. SystemAssembler.assemble(A) and
+ * .assemble(b, x0=u_) (simudo/fem/newton_solver.py:48-77): cell integrals,
+ * exterior-facet natural terms, the base_w interior-facet jump term, and the
+ * element-wise symmetric Dirichlet application with x0 lifting.
+ * d_vals [nnz] (dolfin pattern; structural zeros are written once by
+ * sb_plan_zero_values and never touched again), d_b [N].  Either may be NULL.  */
+int sb_assemble(sb_plan* plan, const sb_state* state,
+                double* d_vals, double* d_b, void* stream);
+int sb_plan_zero_values(sb_plan* plan, double* d_vals, void* stream);
+int64_t sb_plan_nnz(const sb_plan* plan);
+/* materialise the CSR column indices (int32) on the device: for export/solvers */
+int sb_plan_column_indices(sb_plan* plan, int32_t* d_colidx, void* stream);
+
+/* ---- a9: qfl rebasing ----------------------------------------------------------
+ * Replaces MixedQflBand.mixedqfl_do_rebase_w (poisson_drift_diffusion1.py1:339-383)
+ * with default thresholds (0,0): base_w += cellavg(delta_w), BC-adjacent cells
+ * overridden; delta_w re-expressed so base_w + delta_w is unchanged.
+ * bc_cells/bc_avg describe PartitionOffsets.bc_cells (offset_partitioning.py:95-107). */
+int sb_rebase_w(sb_plan* plan, double* d_u, double* d_base_w,
+                int32_t band, int64_t n_bc_cells,
+                const int32_t* d_bc_cells, const double* d_bc_avg, void* stream);
+
+/* ---- a11: Newton update + convergence metrics -----------------------------------
+ * Replaces NewtonSolver.do_update_solution / NewtonSolution.{b_norm, du_norm,
+ * rel_du_norm, combined_du_norm, has_nans} (newton_solver.py:79-122,306-317,533-547).
+ * u -= omega * clip(du, +-max_du) (max_du <= 0: no clipping).
+ * d_out[0]=|b|_inf  [1]=|du|_inf  [2]=sum (du/u)^2 over finite ratios
+ * [3]=max |du| / (rel |u| + abs tol_i)  [4]=nan flag (u or b)  [5]=count of finite ratios */
+int sb_newton_update(sb_plan* plan, double* d_u, const double* d_du, const double* d_b,
+                     const double* d_tol, double omega, double max_du,
+                     double rel_tol, double abs_tol, double* d_out, void* stream);
+
+/* ---- terminal current ----------------------------------------------
+ * Replaces MetaExtractorIntegrals.add_surface_flux (simudo/io/output_writer.py:
+ * 174-231): sum over listed exterior facets of the BDM normal flux of sub-problem
+ * p; d_out[0] = integral j.n ds, d_out[1] = total facet length.                   */
+int sb_surface_flux(sb_plan* plan, const double* d_u, int32_t p,
+                    int64_t n_facets, const int32_t* d_facet_cell,
+                    const int8_t* d_facet_local, const double* d_facet_sign,
+                    double* d_out, void* stream);
+
+/* layout of the packed reference tables expected in sb_problem.h_tables */
+int64_t sb_tables_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMUDO_B200_H */
