@@ -1,0 +1,110 @@
+"""ctypes binding of ``libsimudo_b200.so`` (C ABI: ``include/simudo_b200.h``).
+
+The library is the product: there is no CPU fallback.  If the nvcc-built
+shared object is missing this module raises at first use, and every plan
+insists on CUDA tensors.  (``_use_library_for_tests`` exists only so that the
+GPU-less CI container can run the kernel source through ``tests/emul``'s
+CUDA-on-CPU shim; nothing in the package calls it.)
+"""
+import ctypes as C
+import os
+
+from .fem.model import SbModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, 'csrc', 'libsimudo_b200.so')
+
+_LIB = None
+_EMULATED = False
+
+EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
+            'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
+            'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update',
+            'sb_surface_flux', 'sb_tables_size']
+
+
+class SbProblem(C.Structure):
+    _fields_ = [
+        ('n_cells', C.c_int64), ('n_dofs', C.c_int64), ('P', C.c_int32),
+        ('h_cell_vertices', C.c_void_p), ('h_cell_tag', C.c_void_p),
+        ('h_cell_dofs', C.c_void_p), ('h_cell_neighbors', C.c_void_p),
+        ('h_cell_jump_mask', C.c_void_p), ('h_rowptr', C.c_void_p),
+        ('h_rank_own', C.c_void_p), ('h_rank_fac', C.c_void_p),
+        ('h_tag_params', C.c_void_p),
+        ('n_bc', C.c_int64), ('h_bc_dofs', C.c_void_p),
+        ('n_natbc', C.c_int64), ('h_natbc_cell', C.c_void_p),
+        ('h_natbc_row', C.c_void_p),
+        ('h_tables', C.c_void_p), ('n_tables', C.c_int64)]
+
+
+class SbState(C.Structure):
+    _fields_ = [('d_u', C.c_void_p), ('d_base_w', C.c_void_p),
+                ('d_thmeq_phi', C.c_void_p), ('d_phi_opt', C.c_void_p),
+                ('d_bc_values', C.c_void_p), ('d_natbc_values', C.c_void_p)]
+
+
+def _declare(lib):
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    lib.sb_plan_create.argtypes = [C.POINTER(SbModel), C.POINTER(SbProblem), C.POINTER(vp)]
+    lib.sb_plan_create.restype = C.c_int
+    lib.sb_plan_destroy.argtypes = [vp]
+    lib.sb_plan_destroy.restype = None
+    lib.sb_last_error.restype = C.c_char_p
+    lib.sb_version.restype = C.c_int
+    lib.sb_launch_count.restype = i64
+    lib.sb_tables_size.restype = i64
+    lib.sb_plan_nnz.argtypes = [vp]
+    lib.sb_plan_nnz.restype = i64
+    lib.sb_assemble.argtypes = [vp, C.POINTER(SbState), vp, vp, vp]
+    lib.sb_assemble.restype = C.c_int
+    lib.sb_plan_zero_values.argtypes = [vp, vp, vp]
+    lib.sb_plan_zero_values.restype = C.c_int
+    lib.sb_plan_column_indices.argtypes = [vp, vp, vp]
+    lib.sb_plan_column_indices.restype = C.c_int
+    lib.sb_rebase_w.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp]
+    lib.sb_rebase_w.restype = C.c_int
+    lib.sb_newton_update.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
+    lib.sb_newton_update.restype = C.c_int
+    lib.sb_surface_flux.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp]
+    lib.sb_surface_flux.restype = C.c_int
+    return lib
+
+
+def get():
+    """Load the CUDA extension or fail loudly."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                'simudo_b200 CUDA extension not built: {} is missing. Run '
+                '`python -m simudo_b200.csrc.build` (needs nvcc); there is no '
+                'CPU fallback for the assembly path.'.format(SO_PATH))
+        _LIB = _declare(C.CDLL(SO_PATH))
+    return _LIB
+
+
+def is_emulated():
+    return _EMULATED
+
+
+def check(rc):
+    """Map a negative status to RuntimeError, as dolfin/PETSc failures surface
+    in the reference (``simudo/fem/adaptive_stepper.py:212-217``)."""
+    if rc != 0:
+        msg = get().sb_last_error()
+        raise RuntimeError('simudo_b200: {} (status {})'.format(
+            msg.decode() if msg else 'error', rc))
+
+
+def _use_library_for_tests(path):
+    """TEST ONLY: bind an alternative build of the same C ABI (tests/emul)."""
+    global _LIB, _EMULATED
+    _LIB = _declare(C.CDLL(path))
+    _EMULATED = True
+    return _LIB
+
+
+def _reset_for_tests():
+    global _LIB, _EMULATED
+    _LIB = None
+    _EMULATED = False

@@ -1,0 +1,893 @@
+/*
+ * pdd_kernels.cu -- sm_100a kernels + C ABI (include/simudo_b200.h).
+ *
+ * k_assemble: one CTA = SB_TILE cells.  Thread-per-cell phases A/B write
+ * coefficient moments into a shared-memory tile; warp-per-cell phase C turns
+ * them into element-tensor entries and scatters them into the fixed CSR
+ * (see pdd_device.cuh for the math and the reference citations).
+ * No tensor cores: the path is FP64 gather / pointwise transcendental /
+ * scatter (BASELINE.json north_star).
+ */
+#ifdef SB_EMUL_BUILD
+#include "cuda_emul.h"      /* tests/emul: CPU shim, test infrastructure only */
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emul::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include <atomic>
+
+#include "pdd_device.cuh"
+
+#define SB_TILE 128
+#define SB_TS (SB_TILE + 1)        /* padded tile stride (bank-conflict free) */
+#define SB_WARPS (SB_TILE / 32)
+
+__constant__ SbTables c_T;
+__constant__ sb_model c_M;
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static const void* g_tables_owner = nullptr;
+
+#define CUDA_TRY(x)                                                          \
+  do {                                                                       \
+    cudaError_t e_ = (x);                                                    \
+    if (e_ != cudaSuccess) {                                                 \
+      snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #x,            \
+               cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+      return SB_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+struct PlanDev {
+  int64_t n_cells, N, nnz;
+  int32_t P, L, nb, nb_dof;
+  const double* cell_vertices;
+  const int32_t* cell_tag;
+  const int32_t* cell_dofs;
+  const int32_t* cell_neighbors;
+  const uint8_t* cell_jump_mask;
+  const int64_t* rowptr;
+  const uint8_t* rank_own;
+  const uint8_t* rank_fac;
+  const double* tag_params;
+  const int32_t* cell_special;   /* [n_cells] -1 or special index            */
+  const uint64_t* sp_mask_lo;
+  const uint32_t* sp_mask_hi;
+  const int32_t* sp_bcidx;       /* [n_special][L] index into bc_values | -1 */
+  const int32_t* sp_nat_begin;   /* [n_special+1]                            */
+  const int32_t* natbc_row;      /* sorted by cell                           */
+  const SbTables* tables;        /* global copy for lane-varying indexing    */
+};
+
+struct sb_plan {
+  PlanDev d;
+  sb_model model;
+  SbTables tables;
+  std::vector<void*> allocs;
+  int64_t n_bc, n_natbc, n_special;
+  double* tmp_cells;             /* [n_cells] scratch for rebase             */
+};
+
+struct StateDev {
+  const double* u;
+  const double* base_w;
+  const double* thmeq;
+  const double* phi_opt;
+  const double* bc_values;
+  const double* natbc_values;
+};
+
+/* ------------------------------------------------------------------------- */
+/* zero the slots that two cells add into: residual entries of facet dofs and
+ * the (facet dof, facet dof) Jacobian entries                                */
+__global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  const int L = pl.L;
+  const int32_t* dofs = pl.cell_dofs + c * L;
+  const uint8_t* rf = pl.rank_fac + c * 3 * L;
+  for (int p = 0; p < pl.P; ++p)
+    for (int f = 0; f < 3; ++f)
+      for (int k = 0; k < 3; ++k) {
+        const int li = sb_lbdm(p, 3 * f + k);
+        const int64_t row = dofs[li];
+        if (b) b[row] = 0.0;
+        if (vals) {
+          const int64_t r0 = pl.rowptr[row];
+          for (int k2 = 0; k2 < 3; ++k2) {
+            const uint8_t rk = rf[f * L + sb_lbdm(p, 3 * f + k2)];
+            if (rk != 0xFF) vals[r0 + rk] = 0.0;
+          }
+        }
+      }
+}
+
+/* ------------------------------------------------------------------------- */
+struct TileSmem {
+  /* moment tiles, [moment][cell] with padded stride */
+  double A[SB_NMC + SB_NQ][SB_TS];          /* current band: mC, Q; aliased by G */
+  double X[SB_MAX_BANDS][SB_NRX][SB_TS];    /* d(s u/eps)/dchi per band         */
+  double R[SB_NR][SB_TS];                   /* rho/eps                          */
+  SbWarpScratch ws[SB_WARPS];
+};
+static_assert(SB_NG <= SB_NMC + SB_NQ, "g-moment tile must fit in the A tile");
+
+__device__ __forceinline__ void warp_sync() { __syncwarp(); }
+
+/* load local dofs + Dirichlet lift values of one cell into warp scratch */
+__device__ __forceinline__ void load_cell(const PlanDev& pl, const StateDev& st, int64_t c,
+                                          SbCellCtx& cx, SbWarpScratch& S, int lane,
+                                          double* vals, double* b) {
+  const int L = pl.L;
+  cx.c = c; cx.L = L;
+  cx.dofs = pl.cell_dofs + c * L;
+  cx.rank_own = pl.rank_own + c * L;
+  cx.rank_fac = pl.rank_fac + c * 3 * L;
+  cx.rowptr = pl.rowptr;
+  cx.vals = vals; cx.b = b;
+  const int32_t sp = pl.cell_special[c];
+  cx.bcmask_lo = 0; cx.bcmask_hi = 0;
+  if (sp >= 0) { cx.bcmask_lo = pl.sp_mask_lo[sp]; cx.bcmask_hi = pl.sp_mask_hi[sp]; }
+  for (int l = lane; l < L; l += 32) {
+    const double ul = st.u[cx.dofs[l]];
+    S.ul[l] = ul;
+    double g = 0.0;
+    if (sp >= 0) {
+      const int32_t bi = pl.sp_bcidx[(int64_t)sp * L + l];
+      if (bi >= 0) g = ul - st.bc_values[bi];
+    }
+    S.gl[l] = g;
+    S.bl[l] = 0.0;
+  }
+}
+
+/* add natural-BC values of rows in [lo, hi) of this cell to the local residual */
+__device__ __forceinline__ void add_natbc(const PlanDev& pl, const StateDev& st, int64_t c,
+                                          SbWarpScratch& S, int lo, int hi, int lane) {
+  const int32_t sp = pl.cell_special[c];
+  if (sp < 0) return;
+  const int32_t b0 = pl.sp_nat_begin[sp], b1 = pl.sp_nat_begin[sp + 1];
+  for (int32_t k = b0 + lane; k < b1; k += 32) {
+    const int row = pl.natbc_row[k];
+    if (row >= lo && row < hi) atomicAdd(&S.bl[row], st.natbc_values[k]);
+  }
+}
+
+/* final write of residual rows [lo, hi) */
+__device__ __forceinline__ void write_rows(const SbCellCtx& cx, SbWarpScratch& S,
+                                           int lo, int hi, int lane) {
+  if (!cx.b) return;
+  for (int l = lo + lane; l < hi; l += 32) {
+    const double v = sb_is_bc(cx, l) ? S.gl[l] : S.bl[l];
+    double* dst = cx.b + cx.dofs[l];
+    if (sb_local_facet(l) >= 0) atomicAdd(dst, v); else *dst = v;
+  }
+}
+
+/* ---- phase C, band rows ---------------------------------------------------- */
+__device__ void phaseC_band(const PlanDev& pl, const StateDev& st, TileSmem& sm,
+                            int64_t c, int ct, int k, int lane, SbWarpScratch& S,
+                            double* vals, double* b) {
+  const SbTables& T = *pl.tables;
+  const int p = 1 + k;
+  const int nb = pl.nb;
+  SbCellCtx cx;
+  load_cell(pl, st, c, cx, S, lane, vals, b);
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+  sb_prep_cell(T, g, S, lane, 32);
+  warp_sync();
+  const int rlo = sb_lbdm(p, 0), rhi = rlo + 12;
+  if (inside) {
+    for (int e = lane; e < 21; e += 32) {
+      double v = 0.0;
+      for (int t = 0; t < SB_NMC; ++t) v += T.G22u[e][t] * sm.A[t][ct];
+      S.W[e] = v;
+    }
+    sb_flux_coeffs(S, &S.ul[rlo], S.gc, lane, 32);
+    for (int e = lane; e < 36; e += 32) {
+      const int a = e / 18, r = (e % 18) / 3, l = e % 3;
+      double v = 0.0;
+      for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * sm.A[SB_NMC + a * 10 + t][ct];
+      S.V[a][r][l] = v;
+    }
+    warp_sync();
+    for (int e = lane; e < 144; e += 32) {
+      const int m = e / 12, a = (e % 12) / 6, r = e % 6;
+      double v = 0.0;
+      for (int s = 0; s < 6; ++s) v += S.W[sb_sym21(r, s)] * S.GC[m][a][s];
+      S.Z[m][a][r] = v;
+    }
+    for (int e = lane; e < 12; e += 32) {
+      const int a = e / 6, r = e % 6;
+      double v = 0.0;
+      for (int s = 0; s < 6; ++s) v += S.W[sb_sym21(r, s)] * S.gc[a][s];
+      S.zr[a][r] = v;
+    }
+    warp_sync();
+    /* residual of xi rows: dd term + div xi delta_w - jump */
+    for (int i = lane; i < 12; i += 32) {
+      double v = 0.0;
+      for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.zr[a][r];
+      v *= g.iad;
+      for (int l = 0; l < 3; ++l) v += g.sdet * T.Dhat[i][l] * S.ul[sb_ldg(p, l)];
+      const int f = i / 3;
+      if (f < 3 && (pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
+        const int64_t cn = pl.cell_neighbors[c * 3 + f];
+        const double jump = st.base_w[(int64_t)k * pl.n_cells + cn]
+                          - st.base_w[(int64_t)k * pl.n_cells + c];
+        const double ref_out = (f == 1) ? -1.0 : 1.0;
+        v -= jump * ref_out * g.sdet * T.trI[i % 3];
+      }
+      S.bl[rlo + i] = v;
+    }
+    warp_sync();
+    add_natbc(pl, st, c, S, rlo, rhi, lane);
+    for (int e = lane; e < 144; e += 32) {
+      const int i = e / 12, m = e % 12;
+      double v = 0.0;
+      for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.Z[m][a][r];
+      sb_emit(cx, S, rlo + i, rlo + m, v * g.iad);
+    }
+    for (int e = lane; e < 36; e += 32) {
+      const int i = e / 3, l = e % 3;
+      double v = 0.0;
+      for (int a = 0; a < 2; ++a)
+        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.V[a][r][l];
+      v *= g.iad;
+      sb_emit(cx, S, rlo + i, sb_ldg(p, l), g.sdet * T.Dhat[i][l] + v);
+      sb_emit(cx, S, rlo + i, sb_ldg(0, l), v);
+    }
+  } else {
+    /* outside the band's subdomain: j.xi * c2 */
+    const double c2 = c_M.ext_j_coef * g.iad;
+    for (int i = lane; i < 12; i += 32) {
+      double v = 0.0;
+      for (int m = 0; m < 12; ++m) v += S.GM[i][m] * S.ul[rlo + m];
+      S.bl[rlo + i] = v * c2;
+    }
+    warp_sync();
+    add_natbc(pl, st, c, S, rlo, rhi, lane);
+    for (int e = lane; e < 144; e += 32) {
+      const int i = e / 12, m = e % 12;
+      sb_emit(cx, S, rlo + i, rlo + m, S.GM[i][m] * c2);
+    }
+  }
+  warp_sync();
+  write_rows(cx, S, rlo, rhi, lane);
+  warp_sync();
+  (void)nb;
+}
+
+/* ---- phase C, continuity rows v^k ------------------------------------------ */
+__device__ void phaseC_cont(const PlanDev& pl, const StateDev& st, TileSmem& sm,
+                            int64_t c, int ct, int k, int lane, SbWarpScratch& S,
+                            double* vals, double* b) {
+  const SbTables& T = *pl.tables;
+  const int p = 1 + k;
+  const int nb = pl.nb;
+  SbCellCtx cx;
+  load_cell(pl, st, c, cx, S, lane, vals, b);
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+  const int rlo = sb_ldg(p, 0), rhi = rlo + 3;
+  warp_sync();
+  if (inside) {
+    const double f = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+    for (int i = lane; i < 3; i += 32) {
+      double v = 0.0;
+      for (int m = 0; m < 12; ++m) v += T.Dhat[m][i] * S.ul[sb_lbdm(p, m)];
+      v *= g.sdet;
+      for (int t = 0; t < 3; ++t) v += f * T.G1[i][t] * sm.A[t][ct];
+      S.bl[rlo + i] = v;
+    }
+    warp_sync();
+    for (int e = lane; e < 36; e += 32) {
+      const int i = e / 12, m = e % 12;
+      sb_emit(cx, S, rlo + i, sb_lbdm(p, m), g.sdet * T.Dhat[m][i]);
+    }
+    for (int e = lane; e < 9 * (1 + nb); e += 32) {
+      const int q = e / 9, i = (e % 9) / 3, l = e % 3;   /* q = 0: phi, 1+m: delta_w_m */
+      double v = 0.0;
+      for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.A[3 + 6 * q + t][ct];
+      sb_emit(cx, S, rlo + i, sb_ldg(q, l), f * v);
+    }
+  } else {
+    const double c1 = c_M.ext_w_coef * g.adet;
+    for (int i = lane; i < 3; i += 32) {
+      double v = 0.0;
+      for (int l = 0; l < 3; ++l) v += T.M1[i][l] * S.ul[rlo + l];
+      S.bl[rlo + i] = c1 * v;
+    }
+    warp_sync();
+    for (int e = lane; e < 9; e += 32)
+      sb_emit(cx, S, rlo + e / 3, rlo + e % 3, c1 * T.M1[e / 3][e % 3]);
+  }
+  warp_sync();
+  write_rows(cx, S, rlo, rhi, lane);
+  warp_sync();
+}
+
+/* ---- phase C, Poisson rows ---------------------------------------------------- */
+__device__ void phaseC_poisson(const PlanDev& pl, const StateDev& st, TileSmem& sm,
+                               int64_t c, int ct, int lane, SbWarpScratch& S,
+                               double* vals, double* b) {
+  const SbTables& T = *pl.tables;
+  const int nbd = pl.nb_dof, nb = pl.nb;
+  SbCellCtx cx;
+  load_cell(pl, st, c, cx, S, lane, vals, b);
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  sb_prep_cell(T, g, S, lane, 32);
+  warp_sync();
+  /* residuals: w rows (0..2), psi rows (3..14) */
+  for (int i = lane; i < 15; i += 32) {
+    double v = 0.0;
+    if (i < 3) {
+      for (int m = 0; m < 12; ++m) v += T.Dhat[m][i] * S.ul[sb_lbdm(0, m)];
+      v *= g.sdet;
+      for (int t = 0; t < 3; ++t) v -= g.adet * T.G1[i][t] * sm.R[t][ct];
+    } else {
+      const int ii = i - 3;
+      for (int m = 0; m < 12; ++m) v += S.GM[ii][m] * S.ul[sb_lbdm(0, m)];
+      v *= g.iad;
+      for (int l = 0; l < 3; ++l) v -= g.sdet * T.Dhat[ii][l] * S.ul[l];
+    }
+    S.bl[i] = v;
+  }
+  warp_sync();
+  add_natbc(pl, st, c, S, 0, 15, lane);
+  for (int e = lane; e < 36; e += 32) {           /* (w, E) and (psi, phi) */
+    const int i = e / 12, m = e % 12;
+    sb_emit(cx, S, i, sb_lbdm(0, m), g.sdet * T.Dhat[m][i]);
+    sb_emit(cx, S, sb_lbdm(0, m), i, -g.sdet * T.Dhat[m][i]);
+  }
+  for (int e = lane; e < 144; e += 32)            /* (psi, E) */
+    sb_emit(cx, S, sb_lbdm(0, e / 12), sb_lbdm(0, e % 12), S.GM[e / 12][e % 12] * g.iad);
+  for (int e = lane; e < 9 * (1 + nbd); e += 32) { /* (w, phi), (w, delta_w_k) */
+    const int q = e / 9, i = (e % 9) / 3, l = e % 3;
+    double v = 0.0;
+    if (q == 0) {
+      for (int k = 0; k < nb; ++k)
+        for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.X[k][t][ct];
+    } else {
+      for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.X[q - 1][t][ct];
+    }
+    sb_emit(cx, S, i, sb_ldg(q, l), -g.adet * v);
+  }
+  warp_sync();
+  write_rows(cx, S, 0, 15, lane);
+  warp_sync();
+}
+
+/* ------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(SB_TILE)
+k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
+#ifdef SB_EMUL_BUILD
+  unsigned char* smem_raw = emul::dyn_smem();
+#else
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * SB_TILE;
+  const int64_t c = c0 + tid;
+  const bool valid = c < pl.n_cells;
+  const int nb = pl.nb, nbd = pl.nb_dof;
+  const int L = pl.L;
+  SbWarpScratch& S = sm.ws[warp];
+
+  /* per-thread cell data for the pointwise phases */
+  SbCellGeom g;
+  const double* tp = pl.tag_params;
+  double dgv[1 + SB_MAX_BANDS][3];
+  double w0[SB_MAX_BANDS];
+  const int32_t* dofs = nullptr;
+  if (valid) {
+    g = sb_geom(pl.cell_vertices + c * 6);
+    tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+    dofs = pl.cell_dofs + c * L;
+    for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
+    for (int k = 0; k < nb; ++k) {
+      w0[k] = 0.0;
+      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
+      if (nbd) {
+        w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
+        for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
+      }
+    }
+  }
+  const double beta = valid ? 1.0 / tp[SB_TP_KT] : 1.0;
+  const double inv_eps = valid ? 1.0 / tp[SB_TP_EPS] : 1.0;
+  double mR[SB_NR] = {0.0, 0.0, 0.0};
+  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
+
+  for (int k = 0; k < nb; ++k) {
+    if (valid) {
+      const double* bp = tp + SB_TP_BAND0 + 5 * k;
+      const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
+      const bool dd = inside && nbd;
+      const double N = bp[SB_TPB_N];
+      double gc[2][6];
+      if (dd) {
+        double jc[2][6];
+        for (int a = 0; a < 2; ++a) for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
+        for (int m = 0; m < 12; ++m) {
+          const double jm = st.u[dofs[sb_lbdm(1 + k, m)]];
+          for (int a = 0; a < 2; ++a)
+            for (int r = 0; r < 6; ++r) jc[a][r] += jm * c_T.bdmC[m][a][r];
+        }
+        for (int r = 0; r < 6; ++r) {
+          gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
+          gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
+        }
+      }
+      const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
+      const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
+      const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
+      double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
+      const int kind = c_M.band_kind[k];
+      const double s = (double)c_M.band_sign[k];
+      const int cm = c_M.band_const_mobility[k];
+      const bool rho = (N != 0.0);
+      for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+      if (same_rule) {
+        if (rho || dd)
+          sb_phaseA_band(c_T.sup, rho, dd, kind, s, cm, beta, bp[SB_TPB_E], N,
+                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                         gc, mC, Q, mR, mRx);
+      } else {
+        if (rho)
+          sb_phaseA_band(c_T.rho, true, false, kind, s, cm, beta, bp[SB_TPB_E], N,
+                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                         gc, mC, Q, mR, mRx);
+        if (dd)
+          sb_phaseA_band(c_T.sup, false, true, kind, s, cm, beta, bp[SB_TPB_E], N,
+                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                         gc, mC, Q, mR, mRx);
+      }
+      if (dd) {
+        for (int t = 0; t < SB_NMC; ++t) sm.A[t][tid] = mC[t];
+        for (int t = 0; t < SB_NQ; ++t) sm.A[SB_NMC + t][tid] = Q[t];
+      }
+      for (int t = 0; t < SB_NRX; ++t) sm.X[k][t][tid] = mRx[t];
+    }
+    __syncthreads();
+    if (nbd) {
+      for (int q = 0; q < 32; ++q) {
+        const int ct = warp * 32 + q;
+        const int64_t cc = c0 + ct;
+        if (cc >= pl.n_cells) break;
+        phaseC_band(pl, st, sm, cc, ct, k, lane, S, vals, b);
+      }
+    }
+    __syncthreads();
+  }
+
+  /* generation moments + continuity rows */
+  for (int k = 0; k < nbd; ++k) {
+    if (valid) {
+      const double* bp = tp + SB_TP_BAND0 + 5 * k;
+      if (bp[SB_TPB_IN_SUBDOMAIN] != 0.0) {
+        double mG[SB_NG];
+        sb_phaseB_band(c_T, c_M, tp, k, dgv, w0,
+                       st.thmeq ? st.thmeq + c * 6 : nullptr,
+                       st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
+        for (int t = 0; t < 9 + 6 * nb; ++t) sm.A[t][tid] = mG[t];
+      }
+    }
+    __syncthreads();
+    for (int q = 0; q < 32; ++q) {
+      const int ct = warp * 32 + q;
+      const int64_t cc = c0 + ct;
+      if (cc >= pl.n_cells) break;
+      phaseC_cont(pl, st, sm, cc, ct, k, lane, S, vals, b);
+    }
+    __syncthreads();
+  }
+
+  /* Poisson rows */
+  if (valid) {
+    /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
+    mR[0] += tp[SB_TP_RHO_STATIC] * inv_eps * 0.70710678118654752440;
+    for (int t = 0; t < SB_NR; ++t) sm.R[t][tid] = mR[t];
+  }
+  __syncthreads();
+  for (int q = 0; q < 32; ++q) {
+    const int ct = warp * 32 + q;
+    const int64_t cc = c0 + ct;
+    if (cc >= pl.n_cells) break;
+    phaseC_poisson(pl, st, sm, cc, ct, lane, S, vals, b);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+__global__ void k_colidx(PlanDev pl, int32_t* col) {
+  const int64_t c = blockIdx.x;
+  const int L = pl.L;
+  const int32_t* dofs = pl.cell_dofs + c * L;
+  for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+    const int i = e / L, j = e % L;
+    const int fi = sb_local_facet(i);
+    const uint8_t rk = (fi < 0) ? pl.rank_own[c * L + j] : pl.rank_fac[(c * 3 + fi) * L + j];
+    if (rk != 0xFF) col[pl.rowptr[dofs[i]] + rk] = dofs[j];
+  }
+}
+
+/* ---- a9 rebase --------------------------------------------------------------- */
+__global__ void k_rebase_mean(PlanDev pl, const double* u, const double* base_w, int band,
+                              double* tmp) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  const int32_t* dofs = pl.cell_dofs + c * pl.L + sb_ldg(1 + band, 0);
+  const double m = (u[dofs[0]] + u[dofs[1]] + u[dofs[2]]) / 3.0;
+  tmp[c] = base_w[(int64_t)band * pl.n_cells + c] + m;
+}
+__global__ void k_rebase_override(int64_t n, const int32_t* cells, const double* avg, double* tmp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tmp[cells[i]] = avg[i];
+}
+__global__ void k_rebase_apply(PlanDev pl, double* u, double* base_w, int band, const double* tmp) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  const int32_t* dofs = pl.cell_dofs + c * pl.L + sb_ldg(1 + band, 0);
+  double* bw = base_w + (int64_t)band * pl.n_cells + c;
+  const double shift = *bw - tmp[c];
+  for (int i = 0; i < 3; ++i) u[dofs[i]] += shift;
+  *bw = tmp[c];
+}
+
+/* ---- a11 Newton update + metrics -------------------------------------------- */
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+  /* non-negative doubles order like their bit patterns */
+  atomicMax(reinterpret_cast<unsigned long long*>(addr),
+            static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+
+__global__ void k_newton_update(int64_t N, double* u, const double* du, const double* b,
+                                const double* tol, double omega, double max_du,
+                                double rel_tol, double abs_tol, double* out) {
+  double bmax = 0, dmax = 0, rsum = 0, cmax = 0, nanf = 0, cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const double ui = u[i], di = du[i];
+    const double bi = b ? b[i] : 0.0;
+    if (isnan(ui) || isnan(bi)) nanf = 1.0;
+    const double ab = fabs(bi), ad = fabs(di);
+    if (ab > bmax || isnan(ab)) bmax = isnan(ab) ? bmax : ab;
+    if (ad > dmax) dmax = ad;
+    const double r = fabs(di / ui);
+    if (!isnan(r)) { rsum += r * r; cnt += 1.0; }
+    const double cc = ad / (fabs(ui) * rel_tol + abs_tol * (tol ? tol[i] : 1.0));
+    if (cc > cmax) cmax = cc;
+    if (isnan(cc) || isnan(ad)) nanf = fmax(nanf, isnan(ad) ? 2.0 : nanf);
+    double step = di;
+    if (max_du > 0.0) step = fmin(fmax(step, -max_du), max_du);
+    u[i] = ui - omega * step;
+  }
+  __shared__ double sh[6][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double v[6] = {bmax, dmax, rsum, cmax, nanf, cnt};
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int q = 0; q < 6; ++q) {
+      const double other = __shfl_down_sync(0xffffffffu, v[q], o);
+      v[q] = (q == 2 || q == 5) ? v[q] + other : fmax(v[q], other);
+    }
+  }
+  if (lane == 0) for (int q = 0; q < 6; ++q) sh[q][w] = v[q];
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < 6; ++q) v[q] = lane < nw ? sh[q][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1)
+      for (int q = 0; q < 6; ++q) {
+        const double other = __shfl_down_sync(0xffffffffu, v[q], o);
+        v[q] = (q == 2 || q == 5) ? v[q] + other : fmax(v[q], other);
+      }
+    if (lane == 0) {
+      atomic_max_pos(&out[0], v[0]);
+      atomic_max_pos(&out[1], v[1]);
+      atomicAdd(&out[2], v[2]);
+      atomic_max_pos(&out[3], v[3]);
+      atomic_max_pos(&out[4], v[4]);
+      atomicAdd(&out[5], v[5]);
+    }
+  }
+}
+
+/* ---- terminal current ----------------------------------------------------------- */
+__global__ void k_surface_flux(PlanDev pl, const double* u, int p, int64_t n,
+                               const int32_t* fcell, const int8_t* flocal,
+                               const double* fsign, double* out) {
+  __shared__ double sh[2][256];
+  double flux = 0.0, len = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t c = fcell[i];
+    const int f = flocal[i];
+    const int32_t* dofs = pl.cell_dofs + c * pl.L + sb_lbdm(p, 3 * f);
+    const double* xv = pl.cell_vertices + c * 6;
+    const SbCellGeom g = sb_geom(xv);
+    const double ref_out = (f == 1) ? -1.0 : 1.0;
+    const double t = c_T.trI[0] * u[dofs[0]] + c_T.trI[1] * u[dofs[1]] + c_T.trI[2] * u[dofs[2]];
+    flux += t * ref_out * g.sdet * fsign[i];
+    /* edge opposite vertex f */
+    const int a = (f == 0) ? 1 : 0, bb = (f == 2) ? 1 : 2;
+    const double dx = xv[2 * bb] - xv[2 * a], dy = xv[2 * bb + 1] - xv[2 * a + 1];
+    len += sqrt(dx * dx + dy * dy);
+  }
+  sh[0][threadIdx.x] = flux; sh[1][threadIdx.x] = len;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0][0]; out[1] = sh[1][0]; }
+}
+
+__global__ void k_fill(double* p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+/* ========================================================================= */
+/* host side of the C ABI                                                     */
+/* ========================================================================= */
+template <typename T>
+static int upload(sb_plan* pl, const T* h, size_t n, const T** d) {
+  *d = nullptr;
+  if (n == 0) { n = 1; }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T),
+             cudaGetErrorString(e));
+    return SB_ERR_ALLOC;
+  }
+  pl->allocs.push_back(p);
+  if (h) {
+    e = cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof g_err, "cudaMemcpy H2D failed: %s", cudaGetErrorString(e));
+      return SB_ERR_CUDA;
+    }
+  }
+  *d = static_cast<const T*>(p);
+  return SB_OK;
+}
+
+extern "C" const char* sb_last_error(void) { return g_err; }
+extern "C" int sb_version(void) { return 100; }
+extern "C" int64_t sb_launch_count(void) { return g_launches.load(); }
+extern "C" int64_t sb_tables_size(void) { return (int64_t)sizeof(SbTables); }
+extern "C" int64_t sb_plan_nnz(const sb_plan* p) { return p ? p->d.nnz : -1; }
+
+extern "C" void sb_plan_destroy(sb_plan* pl) {
+  if (!pl) return;
+  for (void* p : pl->allocs) cudaFree(p);
+  if (g_tables_owner == pl) g_tables_owner = nullptr;
+  delete pl;
+}
+
+extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_plan** out) {
+  if (!model || !pr || !out) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
+  const int nbd = model->bands_have_dofs ? model->n_bands : 0;
+  if (pr->P != 1 + nbd || model->n_bands > SB_MAX_BANDS || model->n_procs > SB_MAX_PROCS ||
+      model->n_fields > SB_MAX_FIELDS) {
+    snprintf(g_err, sizeof g_err, "inconsistent model/problem (P=%d, n_bands=%d)", pr->P,
+             model->n_bands);
+    return SB_ERR_ARG;
+  }
+  if (pr->n_tables != (int64_t)(sizeof(SbTables) / sizeof(double)) &&
+      pr->n_tables * 8 != (int64_t)sizeof(SbTables)) {
+    snprintf(g_err, sizeof g_err, "table blob has %lld doubles, expected %zu bytes",
+             (long long)pr->n_tables, sizeof(SbTables));
+    return SB_ERR_ARG;
+  }
+  sb_plan* pl = new sb_plan();
+  pl->model = *model;
+  memcpy(&pl->tables, pr->h_tables, sizeof(SbTables));
+  const int L = 15 * pr->P;
+  const int64_t nc = pr->n_cells, N = pr->n_dofs;
+  PlanDev& d = pl->d;
+  d.n_cells = nc; d.N = N; d.P = pr->P; d.L = L;
+  d.nb = model->n_bands; d.nb_dof = nbd;
+  d.nnz = pr->h_rowptr[N];
+  int rc = SB_OK;
+#define UP(field, src, n) if (rc == SB_OK) rc = upload(pl, src, (size_t)(n), &d.field)
+  UP(cell_vertices, pr->h_cell_vertices, nc * 6);
+  UP(cell_tag, pr->h_cell_tag, nc);
+  UP(cell_dofs, pr->h_cell_dofs, nc * L);
+  UP(cell_neighbors, pr->h_cell_neighbors, nc * 3);
+  UP(cell_jump_mask, pr->h_cell_jump_mask, nc * 3);
+  UP(rowptr, pr->h_rowptr, N + 1);
+  UP(rank_own, pr->h_rank_own, nc * L);
+  UP(rank_fac, pr->h_rank_fac, nc * 3 * L);
+  UP(tag_params, pr->h_tag_params, (size_t)model->n_tags * SB_TAG_STRIDE);
+  UP(tables, &pl->tables, 1);
+  /* special cells: Dirichlet dofs and natural-BC rows */
+  std::vector<int32_t> special(nc, -1);
+  std::vector<uint64_t> mlo; std::vector<uint32_t> mhi; std::vector<int32_t> bcidx;
+  std::vector<int32_t> natbeg;
+  {
+    std::vector<uint8_t> isbc;
+    if (pr->n_bc) {
+      isbc.assign((size_t)N, 0);
+      for (int64_t i = 0; i < pr->n_bc; ++i) {
+        const int32_t dof = pr->h_bc_dofs[i];
+        if (dof < 0 || dof >= N || (i && pr->h_bc_dofs[i - 1] >= dof)) {
+          snprintf(g_err, sizeof g_err, "bc dofs must be sorted, unique and in range");
+          sb_plan_destroy(pl); return SB_ERR_ARG;
+        }
+        isbc[dof] = 1;
+      }
+    }
+    std::vector<uint8_t> hasnat(nc, 0);
+    for (int64_t i = 0; i < pr->n_natbc; ++i) {
+      const int32_t c = pr->h_natbc_cell[i];
+      if (c < 0 || c >= nc || (i && pr->h_natbc_cell[i - 1] > c) ||
+          pr->h_natbc_row[i] < 0 || pr->h_natbc_row[i] >= L) {
+        snprintf(g_err, sizeof g_err, "natbc entries must be sorted by cell and in range");
+        sb_plan_destroy(pl); return SB_ERR_ARG;
+      }
+      hasnat[c] = 1;
+    }
+    int64_t natpos = 0;
+    int32_t ns = 0;
+    for (int64_t c = 0; c < nc; ++c) {
+      uint64_t lo = 0; uint32_t hi = 0;
+      if (pr->n_bc)
+        for (int l = 0; l < L; ++l)
+          if (isbc[pr->h_cell_dofs[c * L + l]]) {
+            if (l < 64) lo |= (1ull << l); else hi |= (1u << (l - 64));
+          }
+      if (!(lo | hi) && !hasnat[c]) continue;
+      special[c] = ns++;
+      mlo.push_back(lo); mhi.push_back(hi);
+      for (int l = 0; l < L; ++l) {
+        int32_t idx = -1;
+        const bool on = l < 64 ? ((lo >> l) & 1ull) : ((hi >> (l - 64)) & 1u);
+        if (on) {
+          const int32_t* bd = pr->h_bc_dofs;
+          idx = (int32_t)(std::lower_bound(bd, bd + pr->n_bc, pr->h_cell_dofs[c * L + l]) - bd);
+        }
+        bcidx.push_back(idx);
+      }
+      while (natpos < pr->n_natbc && pr->h_natbc_cell[natpos] < c) ++natpos;
+      natbeg.push_back((int32_t)natpos);
+      while (natpos < pr->n_natbc && pr->h_natbc_cell[natpos] == c) ++natpos;
+    }
+    natbeg.push_back((int32_t)natpos);
+    pl->n_special = ns;
+  }
+  pl->n_bc = pr->n_bc; pl->n_natbc = pr->n_natbc;
+  UP(cell_special, special.data(), nc);
+  UP(sp_mask_lo, mlo.data(), mlo.size());
+  UP(sp_mask_hi, mhi.data(), mhi.size());
+  UP(sp_bcidx, bcidx.data(), bcidx.size());
+  UP(sp_nat_begin, natbeg.data(), natbeg.size());
+  UP(natbc_row, pr->h_natbc_row, pr->n_natbc);
+  const double* tmp = nullptr;
+  if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc, &tmp);
+  pl->tmp_cells = const_cast<double*>(tmp);
+#undef UP
+  if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }
+  cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(TileSmem));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    sb_plan_destroy(pl); return SB_ERR_CUDA;
+  }
+  *out = pl;
+  return SB_OK;
+}
+
+static int bind_tables(sb_plan* pl, cudaStream_t s) {
+  if (g_tables_owner == pl) return SB_OK;
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_T, &pl->tables, sizeof(SbTables), 0,
+                                   cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_M, &pl->model, sizeof(sb_model), 0,
+                                   cudaMemcpyHostToDevice, s));
+  g_tables_owner = pl;
+  return SB_OK;
+}
+
+extern "C" int sb_plan_zero_values(sb_plan* pl, double* d_vals, void* stream) {
+  if (!pl || !d_vals) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
+  CUDA_TRY(cudaMemsetAsync(d_vals, 0, (size_t)pl->d.nnz * sizeof(double), (cudaStream_t)stream));
+  return SB_OK;
+}
+
+extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, double* d_b,
+                           void* stream) {
+  if (!pl || !st || !st->d_u) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
+  if (pl->d.nb_dof && !st->d_base_w) {
+    snprintf(g_err, sizeof g_err, "base_w required when bands have dofs"); return SB_ERR_ARG;
+  }
+  if (pl->model.n_fields && !st->d_phi_opt) {
+    snprintf(g_err, sizeof g_err, "phi_opt required when n_fields > 0"); return SB_ERR_ARG;
+  }
+  if ((pl->n_bc && !st->d_bc_values) || (pl->n_natbc && !st->d_natbc_values)) {
+    snprintf(g_err, sizeof g_err, "bc_values / natbc_values required"); return SB_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = bind_tables(pl, s);
+  if (rc != SB_OK) return rc;
+  StateDev sd{st->d_u, st->d_base_w, st->d_thmeq_phi, st->d_phi_opt, st->d_bc_values,
+              st->d_natbc_values};
+  const int64_t nc = pl->d.n_cells;
+  SB_LAUNCH(k_zero_shared, (unsigned)((nc + 255) / 256), 256, 0, s, pl->d, d_vals, d_b);
+  SB_LAUNCH(k_assemble, (unsigned)((nc + SB_TILE - 1) / SB_TILE), SB_TILE, sizeof(TileSmem), s, pl->d, sd, d_vals, d_b);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_plan_column_indices(sb_plan* pl, int32_t* d_colidx, void* stream) {
+  if (!pl || !d_colidx) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
+  SB_LAUNCH(k_colidx, (unsigned)pl->d.n_cells, 256, 0, (cudaStream_t)stream, pl->d, d_colidx);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_rebase_w(sb_plan* pl, double* d_u, double* d_base_w, int32_t band,
+                           int64_t n_bc_cells, const int32_t* d_bc_cells,
+                           const double* d_bc_avg, void* stream) {
+  if (!pl || !d_u || !d_base_w || band < 0 || band >= pl->d.nb_dof) {
+    snprintf(g_err, sizeof g_err, "bad argument to sb_rebase_w"); return SB_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned nblk = (unsigned)((pl->d.n_cells + 255) / 256);
+  SB_LAUNCH(k_rebase_mean, nblk, 256, 0, s, pl->d, d_u, d_base_w, band, pl->tmp_cells);
+  if (n_bc_cells > 0)
+    SB_LAUNCH(k_rebase_override, (unsigned)((n_bc_cells + 255) / 256), 256, 0, s, n_bc_cells, d_bc_cells, d_bc_avg, pl->tmp_cells);
+  SB_LAUNCH(k_rebase_apply, nblk, 256, 0, s, pl->d, d_u, d_base_w, band, pl->tmp_cells);
+  g_launches += (n_bc_cells > 0) ? 3 : 2;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_newton_update(sb_plan* pl, double* d_u, const double* d_du, const double* d_b,
+                                const double* d_tol, double omega, double max_du,
+                                double rel_tol, double abs_tol, double* d_out, void* stream) {
+  if (!pl || !d_u || !d_du || !d_out) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, 6 * sizeof(double), s));
+  const int64_t N = pl->d.N;
+  unsigned nblk = (unsigned)std::min<int64_t>((N + 255) / 256, 148 * 8);
+  SB_LAUNCH(k_newton_update, nblk, 256, 0, s, N, d_u, d_du, d_b, d_tol, omega, max_du, rel_tol,
+                                       abs_tol, d_out);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_surface_flux(sb_plan* pl, const double* d_u, int32_t p, int64_t n_facets,
+                               const int32_t* d_facet_cell, const int8_t* d_facet_local,
+                               const double* d_facet_sign, double* d_out, void* stream) {
+  if (!pl || !d_u || !d_out || p < 0 || p >= pl->d.P) {
+    snprintf(g_err, sizeof g_err, "bad argument to sb_surface_flux"); return SB_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = bind_tables(pl, s);
+  if (rc != SB_OK) return rc;
+  SB_LAUNCH(k_surface_flux, 1, 256, 0, s, pl->d, d_u, p, n_facets, d_facet_cell, d_facet_local,
+                                   d_facet_sign, d_out);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
