@@ -198,6 +198,12 @@ int sb_surface_flux(sb_plan* plan, const double* d_u, int32_t p,
                     const int8_t* d_facet_local, const double* d_facet_sign,
                     double* d_out, void* stream);
 
+/* ---- measurement ------------------------------------------------------------------
+ * CUDA-event timing (on the launching stream) of the dominant kernel of the last
+ * sb_assemble call; sb_plan_last_kernel_ms synchronises on that event.            */
+int sb_plan_set_profiling(sb_plan* plan, int on);
+int sb_plan_last_kernel_ms(sb_plan* plan, double* ms);
+
 /* layout of the packed reference tables expected in sb_problem.h_tables */
 int64_t sb_tables_size(void);
 

@@ -56,8 +56,12 @@ static dual ddiv(dual a, dual b) {
 }
 static dual dexp(dual a) { double e = exp(a.v); for (int i = 0; i < ND; ++i) a.d[i] *= e; a.v = e; return a; }
 /* d/dx expm1 = exp  (simudo/fem/ufl_extra.py:32-61) */
-static dual dexpm1(dual a) { double e = exp(a.v); double m = expm1(a.v);
-  for (int i = 0; i < ND; ++i) a.d[i] *= e; a.v = m; return a; }
+static dual dexpm1(dual a) {
+  const double e = exp(a.v), m = expm1(a.v);
+  for (int i = 0; i < ND; ++i) a.d[i] *= e;
+  a.v = m;
+  return a;
+}
 static dual dpow(dual a, double p) {
   dual r; r.v = pow(a.v, p); double f = p * pow(a.v, p - 1.0);
   for (int i = 0; i < ND; ++i) r.d[i] = f * a.d[i];
@@ -245,7 +249,6 @@ static void cell_tensor(const oracle_problem* Q, int64_t c, double* A, double* b
   for (int i = 0; i < L; ++i) ul[i] = Q->u[Q->cell_dofs[c * L + i]];
   memset(A, 0, sizeof(double) * L * L);
   memset(b, 0, sizeof(double) * L);
-  const double kT = tp[SB_TP_KT];
   double w0[SB_MAX_BANDS] = {0, 0, 0, 0};
   if (Q->base_w && dofbands)
     for (int k = 0; k < nb; ++k) w0[k] = Q->base_w[(int64_t)k * Q->n_cells + c];
@@ -348,6 +351,7 @@ static void cell_tensor(const oracle_problem* Q, int64_t c, double* A, double* b
       const double* l = R->p1 + q * 3;
       double bx[12], by[12], bd[12];
       for (int i = 0; i < 12; ++i) PHYS_BDM(R, q, i, bx[i], by[i], bd[i]);
+      (void)bd;
       dual phi = dc(0.0); phi.d[0] = 1.0;
       for (int i = 0; i < 3; ++i) phi.v += ul[i] * l[i];
       for (int k = 0; k < nb; ++k) {

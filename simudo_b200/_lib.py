@@ -20,7 +20,8 @@ _EMULATED = False
 EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
             'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update',
-            'sb_surface_flux', 'sb_tables_size']
+            'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
+            'sb_plan_last_kernel_ms']
 
 
 class SbProblem(C.Structure):
@@ -67,6 +68,10 @@ def _declare(lib):
     lib.sb_newton_update.restype = C.c_int
     lib.sb_surface_flux.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp]
     lib.sb_surface_flux.restype = C.c_int
+    lib.sb_plan_set_profiling.argtypes = [vp, C.c_int]
+    lib.sb_plan_set_profiling.restype = C.c_int
+    lib.sb_plan_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sb_plan_last_kernel_ms.restype = C.c_int
     return lib
 
 

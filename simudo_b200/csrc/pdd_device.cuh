@@ -352,6 +352,8 @@ struct SbWarpScratch {
   double ul[SB_MAXL];    /* local dofs                              */
   double bl[SB_MAXL];    /* local residual                          */
   double gl[SB_MAXL];    /* Dirichlet lift values u_i - bc_i        */
+  double lift[15][9];    /* -A_ij g_j per (row of the phase, constrained facet dof j):
+                            summed in fixed order => bit-reproducible   */
 };
 
 /* everything a cell needs for scatter */
@@ -364,6 +366,7 @@ struct SbCellCtx {
   const int64_t* rowptr;
   uint64_t bcmask_lo;        /* constrained local dofs, bits 0..63    */
   uint32_t bcmask_hi;        /* bits 64..74                           */
+  int row0;                  /* first local row of the current phase  */
   double* vals;              /* may be NULL                           */
   double* b;                 /* may be NULL                           */
 };
@@ -385,7 +388,8 @@ SB_HD void sb_emit(const SbCellCtx& cx, SbWarpScratch& S, int i, int j, double v
     if (sb_is_bc(cx, i)) {
       val = (i == j) ? 1.0 : 0.0;
     } else if (sb_is_bc(cx, j)) {
-      SB_ATOMIC_ADD(&S.bl[i], -val * S.gl[j]);
+      /* constrained dofs are BDM facet dofs: slot = facet-dof number 0..8 */
+      S.lift[i - cx.row0][(j % 15) - 3] = -val * S.gl[j];
       val = 0.0;
     }
   }

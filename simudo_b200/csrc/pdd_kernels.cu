@@ -74,6 +74,10 @@ struct sb_plan {
   std::vector<void*> allocs;
   int64_t n_bc, n_natbc, n_special;
   double* tmp_cells;             /* [n_cells] scratch for rebase             */
+#ifndef SB_EMUL_BUILD
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   /* around k_assemble when profiling */
+#endif
+  int profiling = 0;
 };
 
 struct StateDev {
@@ -125,9 +129,9 @@ __device__ __forceinline__ void warp_sync() { __syncwarp(); }
 /* load local dofs + Dirichlet lift values of one cell into warp scratch */
 __device__ __forceinline__ void load_cell(const PlanDev& pl, const StateDev& st, int64_t c,
                                           SbCellCtx& cx, SbWarpScratch& S, int lane,
-                                          double* vals, double* b) {
+                                          double* vals, double* b, int row0) {
   const int L = pl.L;
-  cx.c = c; cx.L = L;
+  cx.c = c; cx.L = L; cx.row0 = row0;
   cx.dofs = pl.cell_dofs + c * L;
   cx.rank_own = pl.rank_own + c * L;
   cx.rank_fac = pl.rank_fac + c * 3 * L;
@@ -147,6 +151,8 @@ __device__ __forceinline__ void load_cell(const PlanDev& pl, const StateDev& st,
     S.gl[l] = g;
     S.bl[l] = 0.0;
   }
+  if (sp >= 0)
+    for (int e = lane; e < 15 * 9; e += 32) S.lift[e / 9][e % 9] = 0.0;
 }
 
 /* add natural-BC values of rows in [lo, hi) of this cell to the local residual */
@@ -155,18 +161,25 @@ __device__ __forceinline__ void add_natbc(const PlanDev& pl, const StateDev& st,
   const int32_t sp = pl.cell_special[c];
   if (sp < 0) return;
   const int32_t b0 = pl.sp_nat_begin[sp], b1 = pl.sp_nat_begin[sp + 1];
-  for (int32_t k = b0 + lane; k < b1; k += 32) {
-    const int row = pl.natbc_row[k];
-    if (row >= lo && row < hi) atomicAdd(&S.bl[row], st.natbc_values[k]);
-  }
+  if (lane == 0)                       /* few entries; fixed order */
+    for (int32_t k = b0; k < b1; ++k) {
+      const int row = pl.natbc_row[k];
+      if (row >= lo && row < hi) S.bl[row] += st.natbc_values[k];
+    }
+  warp_sync();
 }
 
 /* final write of residual rows [lo, hi) */
 __device__ __forceinline__ void write_rows(const SbCellCtx& cx, SbWarpScratch& S,
                                            int lo, int hi, int lane) {
   if (!cx.b) return;
+  const bool special = (cx.bcmask_lo | cx.bcmask_hi) != 0;
   for (int l = lo + lane; l < hi; l += 32) {
-    const double v = sb_is_bc(cx, l) ? S.gl[l] : S.bl[l];
+    double v = S.bl[l];
+    if (special) {
+      if (sb_is_bc(cx, l)) v = S.gl[l];
+      else for (int q = 0; q < 9; ++q) v += S.lift[l - cx.row0][q];
+    }
     double* dst = cx.b + cx.dofs[l];
     if (sb_local_facet(l) >= 0) atomicAdd(dst, v); else *dst = v;
   }
@@ -180,7 +193,7 @@ __device__ void phaseC_band(const PlanDev& pl, const StateDev& st, TileSmem& sm,
   const int p = 1 + k;
   const int nb = pl.nb;
   SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b);
+  load_cell(pl, st, c, cx, S, lane, vals, b, sb_lbdm(1 + k, 0));
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
   const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
@@ -278,7 +291,7 @@ __device__ void phaseC_cont(const PlanDev& pl, const StateDev& st, TileSmem& sm,
   const int p = 1 + k;
   const int nb = pl.nb;
   SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b);
+  load_cell(pl, st, c, cx, S, lane, vals, b, sb_ldg(1 + k, 0));
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
   const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
@@ -327,7 +340,7 @@ __device__ void phaseC_poisson(const PlanDev& pl, const StateDev& st, TileSmem& 
   const SbTables& T = *pl.tables;
   const int nbd = pl.nb_dof, nb = pl.nb;
   SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b);
+  load_cell(pl, st, c, cx, S, lane, vals, b, 0);
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   sb_prep_cell(T, g, S, lane, 32);
   warp_sync();
@@ -678,6 +691,9 @@ extern "C" int64_t sb_plan_nnz(const sb_plan* p) { return p ? p->d.nnz : -1; }
 extern "C" void sb_plan_destroy(sb_plan* pl) {
   if (!pl) return;
   for (void* p : pl->allocs) cudaFree(p);
+#ifndef SB_EMUL_BUILD
+  if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+#endif
   if (g_tables_owner == pl) g_tables_owner = nullptr;
   delete pl;
 }
@@ -830,9 +846,40 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
               st->d_natbc_values};
   const int64_t nc = pl->d.n_cells;
   SB_LAUNCH(k_zero_shared, (unsigned)((nc + 255) / 256), 256, 0, s, pl->d, d_vals, d_b);
+#ifndef SB_EMUL_BUILD
+  if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
+#endif
   SB_LAUNCH(k_assemble, (unsigned)((nc + SB_TILE - 1) / SB_TILE), SB_TILE, sizeof(TileSmem), s, pl->d, sd, d_vals, d_b);
+#ifndef SB_EMUL_BUILD
+  if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
+#endif
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
+/* CUDA-event timing of the dominant kernel (k_assemble) of the last sb_assemble */
+extern "C" int sb_plan_set_profiling(sb_plan* pl, int on) {
+  if (!pl) return SB_ERR_ARG;
+#ifndef SB_EMUL_BUILD
+  if (on && !pl->ev0) {
+    CUDA_TRY(cudaEventCreate(&pl->ev0));
+    CUDA_TRY(cudaEventCreate(&pl->ev1));
+  }
+#endif
+  pl->profiling = on;
+  return SB_OK;
+}
+extern "C" int sb_plan_last_kernel_ms(sb_plan* pl, double* ms) {
+  if (!pl || !ms) return SB_ERR_ARG;
+  *ms = 0.0;
+#ifndef SB_EMUL_BUILD
+  if (!pl->profiling || !pl->ev1) { snprintf(g_err, sizeof g_err, "profiling is off"); return SB_ERR_ARG; }
+  CUDA_TRY(cudaEventSynchronize(pl->ev1));
+  float f = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&f, pl->ev0, pl->ev1));
+  *ms = f;
+#endif
   return SB_OK;
 }
 

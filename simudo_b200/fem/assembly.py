@@ -148,5 +148,13 @@ class AssemblyPlan(object):
             _p(facet_local), _p(facet_sign), _p(out), self._stream(stream)))
         return out
 
+    def set_profiling(self, on=True):
+        _lib.check(self.lib.sb_plan_set_profiling(self._h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        ms = C.c_double(0.0)
+        _lib.check(self.lib.sb_plan_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def launch_count(self):
         return int(self.lib.sb_launch_count())

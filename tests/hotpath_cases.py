@@ -1,0 +1,219 @@
+"""Parity cases shared by the CPU-emulated run (tests/test_emulated_kernels.py)
+and the real B200 run (tests/test_gpu_parity.py).  Every case drives the
+product through its C ABI (AssemblyPlan -> libsimudo_b200) and checks it
+against the oracle on the same seeded inputs.
+
+Tolerances: the north star asks for 1e-12 relative on assembled entries;
+"relative" is taken per CSR row (max-norm of the oracle's row) because single
+entries of a row span > 20 decades.
+"""
+import numpy as np
+import torch
+
+from oracle import oracle as orc_mod
+from oracle.oracle import Oracle
+from simudo_b200 import synthetic as syn
+from simudo_b200.fem import model as M
+from simudo_b200.fem.assembly import AssemblyPlan
+from simudo_b200.fem.problem_arrays import ProblemArrays
+from simudo_b200.mesh import Product2DMesh
+
+from parity_util import row_scaled_error, vector_error, run_plan
+
+A_TOL = 1e-12
+B_TOL = 1e-12
+
+
+def _oracle(pa, st):
+    return Oracle(pa).assemble(st['u'], st['base_w'], st['thmeq_phi'], st['phi_opt'],
+                               st['bc_values'], st['natbc_values'])
+
+
+def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
+    pa = maker(nx=nx, ny=ny, numbering=numbering, with_bcs=with_bcs, **kw)
+    st = syn.synthetic_state(pa)
+    vals0, b0 = _oracle(pa, st)
+    plan = AssemblyPlan(pa)
+    vals, b = run_plan(plan, st)
+    vals, b = vals.cpu().numpy(), b.cpu().numpy()
+    assert np.isfinite(vals).all() and np.isfinite(b).all()
+    ea, eb = row_scaled_error(pa, vals, vals0), vector_error(b, b0)
+    assert ea < A_TOL, 'Jacobian row-scaled error %.3e' % ea
+    assert eb < B_TOL, 'residual error %.3e' % eb
+    # bit-exact sparsity: device-built column indices == host CSR structure
+    col = plan.column_indices().cpu().numpy()
+    assert (col == pa.csr.column_indices()).all()
+    # structural zeros of the dolfin pattern stay exactly zero
+    assert (vals[vals0 == 0.0] == 0.0).mean() > 0.99
+    return pa, st, plan, vals, b, vals0, b0
+
+
+def thermal_equilibrium_mode():
+    """goal 'thermal equilibrium': bands feed rho with qfl == 0, no band dofs
+    (poisson_drift_diffusion.py:221-223)."""
+    pa_full = syn.pn_problem(nx=7, ny=3, with_bcs=False)
+    model = M.make_model([dict(kind=0, sign=-1), dict(kind=0, sign=+1)], [],
+                         n_tags=2, bands_have_dofs=False)
+    pa = ProblemArrays(pa_full.mesh, pa_full.cell_tag, model, pa_full.tag_params)
+    bf = pa.mesh.boundary_facets()
+    pa.set_bc_dofs(pa.facet_dofs(0, bf[::2]).ravel())
+    st = syn.synthetic_state(pa)
+    st['base_w'] = None
+    st['bc_values'] = 0.01 * np.cos(np.arange(len(pa.bc_dofs)))
+    st['natbc_values'] = np.zeros(0)
+    vals0, b0 = Oracle(pa).assemble(st['u'], None, None, None, st['bc_values'])
+    plan = AssemblyPlan(pa)
+    vals, b = run_plan(plan, st)
+    assert row_scaled_error(pa, vals.cpu().numpy(), vals0) < A_TOL
+    assert vector_error(b.cpu().numpy(), b0) < B_TOL
+
+
+def fill_dependent_ib_mobility():
+    pa, st, plan, vals, b, vals0, b0 = assembly_parity(
+        syn.ib_problem, 6, 3, const_mobility=False)
+
+
+def non_default_quadrature_degrees():
+    """mixedqfl_debug_quad_degree_* are user-settable
+    (example/pn_benchmark/pn_benchmark.py:209-222)."""
+    pa0 = syn.pn_problem(nx=6, ny=3)
+    model = M.make_model([dict(kind=0, sign=-1), dict(kind=0, sign=+1)],
+                         [dict(kind=M.PROC_SRH, dst=0, src=1)], n_tags=2,
+                         quad_degree_rho=12, quad_degree_super=16, quad_degree_g=10)
+    pa = ProblemArrays(pa0.mesh, pa0.cell_tag, model, pa0.tag_params,
+                       jump_facet_mask=np.full(pa0.mesh.num_facets, 3, np.uint8))
+    st = syn.synthetic_state(pa)
+    st['bc_values'] = np.zeros(0)
+    st['natbc_values'] = np.zeros(0)
+    vals0, b0 = _oracle(pa, st)
+    vals, b = run_plan(AssemblyPlan(pa), st)
+    assert row_scaled_error(pa, vals.cpu().numpy(), vals0) < A_TOL
+    assert vector_error(b.cpu().numpy(), b0) < B_TOL
+
+
+def assembly_is_deterministic_and_idempotent():
+    pa = syn.ib_problem(nx=8, ny=4)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    v1, b1 = run_plan(plan, st)
+    T = plan.tensor
+    args = (T(st['u']), T(st['base_w']), T(st['thmeq_phi']), T(st['phi_opt']),
+            T(st['bc_values']), T(plan.natbc_device_order(st['natbc_values'])))
+    v2, b2 = v1.clone(), b1.clone()
+    plan.assemble(*args, v2, b2)          # re-assemble into the used buffers
+    assert torch.equal(v1, v2) and torch.equal(b1, b2)
+    v3, b3 = run_plan(AssemblyPlan(pa), st)
+    assert torch.equal(v1, v3) and torch.equal(b1, b3)
+
+
+def residual_only_and_matrix_only():
+    pa = syn.pn_problem(nx=6, ny=3)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    vals, b = run_plan(plan, st)
+    T = plan.tensor
+    args = (T(st['u']), T(st['base_w']), T(st['thmeq_phi']), None,
+            T(st['bc_values']), T(plan.natbc_device_order(st['natbc_values'])))
+    b_only = plan.new_vector()
+    plan.assemble(*args, None, b_only)
+    v_only = plan.new_values()
+    plan.assemble(*args, v_only, None)
+    assert torch.equal(b, b_only) and torch.equal(vals, v_only)
+
+
+def rebase_w_parity():
+    pa = syn.ib_problem(nx=7, ny=3)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    T = plan.tensor
+    u, bw = T(st['u']).clone(), T(st['base_w']).clone()
+    u_ref, bw_ref = st['u'].copy(), st['base_w'].copy()
+    bc_cells = np.array([0, 3, 7], dtype=np.int32)
+    bc_avg = np.array([0.11, -0.2, 0.05])
+    lay = pa.layout()
+    tot_before = u_ref[pa.cell_dofs[:, lay['dg'][2]]] + bw_ref[1][:, None]
+    for band in range(3):
+        u_ref, bw_ref = orc_mod.rebase_w(pa, u_ref, bw_ref, band, bc_cells, bc_avg)
+        plan.rebase_w(u, bw, band, T(bc_cells, torch.int32), T(bc_avg))
+    assert np.abs(u.cpu().numpy() - u_ref).max() < 1e-15
+    assert np.abs(bw.cpu().numpy() - bw_ref).max() < 1e-15
+    # size-independent property: base_w + delta_w is invariant under rebasing
+    tot_after = u.cpu().numpy()[pa.cell_dofs[:, lay['dg'][2]]] + bw.cpu().numpy()[1][:, None]
+    assert np.abs(tot_after - tot_before).max() < 1e-14
+    assert np.abs(bw.cpu().numpy()[:, bc_cells] - bc_avg[None, :]).max() == 0.0
+
+
+def newton_update_parity():
+    pa = syn.pn_problem(nx=9, ny=4)
+    plan = AssemblyPlan(pa)
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal(pa.N)
+    u[::17] = 0.0                                  # |du/u| = inf / nan cases
+    du = rng.standard_normal(pa.N) * 1e-3
+    du[::34] = 0.0
+    b = rng.standard_normal(pa.N)
+    tol = pa.tolerance_vector([1e-6] * pa.P, [1e-4] + [1e-10] * (pa.P - 1))
+    ref = orc_mod.newton_metrics(u, du, b, tol, 1e-4, 1.0)
+    T = plan.tensor
+    ud = T(u).clone()
+    out = plan.newton_update(ud, T(du), T(b), T(tol), 0.5, 2e-3, 1e-4, 1.0).cpu().numpy()
+    assert out[0] == ref['b_norm'] and out[1] == ref['du_norm']
+    assert np.sqrt(out[2]) == np.float64(ref['rel_du_norm']) or \
+        abs(np.sqrt(out[2]) - ref['rel_du_norm']) < 1e-10 * ref['rel_du_norm'] or \
+        not np.isfinite(ref['rel_du_norm'])
+    assert abs(out[3] - ref['combined_du_norm']) <= 1e-15 * ref['combined_du_norm']
+    assert out[4] == 0.0
+    expect = u - 0.5 * np.clip(du, -2e-3, 2e-3)
+    assert np.abs(ud.cpu().numpy() - expect).max() == 0.0
+    # NaN poisoning is detected, not raised (newton_solver.py:84-89)
+    u2 = u.copy(); u2[5] = np.nan
+    out = plan.newton_update(T(u2), T(du), T(b), T(tol), 1.0, None, 1e-4, 1.0).cpu().numpy()
+    assert out[4] > 0.0
+
+
+def surface_flux_parity():
+    pa = syn.pn_problem(nx=6, ny=5)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    T = plan.tensor
+    mesh = pa.mesh
+    for name in ('left', 'right'):
+        facets = pa.contacts[name]
+        for p in range(pa.P):
+            ref_flux, ref_len = orc_mod.surface_flux(pa, st['u'], p, facets)
+            out = plan.surface_flux(
+                T(st['u']), p, T(mesh.facet_cells[facets, 0], torch.int32),
+                T(mesh.facet_local[facets, 0], torch.int8),
+                T(np.ones(len(facets)))).cpu().numpy()
+            assert abs(out[0] - ref_flux) <= 1e-13 * max(abs(ref_flux), 1e-300)
+            assert abs(out[1] - ref_len) <= 1e-14 * ref_len
+
+
+def jacobian_consistent_with_residual_large(maker, nx, ny):
+    """Size-independent property for meshes the oracle cannot afford:
+    J v == d/dh F(u + h v) (central differences) through the product alone."""
+    pa = maker(nx=nx, ny=ny, with_bcs=False)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    T = plan.tensor
+    lay = pa.layout()
+    scale = np.ones(pa.N)
+    for p in range(pa.P):
+        scale[pa.cell_dofs[:, lay['dg'][p]].ravel()] = 1e-3
+        scale[np.unique(pa.cell_dofs[:, lay['bdm'][p]])] = 1e-3 if p == 0 else 1e-12
+    v = np.random.default_rng(2).standard_normal(pa.N) * scale
+    fixed = (T(st['base_w']), T(st['thmeq_phi']), T(st['phi_opt']), None, None)
+    vals, b0 = plan.new_values(), plan.new_vector()
+    plan.assemble(T(st['u']), *fixed, vals, b0)
+    h = 1e-4
+    bp, bm = plan.new_vector(), plan.new_vector()
+    plan.assemble(T(st['u'] + h * v), *fixed, None, bp)
+    plan.assemble(T(st['u'] - h * v), *fixed, None, bm)
+    col = plan.column_indices()
+    rowptr = T(pa.csr.rowptr, torch.int64)
+    A = torch.sparse_csr_tensor(rowptr, col.to(torch.int64), vals, size=(pa.N, pa.N))
+    an = (A @ T(v).unsqueeze(1)).squeeze(1)
+    fd = (bp - bm) / (2 * h)
+    err = (fd - an).abs().max().item() / an.abs().max().item()
+    assert err < 1e-6, err
+    return pa.n_cells

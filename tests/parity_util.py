@@ -1,0 +1,49 @@
+"""Shared comparison helpers for the parity tests."""
+import numpy as np
+
+
+def row_scaled_error(pa, vals, vals_ref):
+    """max |a - a_ref| / max_row |a_ref| over all CSR entries."""
+    rp = pa.csr.rowptr
+    rowmax = np.maximum.reduceat(np.abs(vals_ref), rp[:-1])
+    rowid = np.repeat(np.arange(pa.N), np.diff(rp))
+    return float((np.abs(vals - vals_ref) / np.maximum(rowmax[rowid], 1e-300)).max())
+
+
+def vector_error(b, b_ref):
+    return float(np.abs(b - b_ref).max() / max(np.abs(b_ref).max(), 1e-300))
+
+
+def block_scaled_error(pa, vals, vals_ref):
+    """Entry error relative to the max of its (row sub-problem, col sub-problem)
+    block class -- stricter than row scaling for small couplings."""
+    L = pa.L
+    pos = pa.csr.entry_positions()
+    worst = 0.0
+    for pi in range(pa.P):
+        for pj in range(pa.P):
+            sl = pos[:, 15 * pi:15 * pi + 15, 15 * pj:15 * pj + 15].ravel()
+            ref = vals_ref[sl]
+            scale = np.abs(ref).max()
+            if scale == 0.0:
+                worst = max(worst, float(np.abs(vals[sl]).max()))
+                continue
+            # entries of one cell block vary over decades: scale per cell
+            refc = np.abs(vals_ref[pos[:, 15 * pi:15 * pi + 15, 15 * pj:15 * pj + 15]]).reshape(pos.shape[0], -1).max(axis=1)
+            d = np.abs(vals[pos[:, 15 * pi:15 * pi + 15, 15 * pj:15 * pj + 15]]
+                       - vals_ref[pos[:, 15 * pi:15 * pi + 15, 15 * pj:15 * pj + 15]]).reshape(pos.shape[0], -1).max(axis=1)
+            ok = refc > 0
+            if ok.any():
+                worst = max(worst, float((d[ok] / refc[ok]).max()))
+    return worst
+
+
+def run_plan(plan, st):
+    T = plan.tensor
+    vals = plan.new_values()
+    b = plan.new_vector()
+    nat = st.get('natbc_values')
+    plan.assemble(T(st['u']), T(st['base_w']), T(st['thmeq_phi']), T(st['phi_opt']),
+                  T(st['bc_values']) if plan.n_bc else None,
+                  T(plan.natbc_device_order(nat)) if plan.n_natbc else None, vals, b)
+    return vals, b

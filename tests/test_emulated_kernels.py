@@ -1,0 +1,54 @@
+"""Kernel *source* exercised on the CPU through tests/emul's CUDA shim.
+
+This is not the product path (the product only loads the nvcc-built library
+and demands a CUDA device); it gives the GPU-less container line coverage of
+csrc/pdd_kernels.cu + pdd_device.cuh against the oracle.  The real parity
+gate is tests/test_gpu_parity.py on the B200.
+"""
+import pytest
+
+import hotpath_cases as hc
+from simudo_b200 import synthetic as syn
+
+
+@pytest.mark.parametrize('maker,nx,ny,numbering,bcs', [
+    (syn.pn_problem, 5, 3, 'b200', True),
+    (syn.pn_problem, 4, 2, 'ufc', True),
+    (syn.ib_problem, 6, 3, 'b200', True),
+    (syn.ib_problem, 5, 2, 'ufc', False),
+    (syn.pn_problem, 34, 3, 'b200', True),      # > 1 CTA tile, ragged last tile
+])
+def test_assembly_parity_emulated(emulated_lib, maker, nx, ny, numbering, bcs):
+    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs)
+
+
+def test_thermal_equilibrium_mode_emulated(emulated_lib):
+    hc.thermal_equilibrium_mode()
+
+
+def test_fill_dependent_ib_mobility_emulated(emulated_lib):
+    hc.fill_dependent_ib_mobility()
+
+
+def test_non_default_quadrature_emulated(emulated_lib):
+    hc.non_default_quadrature_degrees()
+
+
+def test_deterministic_emulated(emulated_lib):
+    hc.assembly_is_deterministic_and_idempotent()
+
+
+def test_residual_only_emulated(emulated_lib):
+    hc.residual_only_and_matrix_only()
+
+
+def test_rebase_emulated(emulated_lib):
+    hc.rebase_w_parity()
+
+
+def test_newton_update_emulated(emulated_lib):
+    hc.newton_update_parity()
+
+
+def test_surface_flux_emulated(emulated_lib):
+    hc.surface_flux_parity()

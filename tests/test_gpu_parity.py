@@ -1,0 +1,83 @@
+"""Parity tests proper: the CUDA path on a B200, through the C ABI, against the
+oracle (bit-exact pattern / indices, 1e-12 row-relative values)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', autouse=True)
+def real_library():
+    from simudo_b200 import _lib
+    _lib._reset_for_tests()
+    lib = _lib.get()                       # raises if the .so is missing
+    assert not _lib.is_emulated()
+    yield lib
+
+
+import hotpath_cases as hc          # noqa: E402
+from simudo_b200 import synthetic as syn   # noqa: E402
+
+
+@pytest.mark.parametrize('maker,nx,ny,numbering,bcs', [
+    (syn.pn_problem, 5, 3, 'b200', True),
+    (syn.pn_problem, 4, 2, 'ufc', True),
+    (syn.pn_problem, 67, 2, 'b200', True),      # config-1 size (132 cells)
+    (syn.ib_problem, 6, 3, 'b200', True),
+    (syn.ib_problem, 5, 2, 'ufc', False),
+    (syn.ib_problem, 279, 2, 'b200', True),     # config-2 size (556 cells)
+    (syn.pn_problem, 40, 33, 'b200', True),     # 2 496 cells, many tiles
+    (syn.ib_problem, 30, 21, 'b200', True),
+])
+def test_assembly_parity(maker, nx, ny, numbering, bcs):
+    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs)
+
+
+def test_thermal_equilibrium_mode():
+    hc.thermal_equilibrium_mode()
+
+
+def test_fill_dependent_ib_mobility():
+    hc.fill_dependent_ib_mobility()
+
+
+def test_non_default_quadrature():
+    hc.non_default_quadrature_degrees()
+
+
+def test_deterministic():
+    hc.assembly_is_deterministic_and_idempotent()
+
+
+def test_residual_only():
+    hc.residual_only_and_matrix_only()
+
+
+def test_rebase():
+    hc.rebase_w_parity()
+
+
+def test_newton_update():
+    hc.newton_update_parity()
+
+
+def test_surface_flux():
+    hc.surface_flux_parity()
+
+
+@pytest.mark.parametrize('maker,nx,ny', [
+    (syn.pn_problem, 224, 224),          # BASELINE config 3: ~100 k cells
+    (syn.ib_problem, 160, 160),
+])
+def test_jacobian_consistent_with_residual_at_scale(maker, nx, ny):
+    n = hc.jacobian_consistent_with_residual_large(maker, nx, ny)
+    assert n > 40000
+
+
+def test_no_cpu_fallback():
+    """The product must refuse to run without CUDA tensors."""
+    import torch
+    from simudo_b200.fem.assembly import AssemblyPlan
+    pa = syn.pn_problem(nx=4, ny=2)
+    with pytest.raises(RuntimeError):
+        AssemblyPlan(pa, device='cpu')

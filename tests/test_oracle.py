@@ -1,0 +1,138 @@
+"""The oracle checked against itself and against closed forms (CPU)."""
+import numpy as np
+import pytest
+
+from oracle import fiat_like as fl
+from oracle.oracle import Oracle
+from simudo_b200 import synthetic as syn
+from simudo_b200.fem import reference_element as re
+
+
+def test_gauss_jacobi_exactness():
+    for m in (5, 11):
+        x, w = fl.gauss_jacobi(m, 1.0, 0.0)
+        for k in range(2 * m):
+            # int_-1^1 (1-x) x^k dx
+            exact = (1 - (-1) ** (k + 1)) / (k + 1) - (1 - (-1) ** (k + 2)) / (k + 2)
+            assert np.dot(w, x ** k) == pytest.approx(exact, abs=1e-13)
+
+
+def test_collapsed_rule_integrates_degree_20():
+    pts, w = fl.collapsed_triangle_rule(11)
+    assert len(w) == 121 and w.sum() == pytest.approx(0.5, abs=1e-14)
+    from math import factorial
+    for a in range(0, 21, 5):
+        for b in range(0, 21 - a, 4):
+            exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+            assert np.dot(w, pts[:, 0] ** a * pts[:, 1] ** b) == pytest.approx(exact, rel=1e-12)
+
+
+def test_two_independent_element_derivations_agree():
+    """sympy-exact FIAT-style tables (oracle) vs Dubiner-based tables (product)."""
+    for m in (5, 11):
+        p1, w1 = fl.collapsed_triangle_rule(m)
+        p2, w2 = re.collapsed_rule(m)
+        assert np.abs(p1 - p2).max() < 1e-15 and np.abs(w1 - w2).max() < 1e-16
+    pts, _ = fl.collapsed_triangle_rule(11)
+    v1, d1 = fl.tabulate_bdm2(pts)
+    v2, d2 = re.bdm2_eval(pts)
+    assert np.abs(v1 - v2.transpose(1, 0, 2)).max() < 1e-12
+    assert np.abs(d1 - d2.T).max() < 1e-12
+    assert np.abs(fl.tabulate_p2(pts) - re.p2_lagrange_eval(pts).T).max() < 1e-15
+
+
+def test_bdm2_dual_basis_definition():
+    """Nodal property against FIAT's dual set (Appendix A3)."""
+    import sympy as sp
+    (X, Y), basis = fl.bdm2_symbolic()
+    # first basis function in closed form (exact rationals)
+    assert sp.expand(basis[0][0] - (7 * X ** 2 + 2 * X * Y - 4 * X)) == 0
+    assert sp.expand(basis[0][1] - (-2 * X * Y + Y ** 2)) == 0
+    _, _, trace, _, _ = fl.facet_tabulation(3)
+    # normal traces of interior functions vanish on every edge
+    assert np.abs(trace[:, :, 9:]).max() < 1e-14
+    # facet functions have zero normal trace on the other edges
+    for f in range(3):
+        others = [i for i in range(9) if i // 3 != f]
+        assert np.abs(trace[f][:, others]).max() < 1e-14
+
+
+@pytest.mark.parametrize('maker', [syn.pn_problem, syn.ib_problem])
+def test_oracle_jacobian_matches_finite_differences(maker):
+    pa = maker(nx=5, ny=3, with_bcs=False)
+    st = syn.synthetic_state(pa)
+    orc = Oracle(pa)
+    args = (st['base_w'], st['thmeq_phi'], st['phi_opt'])
+    vals, _ = orc.assemble(st['u'], *args)
+    A = orc.to_scipy(vals)
+    lay = pa.layout()
+    scale = np.ones(pa.N)
+    for p in range(pa.P):
+        scale[pa.cell_dofs[:, lay['dg'][p]].ravel()] = 1e-3
+        scale[np.unique(pa.cell_dofs[:, lay['bdm'][p]])] = 1e-3 if p == 0 else 1e-12
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal(pa.N) * scale
+    h = 1e-4
+    _, bp = orc.assemble(st['u'] + h * v, *args, want_A=False)
+    _, bm = orc.assemble(st['u'] - h * v, *args, want_A=False)
+    fd = (bp - bm) / (2 * h)
+    an = A @ v
+    assert np.abs(fd - an).max() <= 1e-6 * np.abs(an).max()
+
+
+def test_oracle_thermal_equilibrium_has_zero_generation_and_current_residual():
+    """g == 0 and the drift-diffusion rows vanish when qfl == 0, j == 0 and
+    phi equals the thermal-equilibrium potential."""
+    pa = syn.pn_problem(nx=6, ny=3, with_bcs=False)
+    st = syn.synthetic_state(pa)
+    lay = pa.layout()
+    u = st['u'].copy()
+    for p in (1, 2):
+        u[pa.cell_dofs[:, lay['dg'][p]].ravel()] = 0.0
+        u[np.unique(pa.cell_dofs[:, lay['bdm'][p]])] = 0.0
+    # thermal-equilibrium potential = the (P1) potential itself, as P2 nodal values
+    phi_v = u[pa.cell_dofs[:, lay['dg'][0]]]
+    mid = 0.5 * (phi_v[:, [1, 0, 0]] + phi_v[:, [2, 2, 1]])
+    thmeq = np.concatenate([phi_v, mid], axis=1)
+    orc = Oracle(pa)
+    _, b = orc.assemble(u, np.zeros_like(st['base_w']), thmeq, None, want_A=False)
+    for p in (1, 2):
+        rows = np.concatenate([pa.cell_dofs[:, lay['dg'][p]].ravel(),
+                               np.unique(pa.cell_dofs[:, lay['bdm'][p]])])
+        # generation term exactly zero (n p = n0 p0), no current
+        assert np.abs(b[rows]).max() < 1e-9 * np.abs(b).max()
+
+
+def test_oracle_manufactured_mixed_poisson_converges():
+    """Mixed Poisson alone (no carriers): -div(eps grad phi) = rho with
+    phi = 0 on the contacts has the exact parabola phi = rho x (L - x) / (2 eps)."""
+    import scipy.sparse.linalg as spla
+    from simudo_b200.fem import model as M
+    from simudo_b200.fem.problem_arrays import ProblemArrays
+    from simudo_b200.mesh import Product2DMesh
+    errs = []
+    for nx in (5, 9):
+        mesh = Product2DMesh(np.linspace(0, 1, nx), np.linspace(0, 0.5, 3)).mesh
+        model = M.make_model([], [], n_tags=1, bands_have_dofs=False)
+        tp = M.new_tag_params(1)
+        tp[0, M.TP_KT] = 0.025
+        tp[0, M.TP_EPS] = 2.0
+        tp[0, M.TP_RHO_STATIC] = 3.0
+        pa = ProblemArrays(mesh, np.zeros(mesh.num_cells, np.int32), model, tp)
+        bf = mesh.boundary_facets()
+        n = mesh.boundary_outward_normals(bf)
+        horiz = bf[np.abs(n[:, 1]) > 0.5]
+        pa.set_bc_dofs(pa.facet_dofs(0, horiz).ravel())      # E.n = 0 top/bottom
+        orc = Oracle(pa)
+        u = np.zeros(pa.N)
+        vals, b = orc.assemble(u, bc_values=np.zeros(len(pa.bc_dofs)))
+        du = spla.spsolve(orc.to_scipy(vals).tocsc(), b)
+        u -= du                                                # linear: one Newton step
+        lay = pa.layout()
+        phi = u[pa.cell_dofs[:, lay['dg'][0]]]
+        x = pa.cell_vertices[:, :, 0]
+        exact = 3.0 * x * (1 - x) / (2 * 2.0)
+        errs.append(np.abs(phi - exact).max())
+        _, b2 = orc.assemble(u, bc_values=np.zeros(len(pa.bc_dofs)), want_A=False)
+        assert np.abs(b2).max() < 1e-10
+    assert errs[1] < errs[0] / 3.0          # at least second-order in h
