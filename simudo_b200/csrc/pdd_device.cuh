@@ -14,13 +14,14 @@
  *            sum factorisation (5 + 8 + 5 FMAs per point instead of ~400).
  *   phase B  (one thread per cell, per band): the 25-point rule for the
  *            generation term g and its partial derivatives, same idea.
- *   phase C  (one warp per cell): moments x constant expansion tensors x cell
- *            geometry -> structurally non-zero entries of the element tensor,
- *            Dirichlet application, and scatter into the fixed CSR.
+ *   phase C  (same thread): moments x constant expansion tensors (warp-uniform
+ *            constant-bank operands) x cell geometry -> structurally non-zero
+ *            entries of the element tensor, Dirichlet application, scatter
+ *            into the fixed CSR.  No shared memory, no barriers: 32 cells of a
+ *            warp progress in lock-step, so every table operand is uniform.
  *
- * Everything is written as lane-strided loops so the very same source runs
- * under tests/host_emulation (lane = 0, nlanes = 1) for CPU-side debugging of
- * the kernel logic; that harness is test infrastructure only.
+ * The same source also compiles for the CPU under tests/emul (CUDA shim) for
+ * debugging of the kernel logic; that harness is test infrastructure only.
  */
 #ifndef SB_PDD_DEVICE_CUH
 #define SB_PDD_DEVICE_CUH
@@ -339,40 +340,30 @@ SB_HD void sb_phaseB_band(const SbTables& T, const sb_model& M, const double* tp
 }
 
 /* ------------------------------------------------------------------------- *
- * phase C: per-cell (warp) scratch and scatter
+ * phase C: scatter context of one cell (one thread)
  * ------------------------------------------------------------------------- */
-struct SbWarpScratch {
-  double W[21];
-  double GC[12][2][6];   /* sum_b G_ab C[m][b][s]                   */
-  double Z[12][2][6];    /* sum_s W_rs GC[m][a][s]                  */
-  double V[2][6][3];     /* sum_t G21[r][l][t] Q_a[t]               */
-  double zr[2][6];       /* sum_s W_rs gc[a][s]                     */
-  double gc[2][6];       /* Dubiner-P2 coefficients of G jhat       */
-  double GM[12][12];     /* sum_ab G_ab Mhat[i][j][ab] (iad applied later) */
-  double ul[SB_MAXL];    /* local dofs                              */
-  double bl[SB_MAXL];    /* local residual                          */
-  double gl[SB_MAXL];    /* Dirichlet lift values u_i - bc_i        */
-  double lift[15][9];    /* -A_ij g_j per (row of the phase, constrained facet dof j):
-                            summed in fixed order => bit-reproducible   */
-};
-
-/* everything a cell needs for scatter */
-struct SbCellCtx {
-  int64_t c;
+struct SbIO {
   int L;
-  const int32_t* dofs;       /* [L] global dofs of this cell          */
-  const uint8_t* rank_own;   /* [L]                                   */
-  const uint8_t* rank_fac;   /* [3][L]                                */
+  const int32_t* dofs;       /* [L] global dofs of this cell                */
+  const uint8_t* rank_own;   /* [L]                                         */
+  const uint8_t* rank_fac;   /* [3][L]                                      */
   const int64_t* rowptr;
-  uint64_t bcmask_lo;        /* constrained local dofs, bits 0..63    */
-  uint32_t bcmask_hi;        /* bits 64..74                           */
-  int row0;                  /* first local row of the current phase  */
-  double* vals;              /* may be NULL                           */
-  double* b;                 /* may be NULL                           */
+  const double* u;
+  const double* bc_values;
+  const int32_t* bcidx;      /* [L] index into bc_values | -1 (special cells) */
+  uint64_t mlo;              /* constrained local dofs, bits 0..63          */
+  uint32_t mhi;              /* bits 64..74                                 */
+  double* vals;              /* may be NULL                                 */
+  double* b;                 /* may be NULL                                 */
 };
 
-SB_HD bool sb_is_bc(const SbCellCtx& cx, int l) {
-  return l < 64 ? ((cx.bcmask_lo >> l) & 1ull) : ((cx.bcmask_hi >> (l - 64)) & 1u);
+SB_HD bool sb_is_bc(const SbIO& io, int l) {
+  return l < 64 ? ((io.mlo >> l) & 1ull) : ((io.mhi >> (l - 64)) & 1u);
+}
+SB_HD bool sb_special(const SbIO& io) { return (io.mlo | io.mhi) != 0; }
+/* Dirichlet lift value u_j - bc_j of a constrained local dof */
+SB_HD double sb_lift_value(const SbIO& io, int j) {
+  return io.u[io.dofs[j]] - io.bc_values[io.bcidx[j]];
 }
 
 #if defined(__CUDA_ARCH__) || defined(SB_EMUL_BUILD)
@@ -381,57 +372,164 @@ SB_HD bool sb_is_bc(const SbCellCtx& cx, int l) {
 #define SB_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
-/* write one structurally non-zero Jacobian entry (local i, j) = val with the
- * element-wise symmetric Dirichlet rule.               */
-SB_HD void sb_emit(const SbCellCtx& cx, SbWarpScratch& S, int i, int j, double val) {
-  if (cx.bcmask_lo | cx.bcmask_hi) {
-    if (sb_is_bc(cx, i)) {
+/* Write one structurally non-zero Jacobian entry (local i, j) = val with the
+ * element-wise symmetric Dirichlet rule; Fi is the
+ * residual accumulator of row i (receives the x0 lifting, in program order,
+ * hence bit-reproducible).                                                   */
+SB_HD void sb_emit(const SbIO& io, int i, int j, double val, double& Fi) {
+  if (sb_special(io)) {
+    if (sb_is_bc(io, i)) {
       val = (i == j) ? 1.0 : 0.0;
-    } else if (sb_is_bc(cx, j)) {
-      /* constrained dofs are BDM facet dofs: slot = facet-dof number 0..8 */
-      S.lift[i - cx.row0][(j % 15) - 3] = -val * S.gl[j];
+    } else if (sb_is_bc(io, j)) {
+      Fi -= val * sb_lift_value(io, j);
       val = 0.0;
     }
   }
-  if (!cx.vals) return;
+  if (!io.vals) return;
   const int fi = sb_local_facet(i);
-  const int rk = (fi < 0) ? cx.rank_own[j] : cx.rank_fac[fi * cx.L + j];
+  const int rk = (fi < 0) ? io.rank_own[j] : io.rank_fac[fi * io.L + j];
   if (rk == 0xFF) return;                 /* not in a compacted pattern */
-  double* dst = cx.vals + cx.rowptr[cx.dofs[i]] + rk;
+  double* dst = io.vals + io.rowptr[io.dofs[i]] + rk;
   /* two cells add into the same slot only for (facet dof, facet dof) pairs of
      one facet; two addends onto a zeroed slot commute -> deterministic       */
   if (fi >= 0 && sb_local_facet(j) == fi) SB_ATOMIC_ADD(dst, val);
   else *dst = val;
 }
 
-/* per-cell, band-independent prep: GC, GM, local dofs */
-SB_HD void sb_prep_cell(const SbTables& T, const SbCellGeom& g, SbWarpScratch& S,
-                        int lane, int nl) {
-  for (int e = lane; e < 144; e += nl) {
-    const int m = e / 12, rem = e % 12, a = rem / 6, s = rem % 6;
-    const double Ga0 = a == 0 ? g.G11 : g.G12, Ga1 = a == 0 ? g.G12 : g.G22;
-    S.GC[m][a][s] = Ga0 * T.bdmC[m][0][s] + Ga1 * T.bdmC[m][1][s];
-  }
-  for (int e = lane; e < 144; e += nl) {
-    const int i = e / 12, j = e % 12;
-    S.GM[i][j] = g.G11 * T.Mhat[i][j][0] + g.G12 * T.Mhat[i][j][1] + g.G22 * T.Mhat[i][j][2];
+/* final residual value of local row i */
+SB_HD void sb_put_row(const SbIO& io, int i, double F) {
+  if (!io.b) return;
+  if (sb_special(io) && sb_is_bc(io, i)) F = sb_lift_value(io, i);
+  double* dst = io.b + io.dofs[i];
+  if (sb_local_facet(i) >= 0) SB_ATOMIC_ADD(dst, F); else *dst = F;
+}
+
+SB_HD int sb_pair(int i, int m) {       /* packed index of (i <= m) in 12 x 12 */
+  return i * 12 - (i * (i - 1)) / 2 + (m - i);
+}
+
+/* natural-BC values of this cell for rows [lo, lo+n): F[row-lo] += value */
+SB_HD void sb_add_natbc(const int32_t* nat_row, const double* nat_val, int b0, int b1,
+                        int lo, int n, double* F) {
+  for (int k = b0; k < b1; ++k) {
+    const int r = nat_row[k] - lo;
+    if (r >= 0 && r < n) F[r] += nat_val[k];
   }
 }
 
-/* gc[a][r] = sum_m j_m GC[m][a][r] for flux dofs jl[12]  (needs GC) */
-SB_HD void sb_flux_coeffs(const SbWarpScratch& S, const double* jl, double (*gc)[6],
-                          int lane, int nl) {
-  for (int e = lane; e < 12; e += nl) {
-    const int a = e / 6, r = e % 6;
-    double v = 0.0;
-    for (int m = 0; m < 12; ++m) v += jl[m] * S.GC[m][a][r];
-    gc[a][r] = v;
+/* ---- rows xi^k (BDM test functions of band k) ------------------------------- */
+SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
+                        const SbCellGeom& g, int p, bool is_band, bool inside,
+                        const double* mC, const double* Q,
+                        const double* fl /*[12] flux dofs*/, const double* sl /*[3] scalar dofs*/,
+                        const double* jumpf /*[3] or NULL*/,
+                        const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
+  const int r0 = sb_lbdm(p, 0);
+  double F[12];
+  for (int i = 0; i < 12; ++i) F[i] = 0.0;
+  if (is_band && inside) {
+    /* <xi_i . xi_m c>: symmetric, 78 pairs x 45 FMAs on warp-uniform constants */
+    int pair = 0;
+    for (int i = 0; i < 12; ++i)
+      for (int m = i; m < 12; ++m, ++pair) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) {
+          a0 += mC[t] * T.TB[pair][0][t];
+          a1 += mC[t] * T.TB[pair][1][t];
+          a2 += mC[t] * T.TB[pair][2][t];
+        }
+        const double v = (g.G11 * a0 + g.G12 * a1 + g.G22 * a2) * g.iad;
+        F[i] += v * fl[m];
+        sb_emit(io, r0 + i, r0 + m, v, F[i]);
+        if (m != i) {
+          F[m] += v * fl[i];
+          sb_emit(io, r0 + m, r0 + i, v, F[m]);
+        }
+      }
+    /* <div xi_i delta_w> + <xi_i . j dc/dchi lam_l> */
+    for (int i = 0; i < 12; ++i) {
+      for (int l = 0; l < 3; ++l) {
+        double d = 0.0;
+#pragma unroll
+        for (int t = 0; t < 10; ++t)
+          d += T.TD[i][l][0][t] * Q[t] + T.TD[i][l][1][t] * Q[10 + t];
+        d *= g.iad;
+        const double dv = g.sdet * T.Dhat[i][l];
+        F[i] += dv * sl[l];
+        sb_emit(io, r0 + i, sb_ldg(p, l), dv + d, F[i]);
+        sb_emit(io, r0 + i, sb_ldg(0, l), d, F[i]);
+      }
+      if (jumpf) F[i] -= jumpf[i / 3] * T.trI[i % 3];
+    }
+  } else {
+    /* polynomial mass block: Poisson <psi.E> (scale 1) or the out-of-subdomain
+       penalty <j.xi> c2 (poisson_drift_diffusion1.py1:288-289)               */
+    const double sc = (is_band ? M.ext_j_coef : 1.0) * g.iad;
+    for (int i = 0; i < 12; ++i)
+      for (int m = i; m < 12; ++m) {
+        const double v = sc * (g.G11 * T.Mhat[i][m][0] + g.G12 * T.Mhat[i][m][1]
+                               + g.G22 * T.Mhat[i][m][2]);
+        F[i] += v * fl[m];
+        sb_emit(io, r0 + i, r0 + m, v, F[i]);
+        if (m != i) {
+          F[m] += v * fl[i];
+          sb_emit(io, r0 + m, r0 + i, v, F[m]);
+        }
+      }
+    if (!is_band) {
+      /* - <div psi_i phi> */
+      for (int i = 0; i < 12; ++i)
+        for (int l = 0; l < 3; ++l) {
+          const double dv = -g.sdet * T.Dhat[i][l];
+          F[i] += dv * sl[l];
+          sb_emit(io, r0 + i, sb_ldg(0, l), dv, F[i]);
+        }
+    }
   }
+  if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 12, F);
+  for (int i = 0; i < 12; ++i) sb_put_row(io, r0 + i, F[i]);
 }
 
-SB_HD int sb_sym21(int r, int s) {      /* packed index of (r<=s) in 6x6 */
-  if (r > s) { const int t = r; r = s; s = t; }
-  return r * 6 - (r * (r - 1)) / 2 + (s - r);
+/* ---- rows of the DG1 test functions: w (Poisson, p = 0) or v^k (p = 1 + k) ---- *
+ * coef: multiplies the moment terms (-adet for rho, -s e adet for g)
+ * mom1[3]: P1 moments of the source (rho/eps | g_k)
+ * momJ[q][6]: P2 moments of d source / d (phi | delta_w_q-1), q < nq          */
+SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
+                          const SbCellGeom& g, int p, bool inside,
+                          const double* fl /*[12] flux dofs of p*/, const double* sl /*[3]*/,
+                          double coef, const double* mom1, const double* momJ, int nq,
+                          const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
+  const int r0 = sb_ldg(p, 0);
+  double F[3] = {0.0, 0.0, 0.0};
+  if (inside) {
+    for (int i = 0; i < 3; ++i) {
+      for (int m = 0; m < 12; ++m) {            /* <v_i div j> */
+        const double dv = g.sdet * T.Dhat[m][i];
+        F[i] += dv * fl[m];
+        sb_emit(io, r0 + i, sb_lbdm(p, m), dv, F[i]);
+      }
+      for (int t = 0; t < 3; ++t) F[i] += coef * T.G1[i][t] * mom1[t];
+      for (int q = 0; q < nq; ++q)
+        for (int l = 0; l < 3; ++l) {
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
+          sb_emit(io, r0 + i, sb_ldg(q, l), coef * v, F[i]);
+        }
+    }
+  } else {
+    /* out-of-subdomain penalty <delta_w v> c1 (:285-286) */
+    const double c1 = M.ext_w_coef * g.adet;
+    for (int i = 0; i < 3; ++i)
+      for (int l = 0; l < 3; ++l) {
+        const double v = c1 * T.M1[i][l];
+        F[i] += v * sl[l];
+        sb_emit(io, r0 + i, r0 + l, v, F[i]);
+      }
+  }
+  if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 3, F);
+  for (int i = 0; i < 3; ++i) sb_put_row(io, r0 + i, F[i]);
 }
 
 #endif /* SB_PDD_DEVICE_CUH */

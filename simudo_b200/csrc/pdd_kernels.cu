@@ -1,10 +1,9 @@
 /*
  * pdd_kernels.cu -- sm_100a kernels + C ABI (include/simudo_b200.h).
  *
- * k_assemble: one CTA = SB_TILE cells.  Thread-per-cell phases A/B write
- * coefficient moments into a shared-memory tile; warp-per-cell phase C turns
- * them into element-tensor entries and scatters them into the fixed CSR
- * (see pdd_device.cuh for the math and the reference citations).
+ * k_assemble: one thread = one cell; coefficient moments in registers,
+ * expansion tensors as warp-uniform constant-bank operands, direct scatter
+ * into the fixed CSR (see pdd_device.cuh for the math and the citations).
  * No tensor cores: the path is FP64 gather / pointwise transcendental /
  * scatter (BASELINE.json north_star).
  */
@@ -25,9 +24,7 @@
 
 #include "pdd_device.cuh"
 
-#define SB_TILE 128
-#define SB_TS (SB_TILE + 1)        /* padded tile stride (bank-conflict free) */
-#define SB_WARPS (SB_TILE / 32)
+#define SB_TILE 128                /* threads (= cells) per CTA */
 
 __constant__ SbTables c_T;
 __constant__ sb_model c_M;
@@ -115,413 +112,141 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
 }
 
 /* ------------------------------------------------------------------------- */
-struct TileSmem {
-  /* moment tiles, [moment][cell] with padded stride */
-  double A[SB_NMC + SB_NQ][SB_TS];          /* current band: mC, Q; aliased by G */
-  double X[SB_MAX_BANDS][SB_NRX][SB_TS];    /* d(s u/eps)/dchi per band         */
-  double R[SB_NR][SB_TS];                   /* rho/eps                          */
-  SbWarpScratch ws[SB_WARPS];
-};
-static_assert(SB_NG <= SB_NMC + SB_NQ, "g-moment tile must fit in the A tile");
-
-__device__ __forceinline__ void warp_sync() { __syncwarp(); }
-
-/* load local dofs + Dirichlet lift values of one cell into warp scratch */
-__device__ __forceinline__ void load_cell(const PlanDev& pl, const StateDev& st, int64_t c,
-                                          SbCellCtx& cx, SbWarpScratch& S, int lane,
-                                          double* vals, double* b, int row0) {
-  const int L = pl.L;
-  cx.c = c; cx.L = L; cx.row0 = row0;
-  cx.dofs = pl.cell_dofs + c * L;
-  cx.rank_own = pl.rank_own + c * L;
-  cx.rank_fac = pl.rank_fac + c * 3 * L;
-  cx.rowptr = pl.rowptr;
-  cx.vals = vals; cx.b = b;
-  const int32_t sp = pl.cell_special[c];
-  cx.bcmask_lo = 0; cx.bcmask_hi = 0;
-  if (sp >= 0) { cx.bcmask_lo = pl.sp_mask_lo[sp]; cx.bcmask_hi = pl.sp_mask_hi[sp]; }
-  for (int l = lane; l < L; l += 32) {
-    const double ul = st.u[cx.dofs[l]];
-    S.ul[l] = ul;
-    double g = 0.0;
-    if (sp >= 0) {
-      const int32_t bi = pl.sp_bcidx[(int64_t)sp * L + l];
-      if (bi >= 0) g = ul - st.bc_values[bi];
-    }
-    S.gl[l] = g;
-    S.bl[l] = 0.0;
-  }
-  if (sp >= 0)
-    for (int e = lane; e < 15 * 9; e += 32) S.lift[e / 9][e % 9] = 0.0;
-}
-
-/* add natural-BC values of rows in [lo, hi) of this cell to the local residual */
-__device__ __forceinline__ void add_natbc(const PlanDev& pl, const StateDev& st, int64_t c,
-                                          SbWarpScratch& S, int lo, int hi, int lane) {
-  const int32_t sp = pl.cell_special[c];
-  if (sp < 0) return;
-  const int32_t b0 = pl.sp_nat_begin[sp], b1 = pl.sp_nat_begin[sp + 1];
-  if (lane == 0)                       /* few entries; fixed order */
-    for (int32_t k = b0; k < b1; ++k) {
-      const int row = pl.natbc_row[k];
-      if (row >= lo && row < hi) S.bl[row] += st.natbc_values[k];
-    }
-  warp_sync();
-}
-
-/* final write of residual rows [lo, hi) */
-__device__ __forceinline__ void write_rows(const SbCellCtx& cx, SbWarpScratch& S,
-                                           int lo, int hi, int lane) {
-  if (!cx.b) return;
-  const bool special = (cx.bcmask_lo | cx.bcmask_hi) != 0;
-  for (int l = lo + lane; l < hi; l += 32) {
-    double v = S.bl[l];
-    if (special) {
-      if (sb_is_bc(cx, l)) v = S.gl[l];
-      else for (int q = 0; q < 9; ++q) v += S.lift[l - cx.row0][q];
-    }
-    double* dst = cx.b + cx.dofs[l];
-    if (sb_local_facet(l) >= 0) atomicAdd(dst, v); else *dst = v;
-  }
-}
-
-/* ---- phase C, band rows ---------------------------------------------------- */
-__device__ void phaseC_band(const PlanDev& pl, const StateDev& st, TileSmem& sm,
-                            int64_t c, int ct, int k, int lane, SbWarpScratch& S,
-                            double* vals, double* b) {
-  const SbTables& T = *pl.tables;
-  const int p = 1 + k;
-  const int nb = pl.nb;
-  SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b, sb_lbdm(1 + k, 0));
-  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
-  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
-  sb_prep_cell(T, g, S, lane, 32);
-  warp_sync();
-  const int rlo = sb_lbdm(p, 0), rhi = rlo + 12;
-  if (inside) {
-    for (int e = lane; e < 21; e += 32) {
-      double v = 0.0;
-      for (int t = 0; t < SB_NMC; ++t) v += T.G22u[e][t] * sm.A[t][ct];
-      S.W[e] = v;
-    }
-    sb_flux_coeffs(S, &S.ul[rlo], S.gc, lane, 32);
-    for (int e = lane; e < 36; e += 32) {
-      const int a = e / 18, r = (e % 18) / 3, l = e % 3;
-      double v = 0.0;
-      for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * sm.A[SB_NMC + a * 10 + t][ct];
-      S.V[a][r][l] = v;
-    }
-    warp_sync();
-    for (int e = lane; e < 144; e += 32) {
-      const int m = e / 12, a = (e % 12) / 6, r = e % 6;
-      double v = 0.0;
-      for (int s = 0; s < 6; ++s) v += S.W[sb_sym21(r, s)] * S.GC[m][a][s];
-      S.Z[m][a][r] = v;
-    }
-    for (int e = lane; e < 12; e += 32) {
-      const int a = e / 6, r = e % 6;
-      double v = 0.0;
-      for (int s = 0; s < 6; ++s) v += S.W[sb_sym21(r, s)] * S.gc[a][s];
-      S.zr[a][r] = v;
-    }
-    warp_sync();
-    /* residual of xi rows: dd term + div xi delta_w - jump */
-    for (int i = lane; i < 12; i += 32) {
-      double v = 0.0;
-      for (int a = 0; a < 2; ++a)
-        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.zr[a][r];
-      v *= g.iad;
-      for (int l = 0; l < 3; ++l) v += g.sdet * T.Dhat[i][l] * S.ul[sb_ldg(p, l)];
-      const int f = i / 3;
-      if (f < 3 && (pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
-        const int64_t cn = pl.cell_neighbors[c * 3 + f];
-        const double jump = st.base_w[(int64_t)k * pl.n_cells + cn]
-                          - st.base_w[(int64_t)k * pl.n_cells + c];
-        const double ref_out = (f == 1) ? -1.0 : 1.0;
-        v -= jump * ref_out * g.sdet * T.trI[i % 3];
-      }
-      S.bl[rlo + i] = v;
-    }
-    warp_sync();
-    add_natbc(pl, st, c, S, rlo, rhi, lane);
-    for (int e = lane; e < 144; e += 32) {
-      const int i = e / 12, m = e % 12;
-      double v = 0.0;
-      for (int a = 0; a < 2; ++a)
-        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.Z[m][a][r];
-      sb_emit(cx, S, rlo + i, rlo + m, v * g.iad);
-    }
-    for (int e = lane; e < 36; e += 32) {
-      const int i = e / 3, l = e % 3;
-      double v = 0.0;
-      for (int a = 0; a < 2; ++a)
-        for (int r = 0; r < 6; ++r) v += T.bdmC[i][a][r] * S.V[a][r][l];
-      v *= g.iad;
-      sb_emit(cx, S, rlo + i, sb_ldg(p, l), g.sdet * T.Dhat[i][l] + v);
-      sb_emit(cx, S, rlo + i, sb_ldg(0, l), v);
-    }
-  } else {
-    /* outside the band's subdomain: j.xi * c2 */
-    const double c2 = c_M.ext_j_coef * g.iad;
-    for (int i = lane; i < 12; i += 32) {
-      double v = 0.0;
-      for (int m = 0; m < 12; ++m) v += S.GM[i][m] * S.ul[rlo + m];
-      S.bl[rlo + i] = v * c2;
-    }
-    warp_sync();
-    add_natbc(pl, st, c, S, rlo, rhi, lane);
-    for (int e = lane; e < 144; e += 32) {
-      const int i = e / 12, m = e % 12;
-      sb_emit(cx, S, rlo + i, rlo + m, S.GM[i][m] * c2);
-    }
-  }
-  warp_sync();
-  write_rows(cx, S, rlo, rhi, lane);
-  warp_sync();
-  (void)nb;
-}
-
-/* ---- phase C, continuity rows v^k ------------------------------------------ */
-__device__ void phaseC_cont(const PlanDev& pl, const StateDev& st, TileSmem& sm,
-                            int64_t c, int ct, int k, int lane, SbWarpScratch& S,
-                            double* vals, double* b) {
-  const SbTables& T = *pl.tables;
-  const int p = 1 + k;
-  const int nb = pl.nb;
-  SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b, sb_ldg(1 + k, 0));
-  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
-  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
-  const int rlo = sb_ldg(p, 0), rhi = rlo + 3;
-  warp_sync();
-  if (inside) {
-    const double f = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-    for (int i = lane; i < 3; i += 32) {
-      double v = 0.0;
-      for (int m = 0; m < 12; ++m) v += T.Dhat[m][i] * S.ul[sb_lbdm(p, m)];
-      v *= g.sdet;
-      for (int t = 0; t < 3; ++t) v += f * T.G1[i][t] * sm.A[t][ct];
-      S.bl[rlo + i] = v;
-    }
-    warp_sync();
-    for (int e = lane; e < 36; e += 32) {
-      const int i = e / 12, m = e % 12;
-      sb_emit(cx, S, rlo + i, sb_lbdm(p, m), g.sdet * T.Dhat[m][i]);
-    }
-    for (int e = lane; e < 9 * (1 + nb); e += 32) {
-      const int q = e / 9, i = (e % 9) / 3, l = e % 3;   /* q = 0: phi, 1+m: delta_w_m */
-      double v = 0.0;
-      for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.A[3 + 6 * q + t][ct];
-      sb_emit(cx, S, rlo + i, sb_ldg(q, l), f * v);
-    }
-  } else {
-    const double c1 = c_M.ext_w_coef * g.adet;
-    for (int i = lane; i < 3; i += 32) {
-      double v = 0.0;
-      for (int l = 0; l < 3; ++l) v += T.M1[i][l] * S.ul[rlo + l];
-      S.bl[rlo + i] = c1 * v;
-    }
-    warp_sync();
-    for (int e = lane; e < 9; e += 32)
-      sb_emit(cx, S, rlo + e / 3, rlo + e % 3, c1 * T.M1[e / 3][e % 3]);
-  }
-  warp_sync();
-  write_rows(cx, S, rlo, rhi, lane);
-  warp_sync();
-}
-
-/* ---- phase C, Poisson rows ---------------------------------------------------- */
-__device__ void phaseC_poisson(const PlanDev& pl, const StateDev& st, TileSmem& sm,
-                               int64_t c, int ct, int lane, SbWarpScratch& S,
-                               double* vals, double* b) {
-  const SbTables& T = *pl.tables;
-  const int nbd = pl.nb_dof, nb = pl.nb;
-  SbCellCtx cx;
-  load_cell(pl, st, c, cx, S, lane, vals, b, 0);
-  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
-  sb_prep_cell(T, g, S, lane, 32);
-  warp_sync();
-  /* residuals: w rows (0..2), psi rows (3..14) */
-  for (int i = lane; i < 15; i += 32) {
-    double v = 0.0;
-    if (i < 3) {
-      for (int m = 0; m < 12; ++m) v += T.Dhat[m][i] * S.ul[sb_lbdm(0, m)];
-      v *= g.sdet;
-      for (int t = 0; t < 3; ++t) v -= g.adet * T.G1[i][t] * sm.R[t][ct];
-    } else {
-      const int ii = i - 3;
-      for (int m = 0; m < 12; ++m) v += S.GM[ii][m] * S.ul[sb_lbdm(0, m)];
-      v *= g.iad;
-      for (int l = 0; l < 3; ++l) v -= g.sdet * T.Dhat[ii][l] * S.ul[l];
-    }
-    S.bl[i] = v;
-  }
-  warp_sync();
-  add_natbc(pl, st, c, S, 0, 15, lane);
-  for (int e = lane; e < 36; e += 32) {           /* (w, E) and (psi, phi) */
-    const int i = e / 12, m = e % 12;
-    sb_emit(cx, S, i, sb_lbdm(0, m), g.sdet * T.Dhat[m][i]);
-    sb_emit(cx, S, sb_lbdm(0, m), i, -g.sdet * T.Dhat[m][i]);
-  }
-  for (int e = lane; e < 144; e += 32)            /* (psi, E) */
-    sb_emit(cx, S, sb_lbdm(0, e / 12), sb_lbdm(0, e % 12), S.GM[e / 12][e % 12] * g.iad);
-  for (int e = lane; e < 9 * (1 + nbd); e += 32) { /* (w, phi), (w, delta_w_k) */
-    const int q = e / 9, i = (e % 9) / 3, l = e % 3;
-    double v = 0.0;
-    if (q == 0) {
-      for (int k = 0; k < nb; ++k)
-        for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.X[k][t][ct];
-    } else {
-      for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * sm.X[q - 1][t][ct];
-    }
-    sb_emit(cx, S, i, sb_ldg(q, l), -g.adet * v);
-  }
-  warp_sync();
-  write_rows(cx, S, 0, 15, lane);
-  warp_sync();
-}
-
-/* ------------------------------------------------------------------------- */
+/* One thread = one cell.  All table operands are warp-uniform (constant bank),
+ * moments live in registers; the only memory traffic is the nodal gather, the
+ * per-cell index data and the scatter.                                        */
 __global__ void __launch_bounds__(SB_TILE)
 k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
-#ifdef SB_EMUL_BUILD
-  unsigned char* smem_raw = emul::dyn_smem();
-#else
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-#endif
-  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t c0 = (int64_t)blockIdx.x * SB_TILE;
-  const int64_t c = c0 + tid;
-  const bool valid = c < pl.n_cells;
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
   const int nb = pl.nb, nbd = pl.nb_dof;
   const int L = pl.L;
-  SbWarpScratch& S = sm.ws[warp];
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const int32_t* dofs = pl.cell_dofs + c * L;
 
-  /* per-thread cell data for the pointwise phases */
-  SbCellGeom g;
-  const double* tp = pl.tag_params;
+  SbIO io;
+  io.L = L; io.dofs = dofs;
+  io.rank_own = pl.rank_own + c * L;
+  io.rank_fac = pl.rank_fac + c * 3 * L;
+  io.rowptr = pl.rowptr;
+  io.u = st.u; io.bc_values = st.bc_values;
+  io.vals = vals; io.b = b;
+  io.mlo = 0; io.mhi = 0; io.bcidx = nullptr;
+  int nb0 = 0, nb1 = 0;
+  const int32_t sp = pl.cell_special[c];
+  if (sp >= 0) {
+    io.mlo = pl.sp_mask_lo[sp]; io.mhi = pl.sp_mask_hi[sp];
+    io.bcidx = pl.sp_bcidx + (int64_t)sp * L;
+    nb0 = pl.sp_nat_begin[sp]; nb1 = pl.sp_nat_begin[sp + 1];
+  }
+
+  /* nodal values of the DG1 fields phi, delta_w_k and base_w */
   double dgv[1 + SB_MAX_BANDS][3];
   double w0[SB_MAX_BANDS];
-  const int32_t* dofs = nullptr;
-  if (valid) {
-    g = sb_geom(pl.cell_vertices + c * 6);
-    tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-    dofs = pl.cell_dofs + c * L;
-    for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
-    for (int k = 0; k < nb; ++k) {
-      w0[k] = 0.0;
-      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
-      if (nbd) {
-        w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
-        for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
-      }
+  for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
+  for (int k = 0; k < nb; ++k) {
+    w0[k] = 0.0;
+    for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
+    if (nbd) {
+      w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
+      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
     }
   }
-  const double beta = valid ? 1.0 / tp[SB_TP_KT] : 1.0;
-  const double inv_eps = valid ? 1.0 / tp[SB_TP_EPS] : 1.0;
+  const double beta = 1.0 / tp[SB_TP_KT];
+  const double inv_eps = 1.0 / tp[SB_TP_EPS];
   double mR[SB_NR] = {0.0, 0.0, 0.0};
+  double mX[1 + SB_MAX_BANDS][SB_NRX];      /* [0] = sum over bands, [1+k] = band k */
+  for (int t = 0; t < SB_NRX; ++t) mX[0][t] = 0.0;
   const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
 
   for (int k = 0; k < nb; ++k) {
-    if (valid) {
-      const double* bp = tp + SB_TP_BAND0 + 5 * k;
-      const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
-      const bool dd = inside && nbd;
-      const double N = bp[SB_TPB_N];
-      double gc[2][6];
-      if (dd) {
-        double jc[2][6];
-        for (int a = 0; a < 2; ++a) for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
-        for (int m = 0; m < 12; ++m) {
-          const double jm = st.u[dofs[sb_lbdm(1 + k, m)]];
-          for (int a = 0; a < 2; ++a)
-            for (int r = 0; r < 6; ++r) jc[a][r] += jm * c_T.bdmC[m][a][r];
-        }
-        for (int r = 0; r < 6; ++r) {
-          gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
-          gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
-        }
-      }
-      const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
-      const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
-      const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
-      double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
-      const int kind = c_M.band_kind[k];
-      const double s = (double)c_M.band_sign[k];
-      const int cm = c_M.band_const_mobility[k];
-      const bool rho = (N != 0.0);
-      for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
-      if (same_rule) {
-        if (rho || dd)
-          sb_phaseA_band(c_T.sup, rho, dd, kind, s, cm, beta, bp[SB_TPB_E], N,
-                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                         gc, mC, Q, mR, mRx);
-      } else {
-        if (rho)
-          sb_phaseA_band(c_T.rho, true, false, kind, s, cm, beta, bp[SB_TPB_E], N,
-                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                         gc, mC, Q, mR, mRx);
-        if (dd)
-          sb_phaseA_band(c_T.sup, false, true, kind, s, cm, beta, bp[SB_TPB_E], N,
-                         bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                         gc, mC, Q, mR, mRx);
-      }
-      if (dd) {
-        for (int t = 0; t < SB_NMC; ++t) sm.A[t][tid] = mC[t];
-        for (int t = 0; t < SB_NQ; ++t) sm.A[SB_NMC + t][tid] = Q[t];
-      }
-      for (int t = 0; t < SB_NRX; ++t) sm.X[k][t][tid] = mRx[t];
-    }
-    __syncthreads();
+    const double* bp = tp + SB_TP_BAND0 + 5 * k;
+    const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
+    const bool dd = inside && nbd;
+    const double N = bp[SB_TPB_N];
+    double fl[12];
+    double gc[2][6];
     if (nbd) {
-      for (int q = 0; q < 32; ++q) {
-        const int ct = warp * 32 + q;
-        const int64_t cc = c0 + ct;
-        if (cc >= pl.n_cells) break;
-        phaseC_band(pl, st, sm, cc, ct, k, lane, S, vals, b);
+      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
+    }
+    if (dd) {
+      double jc[2][6];
+      for (int a = 0; a < 2; ++a) for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
+      for (int m = 0; m < 12; ++m)
+        for (int a = 0; a < 2; ++a)
+          for (int r = 0; r < 6; ++r) jc[a][r] += fl[m] * c_T.bdmC[m][a][r];
+      for (int r = 0; r < 6; ++r) {
+        gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
+        gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
       }
     }
-    __syncthreads();
+    const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
+    const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
+    const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
+    double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
+    const int kind = c_M.band_kind[k];
+    const double s = (double)c_M.band_sign[k];
+    const int cm = c_M.band_const_mobility[k];
+    const bool rho = (N != 0.0);
+    for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+    if (same_rule) {
+      if (rho || dd)
+        sb_phaseA_band(c_T.sup, rho, dd, kind, s, cm, beta, bp[SB_TPB_E], N,
+                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                       gc, mC, Q, mR, mRx);
+    } else {
+      if (rho)
+        sb_phaseA_band(c_T.rho, true, false, kind, s, cm, beta, bp[SB_TPB_E], N,
+                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                       gc, mC, Q, mR, mRx);
+      if (dd)
+        sb_phaseA_band(c_T.sup, false, true, kind, s, cm, beta, bp[SB_TPB_E], N,
+                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
+                       gc, mC, Q, mR, mRx);
+    }
+    for (int t = 0; t < SB_NRX; ++t) { mX[1 + k][t] = mRx[t]; mX[0][t] += mRx[t]; }
+    if (nbd) {
+      /* base_w jump term on interior facets where this cell is the '+' side */
+      double jumpf[3];
+      for (int f = 0; f < 3; ++f) {
+        jumpf[f] = 0.0;
+        if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
+          const int64_t cn = pl.cell_neighbors[c * 3 + f];
+          const double ref_out = (f == 1) ? -1.0 : 1.0;
+          jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
+        }
+      }
+      sb_rows_flux(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+                   pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
   }
 
-  /* generation moments + continuity rows */
+  /* generation moments + continuity rows v^k */
   for (int k = 0; k < nbd; ++k) {
-    if (valid) {
-      const double* bp = tp + SB_TP_BAND0 + 5 * k;
-      if (bp[SB_TPB_IN_SUBDOMAIN] != 0.0) {
-        double mG[SB_NG];
-        sb_phaseB_band(c_T, c_M, tp, k, dgv, w0,
-                       st.thmeq ? st.thmeq + c * 6 : nullptr,
-                       st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
-        for (int t = 0; t < 9 + 6 * nb; ++t) sm.A[t][tid] = mG[t];
-      }
-    }
-    __syncthreads();
-    for (int q = 0; q < 32; ++q) {
-      const int ct = warp * 32 + q;
-      const int64_t cc = c0 + ct;
-      if (cc >= pl.n_cells) break;
-      phaseC_cont(pl, st, sm, cc, ct, k, lane, S, vals, b);
-    }
-    __syncthreads();
+    const double* bp = tp + SB_TP_BAND0 + 5 * k;
+    const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
+    double mG[SB_NG];
+    if (inside)
+      sb_phaseB_band(c_T, c_M, tp, k, dgv, w0, st.thmeq ? st.thmeq + c * 6 : nullptr,
+                     st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
+    double fl[12];
+    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
+    const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+    sb_rows_scalar(c_T, c_M, io, g, 1 + k, inside, fl, dgv[1 + k], coef, mG, mG + 3,
+                   1 + nb, pl.natbc_row, st.natbc_values, nb0, nb1);
   }
 
   /* Poisson rows */
-  if (valid) {
+  {
     /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
     mR[0] += tp[SB_TP_RHO_STATIC] * inv_eps * 0.70710678118654752440;
-    for (int t = 0; t < SB_NR; ++t) sm.R[t][tid] = mR[t];
-  }
-  __syncthreads();
-  for (int q = 0; q < 32; ++q) {
-    const int ct = warp * 32 + q;
-    const int64_t cc = c0 + ct;
-    if (cc >= pl.n_cells) break;
-    phaseC_poisson(pl, st, sm, cc, ct, lane, S, vals, b);
+    double fl[12];
+    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
+    sb_rows_scalar(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0], 1 + nbd,
+                   pl.natbc_row, st.natbc_values, nb0, nb1);
+    sb_rows_flux(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+                 pl.natbc_row, st.natbc_values, nb0, nb1);
   }
 }
 
@@ -801,12 +526,6 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   pl->tmp_cells = const_cast<double*>(tmp);
 #undef UP
   if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }
-  cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(TileSmem));
-  if (e != cudaSuccess) {
-    snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    sb_plan_destroy(pl); return SB_ERR_CUDA;
-  }
   *out = pl;
   return SB_OK;
 }
@@ -849,7 +568,7 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
 #endif
-  SB_LAUNCH(k_assemble, (unsigned)((nc + SB_TILE - 1) / SB_TILE), SB_TILE, sizeof(TileSmem), s, pl->d, sd, d_vals, d_b);
+  SB_LAUNCH(k_assemble, (unsigned)((nc + SB_TILE - 1) / SB_TILE), SB_TILE, 0, s, pl->d, sd, d_vals, d_b);
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
 #endif

@@ -10,6 +10,7 @@
 
 #define SB_QM 11            /* max collapsed-rule points per axis */
 #define SB_QG (SB_QM * SB_QM)
+#define SB_NPAIR 78         /* (i <= m) pairs of the 12 BDM2 functions */
 
 /* factored collapsed Gauss-Jacobi rule + separable Dubiner factors at its
  * nodes: point (i, j) = (a_i (1 - b_j), b_j), weight wa_i wb_j,
@@ -26,19 +27,22 @@ typedef struct SbRule {
 } SbRule;
 
 typedef struct SbTables {
-  double bdmC[12][2][6];  /* BDM2 nodal basis in Dubiner P2          */
-  double G22u[21][15];    /* int Psi_t pi_r pi_s, (r<=s) packed      */
-  double G21[6][3][10];   /* int Psi_t pi_r lam_l                    */
-  double G11[3][3][6];    /* int Psi_t lam_i lam_j                   */
-  double G1[3][3];        /* int Psi_t lam_i                         */
-  double Mhat[12][12][3]; /* int psi_i^a psi_j^b: (11, 12+21, 22)    */
-  double Dhat[12][3];     /* int div psi_i lam_l                     */
-  double M1[3][3];        /* int lam_i lam_j                         */
-  double trI[3];          /* int_0^1 of the 3 edge trace functions   */
+  double bdmC[12][2][6];  /* BDM2 nodal basis in Dubiner P2                      */
+  /* int c psi_i . psi_m = iad * sum_t m_t (G11 TB[.][0][t] + G12 TB[.][1][t]
+     + G22 TB[.][2][t]) for the moment vector m_t of c against Dubiner P4       */
+  double TB[SB_NPAIR][3][15];
+  /* int c' (psi_i . g) lam_l = iad * sum_a sum_t TD[i][l][a][t] Q_a[t]          */
+  double TD[12][3][2][10];
+  double G11[3][3][6];    /* int Psi_t lam_i lam_j                               */
+  double G1[3][3];        /* int Psi_t lam_i                                     */
+  double Mhat[12][12][3]; /* int psi_i^a psi_j^b: (11, 12+21, 22)                */
+  double Dhat[12][3];     /* int div psi_i lam_l                                 */
+  double M1[3][3];        /* int lam_i lam_j                                     */
+  double trI[3];          /* int_0^1 of the 3 edge trace functions               */
   double pad_;
-  SbRule rho;             /* rule of the rho term                    */
-  SbRule sup;             /* rule of the xi.j/(mu u) term            */
-  /* generation rule, unfactored: point n, X, Y, weight*Psi_t, P2 Lagrange */
+  SbRule rho;             /* rule of the rho term                                */
+  SbRule sup;             /* rule of the xi.j/(mu u) term                        */
+  /* generation rule, unfactored: point n, X, Y, weight*Psi_t, P2 Lagrange       */
   int32_t ng;
   int32_t pad2_;
   double gX[SB_QG];
