@@ -30,7 +30,8 @@ class SbProblem(C.Structure):
         ('h_cell_vertices', C.c_void_p), ('h_cell_tag', C.c_void_p),
         ('h_cell_dofs', C.c_void_p), ('h_cell_neighbors', C.c_void_p),
         ('h_cell_jump_mask', C.c_void_p), ('h_rowptr', C.c_void_p),
-        ('h_rank_own', C.c_void_p), ('h_rank_fac', C.c_void_p),
+        ('n_patterns', C.c_int64), ('h_patterns', C.c_void_p),
+        ('h_cell_pattern', C.c_void_p),
         ('h_tag_params', C.c_void_p),
         ('n_bc', C.c_int64), ('h_bc_dofs', C.c_void_p),
         ('n_natbc', C.c_int64), ('h_natbc_cell', C.c_void_p),

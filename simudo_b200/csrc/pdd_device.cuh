@@ -76,46 +76,77 @@ SB_HD int sb_local_facet(int l) {
   return (r >= 3 && r < 12) ? (r - 3) / 3 : -1;
 }
 
-/* Pointwise band quantities at chi = e phi + w (band statistics
- * poisson_drift_diffusion1.py1:170-245).  Outputs:
- *   su  = s u / eps               dsu = d(su)/dchi
- *   c   = dd_scale / (mu u)       dc  = dc/dchi                      */
-struct SbBandPoint { double su, dsu, c, dc, u, du; };
+/* Per (cell, band) constants hoisted out of the quadrature loops. */
+struct SbBandK {
+  int kind, const_mob;
+  double s, beta, sbeta;   /* sign, 1/kT, s/kT                         */
+  double E, N, mob;
+  double N_eps;            /* N / eps                                   */
+  double cinv;             /* dd_scale / (mob N)                        */
+  double dd_scale;
+};
 
-SB_HD SbBandPoint sb_band_point(int kind, double s, int const_mob, double beta,
-                                double E, double N, double mob, double inv_eps,
-                                double dd_scale, double chi) {
-  SbBandPoint r;
-  const double t = s * beta * (chi - E);
-  const double e = exp(t);
-  if (kind == SB_BAND_NONDEGENERATE) {
-    const double inv = 1.0 / e;
-    r.u = N * inv;
-    r.du = -s * beta * r.u;
-    r.c = dd_scale * e / (mob * N);
-    r.dc = s * beta * r.c;
+SB_HD SbBandK sb_band_consts(const sb_model& M, const double* tp, int k) {
+  const double* bp = tp + SB_TP_BAND0 + 5 * k;
+  SbBandK K;
+  K.kind = M.band_kind[k];
+  K.const_mob = M.band_const_mobility[k];
+  K.s = (double)M.band_sign[k];
+  K.beta = 1.0 / tp[SB_TP_KT];
+  K.sbeta = K.s * K.beta;
+  K.E = bp[SB_TPB_E];
+  K.N = bp[SB_TPB_N];
+  K.mob = bp[SB_TPB_MOBILITY];
+  K.N_eps = K.N / tp[SB_TP_EPS];
+  K.dd_scale = M.dd_scale;
+  K.cinv = M.dd_scale / (K.mob * K.N);
+  return K;
+}
+
+/* Pointwise band quantities at chi = e phi + w (band statistics
+ * poisson_drift_diffusion1.py1:170-245):
+ *   su = s u / eps, dsu = d(su)/dchi, c = dd_scale / (mu u), dc = dc/dchi   */
+SB_HD void sb_band_point(const SbBandK& K, double chi,
+                         double& su, double& dsu, double& c, double& dc) {
+  const double e = exp(K.sbeta * (chi - K.E));
+  if (K.kind == SB_BAND_NONDEGENERATE) {
+    const double ue = K.N_eps / e;            /* u / eps */
+    su = K.s * ue;
+    dsu = -K.beta * ue;
+    c = K.cinv * e;
+    dc = K.sbeta * c;
   } else {
     const double f = 1.0 / (1.0 + e);
     const double omf = e * f;                 /* 1 - f */
-    r.u = N * f;
-    const double df = -s * beta * f * omf;    /* df/dchi */
-    r.du = N * df;
-    if (const_mob) {
-      r.c = dd_scale * (1.0 + e) / (mob * N);
-      r.dc = dd_scale * s * beta * e / (mob * N);
+    su = K.s * K.N_eps * f;
+    dsu = -K.beta * K.N_eps * f * omf;
+    if (K.const_mob) {
+      c = K.cinv * (1.0 + e);
+      dc = K.cinv * K.sbeta * e;
     } else {
       /* mu = mu0 [(1-f) - 1/2 f^0.33 (1-f)^1.33]  (:228-231) */
+      const double df = -K.sbeta * f * omf;   /* df/dchi */
       const double fa = pow(f, 0.33), ob = pow(omf, 1.33);
-      const double mu = mob * (omf - 0.5 * fa * ob);
-      const double dmu = mob * (-df - 0.5 * (0.33 * fa / f * df * ob
-                                             + fa * 1.33 * ob / omf * (-df)));
-      r.c = dd_scale / (mu * r.u);
-      r.dc = -r.c * (dmu / mu + df / f);
+      const double mu = K.mob * (omf - 0.5 * fa * ob);
+      const double dmu = K.mob * (-df - 0.5 * (0.33 * fa / f * df * ob
+                                               + fa * 1.33 * ob / omf * (-df)));
+      c = K.dd_scale / (mu * K.N * f);
+      dc = -c * (dmu / mu + df / f);
     }
   }
-  r.su = s * r.u * inv_eps;
-  r.dsu = s * r.du * inv_eps;
-  return r;
+}
+
+/* carrier density and its chi-derivative only (generation term) */
+SB_HD void sb_band_u(const SbBandK& K, double chi, double& u, double& du) {
+  if (K.kind == SB_BAND_NONDEGENERATE) {
+    u = K.N * exp(-K.sbeta * (chi - K.E));
+    du = -K.sbeta * u;
+  } else {
+    const double e = exp(K.sbeta * (chi - K.E));
+    const double f = 1.0 / (1.0 + e);
+    u = K.N * f;
+    du = -K.sbeta * u * (e * f);
+  }
 }
 
 /* ------------------------------------------------------------------------- *
@@ -125,19 +156,25 @@ SB_HD SbBandPoint sb_band_point(int kind, double s, int const_mob, double beta,
  * outputs (overwritten unless noted):
  *   mC[15], Q[2][10]          if do_dd
  *   mRx[6], mR[3] (+=)        if do_rho
+ * MM > 0: compile-time number of points per axis (inner loop unrolled, the
+ * independent exp chains of neighbouring points interleave); MM = 0: R.m.
  * ------------------------------------------------------------------------- */
-SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd,
-                          int kind, double s, int const_mob, double beta,
-                          double E, double N, double mob, double inv_eps,
-                          double dd_scale, double chi0, double chix, double chiy,
-                          const double (*gc)[6],
+template <int MM>
+SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBandK& K,
+                          double chi0, double chix, double chiy, const double (*gc)[6],
                           double* mC, double* Q, double* mR, double* mRx) {
-  const int m = R.m;
+  const int m = MM > 0 ? MM : R.m;
   if (do_dd) {
+#pragma unroll
     for (int t = 0; t < SB_NMC; ++t) mC[t] = 0.0;
+#pragma unroll
     for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
   }
-  if (do_rho) for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+  if (do_rho) {
+#pragma unroll
+    for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+  }
+#pragma unroll 1
   for (int j = 0; j < m; ++j) {
     const double bj = R.b[j];
     const double omb = 1.0 - bj;
@@ -145,6 +182,7 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd,
     double H[2][3];
     if (do_dd) {
       const double* h = R.h6[j];   /* order: (0,0) (0,1) (1,0) (0,2) (1,1) (2,0) */
+#pragma unroll
       for (int a = 0; a < 2; ++a) {
         H[a][0] = gc[a][0] * h[0] + gc[a][1] * h[1] + gc[a][3] * h[3];
         H[a][1] = gc[a][2] * h[2] + gc[a][4] * h[4];
@@ -157,21 +195,24 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd,
     double Sx[3] = {0, 0, 0};
     const double chij = chi0 + chiy * bj;
     const double chis = chix * omb;
+#pragma unroll
     for (int i = 0; i < m; ++i) {
       const double chi = chij + chis * R.a[i];
-      const SbBandPoint bp = sb_band_point(kind, s, const_mob, beta, E, N, mob,
-                                           inv_eps, dd_scale, chi);
+      double su, dsu, c, dc;
+      sb_band_point(K, chi, su, dsu, c, dc);
       const double* wg = R.wag[i];
       if (do_dd) {
         const double* g3 = R.g3[i];
-        const double q0 = bp.dc * (g3[0] * H[0][0] + g3[1] * H[0][1] + g3[2] * H[0][2]);
-        const double q1 = bp.dc * (g3[0] * H[1][0] + g3[1] * H[1][1] + g3[2] * H[1][2]);
-        for (int p = 0; p < 5; ++p) Sc[p] += wg[p] * bp.c;
+        const double q0 = dc * (g3[0] * H[0][0] + g3[1] * H[0][1] + g3[2] * H[0][2]);
+        const double q1 = dc * (g3[0] * H[1][0] + g3[1] * H[1][1] + g3[2] * H[1][2]);
+#pragma unroll
+        for (int p = 0; p < 5; ++p) Sc[p] += wg[p] * c;
+#pragma unroll
         for (int p = 0; p < 4; ++p) { Sq[0][p] += wg[p] * q0; Sq[1][p] += wg[p] * q1; }
       }
       if (do_rho) {
-        Sr[0] += wg[0] * bp.su; Sr[1] += wg[1] * bp.su;
-        Sx[0] += wg[0] * bp.dsu; Sx[1] += wg[1] * bp.dsu; Sx[2] += wg[2] * bp.dsu;
+        Sr[0] += wg[0] * su; Sr[1] += wg[1] * su;
+        Sx[0] += wg[0] * dsu; Sx[1] += wg[1] * dsu; Sx[2] += wg[2] * dsu;
       }
     }
     /* outer accumulation: Psi_t = g_p h_pq, t in hierarchical (degree, p) order:
@@ -180,10 +221,14 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd,
     const double* wh = R.wbh[j];
     if (do_dd) {
       int t = 0;
+#pragma unroll
       for (int n = 0; n <= 4; ++n)
+#pragma unroll
         for (int p = 0; p <= n; ++p, ++t) mC[t] += wh[t] * Sc[p];
       t = 0;
+#pragma unroll
       for (int n = 0; n <= 3; ++n)
+#pragma unroll
         for (int p = 0; p <= n; ++p, ++t) {
           Q[t] += wh[t] * Sq[0][p];
           Q[10 + t] += wh[t] * Sq[1][p];
@@ -192,14 +237,16 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd,
     if (do_rho) {
       mR[0] += wh[0] * Sr[0]; mR[1] += wh[1] * Sr[0]; mR[2] += wh[2] * Sr[1];
       int t = 0;
+#pragma unroll
       for (int n = 0; n <= 2; ++n)
+#pragma unroll
         for (int p = 0; p <= n; ++p, ++t) mRx[t] += wh[t] * Sx[p];
     }
   }
 }
 
 /* ------------------------------------------------------------------------- *
- * phase B: generation term of band k at the points of the g-rule.
+ * phase B: generation terms of all bands at the points of the g-rule.
  * ------------------------------------------------------------------------- */
 struct SbBandsAtPoint {
   double u[SB_MAX_BANDS], du[SB_MAX_BANDS], w[SB_MAX_BANDS], u0[SB_MAX_BANDS];
@@ -293,49 +340,66 @@ SB_HD void sb_generation(const sb_model& M, const double* tp, int k,
   }
 }
 
-/* Moments of g_k, dg_k/dphi, dg_k/dw_l over the g-rule.
- * dgv[p][3]: P1 nodal values of (phi | delta_w_l) ; w0[l]: base_w of the cell.
- * out: mG[0..2] (P1), mG[3..8] (dphi, P2), mG[9+6l ..] (dw_l, P2)            */
-SB_HD void sb_phaseB_band(const SbTables& T, const sb_model& M, const double* tp, int k,
-                          const double (*dgv)[3], const double* w0,
-                          const double* thmeq6, const double* phi_opt, int64_t field_stride,
-                          double* mG) {
-  const int nb = M.n_bands;
-  for (int t = 0; t < SB_NG; ++t) mG[t] = 0.0;
-  const double beta = 1.0 / tp[SB_TP_KT];
+/* Moments of g_k, dg_k/dphi, dg_k/dw_l for every band k at once (each point's
+ * band data is evaluated once).  dgv[p][3]: P1 nodal values of (phi |
+ * delta_w_l); w0[l]: base_w of the cell; inside[k]: cell in band k's subdomain.
+ * out mG[k][.]: [0..2] g (P1), [3..8] d/dphi (P2), [9+6l ..] d/dw_l (P2).       */
+template <int NB>
+SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
+                         const double (*dgv)[3], const double* w0, const bool* inside,
+                         const double* thmeq6, const double* phi_opt, int64_t field_stride,
+                         double (*mG)[SB_NG]) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+#pragma unroll
+    for (int t = 0; t < 9 + 6 * NB; ++t) mG[k][t] = 0.0;
+  SbBandK K[NB > 0 ? NB : 1];
+  bool need_u0 = false;
+  for (int p = 0; p < M.n_procs; ++p) need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
+#pragma unroll
+  for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
+#pragma unroll 1
   for (int n = 0; n < T.ng; ++n) {
     const double X = T.gX[n], Y = T.gY[n];
     const double l0 = 1.0 - X - Y;
     const double phi = dgv[0][0] * l0 + dgv[0][1] * X + dgv[0][2] * Y;
     const double* n2 = T.gp2[n];
     double phi_te = 0.0;
-    if (thmeq6) for (int a = 0; a < 6; ++a) phi_te += thmeq6[a] * n2[a];
+    if (need_u0 && thmeq6) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) phi_te += thmeq6[a] * n2[a];
+    }
     SbBandsAtPoint B;
-    for (int l = 0; l < nb; ++l) {
-      const double* bp = tp + SB_TP_BAND0 + 5 * l;
+#pragma unroll
+    for (int l = 0; l < NB; ++l) {
       B.w[l] = w0[l] + dgv[1 + l][0] * l0 + dgv[1 + l][1] * X + dgv[1 + l][2] * Y;
-      const double s = (double)M.band_sign[l];
-      const SbBandPoint q = sb_band_point(M.band_kind[l], s, 1, beta, bp[SB_TPB_E],
-                                          bp[SB_TPB_N], 1.0, 1.0, 1.0, phi + B.w[l]);
-      B.u[l] = q.u; B.du[l] = q.du;
-      const SbBandPoint q0 = sb_band_point(M.band_kind[l], s, 1, beta, bp[SB_TPB_E],
-                                           bp[SB_TPB_N], 1.0, 1.0, 1.0, phi_te);
-      B.u0[l] = q0.u;
+      sb_band_u(K[l], phi + B.w[l], B.u[l], B.du[l]);
+      B.u0[l] = 0.0;
+      if (need_u0) { double d_; sb_band_u(K[l], phi_te, B.u0[l], d_); }
     }
     double phi_clip[SB_MAX_FIELDS];
     for (int f = 0; f < M.n_fields; ++f) {
       const double* pf = phi_opt + (int64_t)f * field_stride;
       double v = 0.0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) v += pf[a] * n2[a];
       phi_clip[f] = v < 0.0 ? 0.0 : v;      /* optical.py:201-203 */
     }
-    double g, dphi, dw[SB_MAX_BANDS];
-    sb_generation(M, tp, k, B, phi_clip, g, dphi, dw);
     const double* wp = T.gwpsi[n];
-    for (int t = 0; t < 3; ++t) mG[t] += wp[t] * g;
-    for (int t = 0; t < 6; ++t) mG[3 + t] += wp[t] * dphi;
-    for (int l = 0; l < nb; ++l)
-      for (int t = 0; t < 6; ++t) mG[9 + 6 * l + t] += wp[t] * dw[l];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      if (!inside[k]) continue;
+      double g, dphi, dw[SB_MAX_BANDS];
+      sb_generation(M, tp, k, B, phi_clip, g, dphi, dw);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) mG[k][t] += wp[t] * g;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) mG[k][3 + t] += wp[t] * dphi;
+#pragma unroll
+      for (int l = 0; l < NB; ++l)
+#pragma unroll
+        for (int t = 0; t < 6; ++t) mG[k][9 + 6 * l + t] += wp[t] * dw[l];
+    }
   }
 }
 
@@ -345,8 +409,7 @@ SB_HD void sb_phaseB_band(const SbTables& T, const sb_model& M, const double* tp
 struct SbIO {
   int L;
   const int32_t* dofs;       /* [L] global dofs of this cell                */
-  const uint8_t* rank_own;   /* [L]                                         */
-  const uint8_t* rank_fac;   /* [3][L]                                      */
+  const uint8_t* pat;        /* [4][L] rank pattern of this cell            */
   const int64_t* rowptr;
   const double* u;
   const double* bc_values;
@@ -360,7 +423,6 @@ struct SbIO {
 SB_HD bool sb_is_bc(const SbIO& io, int l) {
   return l < 64 ? ((io.mlo >> l) & 1ull) : ((io.mhi >> (l - 64)) & 1u);
 }
-SB_HD bool sb_special(const SbIO& io) { return (io.mlo | io.mhi) != 0; }
 /* Dirichlet lift value u_j - bc_j of a constrained local dof */
 SB_HD double sb_lift_value(const SbIO& io, int j) {
   return io.u[io.dofs[j]] - io.bc_values[io.bcidx[j]];
@@ -372,12 +434,14 @@ SB_HD double sb_lift_value(const SbIO& io, int j) {
 #define SB_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
-/* Write one structurally non-zero Jacobian entry (local i, j) = val with the
- * element-wise symmetric Dirichlet rule; Fi is the
- * residual accumulator of row i (receives the x0 lifting, in program order,
- * hence bit-reproducible).                                                   */
-SB_HD void sb_emit(const SbIO& io, int i, int j, double val, double& Fi) {
-  if (sb_special(io)) {
+/* Write one structurally non-zero Jacobian entry (local i, j) = val.
+ * rowbase = rowptr[dofs[i]].  SP: the cell has Dirichlet dofs -> element-wise
+ * symmetric rule; Fi is the residual accumulator of row i
+ * and receives the x0 lifting in program order (bit-reproducible).  With
+ * compile-time (i, j) every facet test folds away.                            */
+template <bool SP>
+SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, double& Fi) {
+  if (SP) {
     if (sb_is_bc(io, i)) {
       val = (i == j) ? 1.0 : 0.0;
     } else if (sb_is_bc(io, j)) {
@@ -387,9 +451,9 @@ SB_HD void sb_emit(const SbIO& io, int i, int j, double val, double& Fi) {
   }
   if (!io.vals) return;
   const int fi = sb_local_facet(i);
-  const int rk = (fi < 0) ? io.rank_own[j] : io.rank_fac[fi * io.L + j];
+  const int rk = io.pat[(fi + 1) * io.L + j];
   if (rk == 0xFF) return;                 /* not in a compacted pattern */
-  double* dst = io.vals + io.rowptr[io.dofs[i]] + rk;
+  double* dst = io.vals + rowbase + rk;
   /* two cells add into the same slot only for (facet dof, facet dof) pairs of
      one facet; two addends onto a zeroed slot commute -> deterministic       */
   if (fi >= 0 && sb_local_facet(j) == fi) SB_ATOMIC_ADD(dst, val);
@@ -397,15 +461,12 @@ SB_HD void sb_emit(const SbIO& io, int i, int j, double val, double& Fi) {
 }
 
 /* final residual value of local row i */
+template <bool SP>
 SB_HD void sb_put_row(const SbIO& io, int i, double F) {
   if (!io.b) return;
-  if (sb_special(io) && sb_is_bc(io, i)) F = sb_lift_value(io, i);
+  if (SP && sb_is_bc(io, i)) F = sb_lift_value(io, i);
   double* dst = io.b + io.dofs[i];
   if (sb_local_facet(i) >= 0) SB_ATOMIC_ADD(dst, F); else *dst = F;
-}
-
-SB_HD int sb_pair(int i, int m) {       /* packed index of (i <= m) in 12 x 12 */
-  return i * 12 - (i * (i - 1)) / 2 + (m - i);
 }
 
 /* natural-BC values of this cell for rows [lo, lo+n): F[row-lo] += value */
@@ -417,7 +478,12 @@ SB_HD void sb_add_natbc(const int32_t* nat_row, const double* nat_val, int b0, i
   }
 }
 
-/* ---- rows xi^k (BDM test functions of band k) ------------------------------- */
+/* Loops over local rows/columns are fully unrolled on the fast path (all
+ * indices compile-time: table operands become constant-bank immediates, rank
+ * loads get immediate offsets) and kept rolled on the rare Dirichlet path.    */
+
+/* ---- rows psi (Poisson) / xi^k (band k): BDM test functions ------------------ */
+template <bool SP>
 SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
                         const SbCellGeom& g, int p, bool is_band, bool inside,
                         const double* mC, const double* Q,
@@ -426,11 +492,15 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
                         const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
   const int r0 = sb_lbdm(p, 0);
   double F[12];
-  for (int i = 0; i < 12; ++i) F[i] = 0.0;
+  int64_t rb[12];
+#pragma unroll (SP ? 1 : 12)
+  for (int i = 0; i < 12; ++i) { F[i] = 0.0; rb[i] = io.rowptr[io.dofs[r0 + i]]; }
   if (is_band && inside) {
     /* <xi_i . xi_m c>: symmetric, 78 pairs x 45 FMAs on warp-uniform constants */
     int pair = 0;
+#pragma unroll (SP ? 1 : 12)
     for (int i = 0; i < 12; ++i)
+#pragma unroll (SP ? 1 : 12)
       for (int m = i; m < 12; ++m, ++pair) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
@@ -441,14 +511,16 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
         }
         const double v = (g.G11 * a0 + g.G12 * a1 + g.G22 * a2) * g.iad;
         F[i] += v * fl[m];
-        sb_emit(io, r0 + i, r0 + m, v, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, r0 + m, v, F[i]);
         if (m != i) {
           F[m] += v * fl[i];
-          sb_emit(io, r0 + m, r0 + i, v, F[m]);
+          sb_emit<SP>(io, rb[m], r0 + m, r0 + i, v, F[m]);
         }
       }
     /* <div xi_i delta_w> + <xi_i . j dc/dchi lam_l> */
+#pragma unroll (SP ? 1 : 12)
     for (int i = 0; i < 12; ++i) {
+#pragma unroll (SP ? 1 : 3)
       for (int l = 0; l < 3; ++l) {
         double d = 0.0;
 #pragma unroll
@@ -457,79 +529,96 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
         d *= g.iad;
         const double dv = g.sdet * T.Dhat[i][l];
         F[i] += dv * sl[l];
-        sb_emit(io, r0 + i, sb_ldg(p, l), dv + d, F[i]);
-        sb_emit(io, r0 + i, sb_ldg(0, l), d, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(p, l), dv + d, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(0, l), d, F[i]);
       }
-      if (jumpf) F[i] -= jumpf[i / 3] * T.trI[i % 3];
+      if (jumpf && i < 9) F[i] -= jumpf[i / 3] * T.trI[i % 3];   /* facet dofs only */
     }
   } else {
     /* polynomial mass block: Poisson <psi.E> (scale 1) or the out-of-subdomain
        penalty <j.xi> c2 (poisson_drift_diffusion1.py1:288-289)               */
     const double sc = (is_band ? M.ext_j_coef : 1.0) * g.iad;
+#pragma unroll (SP ? 1 : 12)
     for (int i = 0; i < 12; ++i)
+#pragma unroll (SP ? 1 : 12)
       for (int m = i; m < 12; ++m) {
         const double v = sc * (g.G11 * T.Mhat[i][m][0] + g.G12 * T.Mhat[i][m][1]
                                + g.G22 * T.Mhat[i][m][2]);
         F[i] += v * fl[m];
-        sb_emit(io, r0 + i, r0 + m, v, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, r0 + m, v, F[i]);
         if (m != i) {
           F[m] += v * fl[i];
-          sb_emit(io, r0 + m, r0 + i, v, F[m]);
+          sb_emit<SP>(io, rb[m], r0 + m, r0 + i, v, F[m]);
         }
       }
     if (!is_band) {
       /* - <div psi_i phi> */
+#pragma unroll (SP ? 1 : 12)
       for (int i = 0; i < 12; ++i)
+#pragma unroll (SP ? 1 : 3)
         for (int l = 0; l < 3; ++l) {
           const double dv = -g.sdet * T.Dhat[i][l];
           F[i] += dv * sl[l];
-          sb_emit(io, r0 + i, sb_ldg(0, l), dv, F[i]);
+          sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(0, l), dv, F[i]);
         }
     }
   }
   if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 12, F);
-  for (int i = 0; i < 12; ++i) sb_put_row(io, r0 + i, F[i]);
+#pragma unroll (SP ? 1 : 12)
+  for (int i = 0; i < 12; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 
 /* ---- rows of the DG1 test functions: w (Poisson, p = 0) or v^k (p = 1 + k) ---- *
  * coef: multiplies the moment terms (-adet for rho, -s e adet for g)
  * mom1[3]: P1 moments of the source (rho/eps | g_k)
- * momJ[q][6]: P2 moments of d source / d (phi | delta_w_q-1), q < nq          */
+ * momJ[q][6]: P2 moments of d source / d (phi | delta_w_q-1), q < NQ          */
+template <bool SP, int NQ>
 SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
                           const SbCellGeom& g, int p, bool inside,
                           const double* fl /*[12] flux dofs of p*/, const double* sl /*[3]*/,
-                          double coef, const double* mom1, const double* momJ, int nq,
+                          double coef, const double* mom1, const double* momJ,
                           const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
   const int r0 = sb_ldg(p, 0);
   double F[3] = {0.0, 0.0, 0.0};
+  int64_t rb[3];
+#pragma unroll (SP ? 1 : 12)
+  for (int i = 0; i < 3; ++i) rb[i] = io.rowptr[io.dofs[r0 + i]];
   if (inside) {
+#pragma unroll (SP ? 1 : 12)
     for (int i = 0; i < 3; ++i) {
+#pragma unroll (SP ? 1 : 12)
       for (int m = 0; m < 12; ++m) {            /* <v_i div j> */
         const double dv = g.sdet * T.Dhat[m][i];
         F[i] += dv * fl[m];
-        sb_emit(io, r0 + i, sb_lbdm(p, m), dv, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, sb_lbdm(p, m), dv, F[i]);
       }
+#pragma unroll
       for (int t = 0; t < 3; ++t) F[i] += coef * T.G1[i][t] * mom1[t];
-      for (int q = 0; q < nq; ++q)
+#pragma unroll (SP ? 1 : 8)
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll (SP ? 1 : 3)
         for (int l = 0; l < 3; ++l) {
           double v = 0.0;
 #pragma unroll
           for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
-          sb_emit(io, r0 + i, sb_ldg(q, l), coef * v, F[i]);
+          sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(q, l), coef * v, F[i]);
         }
     }
   } else {
     /* out-of-subdomain penalty <delta_w v> c1 (:285-286) */
     const double c1 = M.ext_w_coef * g.adet;
+#pragma unroll (SP ? 1 : 12)
     for (int i = 0; i < 3; ++i)
+#pragma unroll (SP ? 1 : 3)
       for (int l = 0; l < 3; ++l) {
         const double v = c1 * T.M1[i][l];
         F[i] += v * sl[l];
-        sb_emit(io, r0 + i, r0 + l, v, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, r0 + l, v, F[i]);
       }
   }
   if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 3, F);
-  for (int i = 0; i < 3; ++i) sb_put_row(io, r0 + i, F[i]);
+#pragma unroll (SP ? 1 : 12)
+  for (int i = 0; i < 3; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 
 #endif /* SB_PDD_DEVICE_CUH */

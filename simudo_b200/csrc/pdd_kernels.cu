@@ -52,8 +52,8 @@ struct PlanDev {
   const int32_t* cell_neighbors;
   const uint8_t* cell_jump_mask;
   const int64_t* rowptr;
-  const uint8_t* rank_own;
-  const uint8_t* rank_fac;
+  const uint8_t* patterns;       /* [n_patterns][4][L]                       */
+  const int32_t* cell_pattern;   /* [n_cells]                                */
   const double* tag_params;
   const int32_t* cell_special;   /* [n_cells] -1 or special index            */
   const uint64_t* sp_mask_lo;
@@ -94,7 +94,7 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
   if (c >= pl.n_cells) return;
   const int L = pl.L;
   const int32_t* dofs = pl.cell_dofs + c * L;
-  const uint8_t* rf = pl.rank_fac + c * 3 * L;
+  const uint8_t* rf = pl.patterns + ((int64_t)pl.cell_pattern[c] * 4 + 1) * L;
   for (int p = 0; p < pl.P; ++p)
     for (int f = 0; f < 3; ++f)
       for (int k = 0; k < 3; ++k) {
@@ -114,21 +114,154 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
 /* ------------------------------------------------------------------------- */
 /* One thread = one cell.  All table operands are warp-uniform (constant bank),
  * moments live in registers; the only memory traffic is the nodal gather, the
- * per-cell index data and the scatter.                                        */
+ * per-cell index data and the scatter.  NB = number of bands with dofs
+ * (compile-time so every per-band array stays in registers); SP = the cell has
+ * Dirichlet dofs (rare; kept on a compact rolled code path).                  */
+template <int NB, bool SP>
+__device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev& st,
+                                              double* vals, double* b, int64_t c, SbIO& io,
+                                              int nb0, int nb1) {
+  const int nb = pl.nb;                       /* bands entering rho */
+  const int L = pl.L;
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const int32_t* dofs = io.dofs;
+  (void)L;
+
+  /* nodal values of the DG1 fields phi, delta_w_k and base_w */
+  double dgv[1 + SB_MAX_BANDS][3];
+  double w0[SB_MAX_BANDS];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
+#pragma unroll
+  for (int k = 0; k < SB_MAX_BANDS; ++k) {
+    w0[k] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
+    if (k < NB) {
+      w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
+    }
+  }
+  double mR[SB_NR] = {0.0, 0.0, 0.0};
+  double mX[1 + SB_MAX_BANDS][SB_NRX];      /* [0] = sum over bands, [1+k] = band k */
+#pragma unroll
+  for (int q = 0; q < 1 + SB_MAX_BANDS; ++q)
+#pragma unroll
+    for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
+  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
+  const bool std_rule = same_rule && (c_M.quad_m_super == 11);
+  bool inside_k[SB_MAX_BANDS] = {false, false, false, false};
+
+#pragma unroll
+  for (int k = 0; k < SB_MAX_BANDS; ++k) {
+    if (k >= nb) break;
+    const SbBandK K = sb_band_consts(c_M, tp, k);
+    const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+    const bool dd = inside && (k < NB);
+    inside_k[k] = inside;
+    double fl[12];
+    double gc[2][6];
+    if (k < NB) {
+#pragma unroll
+      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
+    }
+    if (dd) {
+      double jc[2][6];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
+#pragma unroll
+      for (int m = 0; m < 12; ++m)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int r = 0; r < 6; ++r) jc[a][r] += fl[m] * c_T.bdmC[m][a][r];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
+        gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
+      }
+    }
+    const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
+    const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
+    const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
+    double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
+    const bool rho = (K.N != 0.0);
+#pragma unroll
+    for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+    if (std_rule) {
+      if (rho || dd)
+        sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    } else if (same_rule) {
+      if (rho || dd)
+        sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    } else {
+      if (rho) sb_phaseA_band<0>(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+      if (dd) sb_phaseA_band<0>(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    }
+#pragma unroll
+    for (int t = 0; t < SB_NRX; ++t) { mX[1 + k][t] = mRx[t]; mX[0][t] += mRx[t]; }
+    if (k < NB) {
+      /* base_w jump term on interior facets where this cell is the '+' side */
+      double jumpf[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        jumpf[f] = 0.0;
+        if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
+          const int64_t cn = pl.cell_neighbors[c * 3 + f];
+          const double ref_out = (f == 1) ? -1.0 : 1.0;
+          jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
+        }
+      }
+      sb_rows_flux<SP>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+                       pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
+  }
+
+  /* generation moments (all bands at once) + continuity rows v^k */
+  if (NB > 0) {
+    double mG[NB > 0 ? NB : 1][SB_NG];
+    sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k,
+                      st.thmeq ? st.thmeq + c * 6 : nullptr,
+                      st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      double fl[12];
+#pragma unroll
+      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
+      const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+      sb_rows_scalar<SP, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
+                                 mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
+  }
+
+  /* Poisson rows */
+  {
+    /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
+    mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
+    double fl[12];
+#pragma unroll
+    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
+    sb_rows_scalar<SP, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
+                               pl.natbc_row, st.natbc_values, nb0, nb1);
+    sb_rows_flux<SP>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+                     pl.natbc_row, st.natbc_values, nb0, nb1);
+  }
+}
+
+template <int NB>
 __global__ void __launch_bounds__(SB_TILE)
 k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
-  const int nb = pl.nb, nbd = pl.nb_dof;
   const int L = pl.L;
-  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
-  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-  const int32_t* dofs = pl.cell_dofs + c * L;
-
   SbIO io;
-  io.L = L; io.dofs = dofs;
-  io.rank_own = pl.rank_own + c * L;
-  io.rank_fac = pl.rank_fac + c * 3 * L;
+  io.L = L;
+  io.dofs = pl.cell_dofs + c * L;
+  io.pat = pl.patterns + (int64_t)pl.cell_pattern[c] * 4 * L;
   io.rowptr = pl.rowptr;
   io.u = st.u; io.bc_values = st.bc_values;
   io.vals = vals; io.b = b;
@@ -140,114 +273,8 @@ k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
     io.bcidx = pl.sp_bcidx + (int64_t)sp * L;
     nb0 = pl.sp_nat_begin[sp]; nb1 = pl.sp_nat_begin[sp + 1];
   }
-
-  /* nodal values of the DG1 fields phi, delta_w_k and base_w */
-  double dgv[1 + SB_MAX_BANDS][3];
-  double w0[SB_MAX_BANDS];
-  for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
-  for (int k = 0; k < nb; ++k) {
-    w0[k] = 0.0;
-    for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
-    if (nbd) {
-      w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
-      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
-    }
-  }
-  const double beta = 1.0 / tp[SB_TP_KT];
-  const double inv_eps = 1.0 / tp[SB_TP_EPS];
-  double mR[SB_NR] = {0.0, 0.0, 0.0};
-  double mX[1 + SB_MAX_BANDS][SB_NRX];      /* [0] = sum over bands, [1+k] = band k */
-  for (int t = 0; t < SB_NRX; ++t) mX[0][t] = 0.0;
-  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
-
-  for (int k = 0; k < nb; ++k) {
-    const double* bp = tp + SB_TP_BAND0 + 5 * k;
-    const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
-    const bool dd = inside && nbd;
-    const double N = bp[SB_TPB_N];
-    double fl[12];
-    double gc[2][6];
-    if (nbd) {
-      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
-    }
-    if (dd) {
-      double jc[2][6];
-      for (int a = 0; a < 2; ++a) for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
-      for (int m = 0; m < 12; ++m)
-        for (int a = 0; a < 2; ++a)
-          for (int r = 0; r < 6; ++r) jc[a][r] += fl[m] * c_T.bdmC[m][a][r];
-      for (int r = 0; r < 6; ++r) {
-        gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
-        gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
-      }
-    }
-    const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
-    const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
-    const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
-    double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
-    const int kind = c_M.band_kind[k];
-    const double s = (double)c_M.band_sign[k];
-    const int cm = c_M.band_const_mobility[k];
-    const bool rho = (N != 0.0);
-    for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
-    if (same_rule) {
-      if (rho || dd)
-        sb_phaseA_band(c_T.sup, rho, dd, kind, s, cm, beta, bp[SB_TPB_E], N,
-                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                       gc, mC, Q, mR, mRx);
-    } else {
-      if (rho)
-        sb_phaseA_band(c_T.rho, true, false, kind, s, cm, beta, bp[SB_TPB_E], N,
-                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                       gc, mC, Q, mR, mRx);
-      if (dd)
-        sb_phaseA_band(c_T.sup, false, true, kind, s, cm, beta, bp[SB_TPB_E], N,
-                       bp[SB_TPB_MOBILITY], inv_eps, c_M.dd_scale, chi0, chix, chiy,
-                       gc, mC, Q, mR, mRx);
-    }
-    for (int t = 0; t < SB_NRX; ++t) { mX[1 + k][t] = mRx[t]; mX[0][t] += mRx[t]; }
-    if (nbd) {
-      /* base_w jump term on interior facets where this cell is the '+' side */
-      double jumpf[3];
-      for (int f = 0; f < 3; ++f) {
-        jumpf[f] = 0.0;
-        if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
-          const int64_t cn = pl.cell_neighbors[c * 3 + f];
-          const double ref_out = (f == 1) ? -1.0 : 1.0;
-          jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
-        }
-      }
-      sb_rows_flux(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
-                   pl.natbc_row, st.natbc_values, nb0, nb1);
-    }
-  }
-
-  /* generation moments + continuity rows v^k */
-  for (int k = 0; k < nbd; ++k) {
-    const double* bp = tp + SB_TP_BAND0 + 5 * k;
-    const bool inside = bp[SB_TPB_IN_SUBDOMAIN] != 0.0;
-    double mG[SB_NG];
-    if (inside)
-      sb_phaseB_band(c_T, c_M, tp, k, dgv, w0, st.thmeq ? st.thmeq + c * 6 : nullptr,
-                     st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
-    double fl[12];
-    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
-    const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-    sb_rows_scalar(c_T, c_M, io, g, 1 + k, inside, fl, dgv[1 + k], coef, mG, mG + 3,
-                   1 + nb, pl.natbc_row, st.natbc_values, nb0, nb1);
-  }
-
-  /* Poisson rows */
-  {
-    /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
-    mR[0] += tp[SB_TP_RHO_STATIC] * inv_eps * 0.70710678118654752440;
-    double fl[12];
-    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
-    sb_rows_scalar(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0], 1 + nbd,
-                   pl.natbc_row, st.natbc_values, nb0, nb1);
-    sb_rows_flux(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
-                 pl.natbc_row, st.natbc_values, nb0, nb1);
-  }
+  if (io.mlo | io.mhi) assemble_cell<NB, true>(pl, st, vals, b, c, io, nb0, nb1);
+  else assemble_cell<NB, false>(pl, st, vals, b, c, io, nb0, nb1);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -258,7 +285,7 @@ __global__ void k_colidx(PlanDev pl, int32_t* col) {
   for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
     const int i = e / L, j = e % L;
     const int fi = sb_local_facet(i);
-    const uint8_t rk = (fi < 0) ? pl.rank_own[c * L + j] : pl.rank_fac[(c * 3 + fi) * L + j];
+    const uint8_t rk = pl.patterns[((int64_t)pl.cell_pattern[c] * 4 + fi + 1) * L + j];
     if (rk != 0xFF) col[pl.rowptr[dofs[i]] + rk] = dofs[j];
   }
 }
@@ -455,8 +482,8 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   UP(cell_neighbors, pr->h_cell_neighbors, nc * 3);
   UP(cell_jump_mask, pr->h_cell_jump_mask, nc * 3);
   UP(rowptr, pr->h_rowptr, N + 1);
-  UP(rank_own, pr->h_rank_own, nc * L);
-  UP(rank_fac, pr->h_rank_fac, nc * 3 * L);
+  UP(patterns, pr->h_patterns, pr->n_patterns * 4 * L);
+  UP(cell_pattern, pr->h_cell_pattern, nc);
   UP(tag_params, pr->h_tag_params, (size_t)model->n_tags * SB_TAG_STRIDE);
   UP(tables, &pl->tables, 1);
   /* special cells: Dirichlet dofs and natural-BC rows */
@@ -568,7 +595,14 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
 #endif
-  SB_LAUNCH(k_assemble, (unsigned)((nc + SB_TILE - 1) / SB_TILE), SB_TILE, 0, s, pl->d, sd, d_vals, d_b);
+  const unsigned nblk = (unsigned)((nc + SB_TILE - 1) / SB_TILE);
+  switch (pl->d.nb_dof) {
+    case 0: SB_LAUNCH(k_assemble<0>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+    case 1: SB_LAUNCH(k_assemble<1>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+    case 2: SB_LAUNCH(k_assemble<2>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+    case 3: SB_LAUNCH(k_assemble<3>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+    default: SB_LAUNCH(k_assemble<4>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+  }
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
 #endif

@@ -51,12 +51,13 @@ class AssemblyPlan(object):
         pr = _lib.SbProblem()
         pr.n_cells, pr.n_dofs, pr.P = pa.n_cells, pa.N, pa.P
         keep = [pa.cell_vertices, pa.cell_tag, pa.cell_dofs, pa.cell_neighbors,
-                pa.cell_jump_mask, pa.csr.rowptr, pa.csr.rank_own, pa.csr.rank_fac,
+                pa.cell_jump_mask, pa.csr.rowptr, pa.csr.patterns, pa.csr.cell_pattern,
                 pa.tag_params, pa.bc_dofs, pa.natbc_cell, pa.natbc_row]
         (pr.h_cell_vertices, pr.h_cell_tag, pr.h_cell_dofs, pr.h_cell_neighbors,
-         pr.h_cell_jump_mask, pr.h_rowptr, pr.h_rank_own, pr.h_rank_fac,
+         pr.h_cell_jump_mask, pr.h_rowptr, pr.h_patterns, pr.h_cell_pattern,
          pr.h_tag_params, pr.h_bc_dofs, pr.h_natbc_cell, pr.h_natbc_row) = \
             [_hp(np.ascontiguousarray(a)) for a in keep]
+        pr.n_patterns = pa.csr.patterns.shape[0]
         pr.n_bc = len(pa.bc_dofs)
         pr.n_natbc = len(pa.natbc_cell)
         pr.h_tables = C.cast(C.pointer(tables), C.c_void_p)

@@ -88,6 +88,8 @@ class CsrStructure(object):
     position of local column j in the rows of the dofs on local facet f
     (shared with the neighbour across f, if any).  Position in ``vals`` of
     local entry (i, j) of cell c is ``rowptr[cell_dofs[c, i]] + rank``.
+    ``patterns[npat, 4, L]`` / ``cell_pattern[Nc]``: the same tables
+    de-duplicated (class 0 = own rows, 1..3 = rows on local facet 0..2).
     """
 
     def __init__(self, mesh, cell_dofs, P, N):
@@ -133,6 +135,12 @@ class CsrStructure(object):
                     rowlen[rows] = ncols
         self.rank_own = rank_own
         self.rank_fac = np.ascontiguousarray(rank_fac)
+        # cells with identical rank tables share one pattern (a product mesh has
+        # a handful): the kernels look ranks up in this small table
+        tab = np.concatenate([rank_own[:, None, :], self.rank_fac], axis=1).reshape(nc, 4 * L)
+        pats, inv = np.unique(tab, axis=0, return_inverse=True)
+        self.patterns = np.ascontiguousarray(pats.reshape(-1, 4, L))
+        self.cell_pattern = np.ascontiguousarray(inv.reshape(-1).astype(np.int32))
         self.rowptr = np.zeros(N + 1, dtype=np.int64)
         np.cumsum(rowlen, out=self.rowptr[1:])
         self.nnz = int(self.rowptr[-1])
