@@ -34,9 +34,11 @@
 #if defined(__CUDACC__)
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_D __device__ __forceinline__
+#define SB_NOINLINE __host__ __device__ __noinline__
 #else
 #define SB_HD inline
 #define SB_D inline
+#define SB_NOINLINE inline
 #endif
 
 #define SB_MAXL (15 * (1 + SB_MAX_BANDS))
@@ -103,6 +105,20 @@ SB_HD SbBandK sb_band_consts(const sb_model& M, const double* tp, int k) {
   return K;
 }
 
+/* IB with filling-dependent mobility mu = mu0 [(1-f) - 1/2 f^0.33 (1-f)^1.33]
+ * (poisson_drift_diffusion1.py1:228-231); out of line: pow() is bulky and this
+ * is the rarely used model (use_constant_mobility = False)                  */
+SB_NOINLINE void sb_ib_fill_mobility(double mob, double N, double dd_scale, double sbeta,
+                                     double f, double omf, double* c, double* dc) {
+  const double df = -sbeta * f * omf;       /* df/dchi */
+  const double fa = pow(f, 0.33), ob = pow(omf, 1.33);
+  const double mu = mob * (omf - 0.5 * fa * ob);
+  const double dmu = mob * (-df - 0.5 * (0.33 * fa / f * df * ob
+                                          + fa * 1.33 * ob / omf * (-df)));
+  *c = dd_scale / (mu * N * f);
+  *dc = -(*c) * (dmu / mu + df / f);
+}
+
 /* Pointwise band quantities at chi = e phi + w (band statistics
  * poisson_drift_diffusion1.py1:170-245):
  *   su = s u / eps, dsu = d(su)/dchi, c = dd_scale / (mu u), dc = dc/dchi   */
@@ -124,14 +140,7 @@ SB_HD void sb_band_point(const SbBandK& K, double chi,
       c = K.cinv * (1.0 + e);
       dc = K.cinv * K.sbeta * e;
     } else {
-      /* mu = mu0 [(1-f) - 1/2 f^0.33 (1-f)^1.33]  (:228-231) */
-      const double df = -K.sbeta * f * omf;   /* df/dchi */
-      const double fa = pow(f, 0.33), ob = pow(omf, 1.33);
-      const double mu = K.mob * (omf - 0.5 * fa * ob);
-      const double dmu = K.mob * (-df - 0.5 * (0.33 * fa / f * df * ob
-                                               + fa * 1.33 * ob / omf * (-df)));
-      c = K.dd_scale / (mu * K.N * f);
-      dc = -c * (dmu / mu + df / f);
+      sb_ib_fill_mobility(K.mob, K.N, K.dd_scale, K.sbeta, f, omf, &c, &dc);
     }
   }
 }
@@ -281,7 +290,7 @@ SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff,
 }
 
 /* g_k and its partials w.r.t. phi and every w_l at one point */
-SB_HD void sb_generation(const sb_model& M, const double* tp, int k,
+SB_NOINLINE void sb_generation(const sb_model& M, const double* tp, int k,
                          const SbBandsAtPoint& B, const double* phi_clip,
                          double& g, double& dphi, double* dw) {
   g = 0.0; dphi = 0.0;
@@ -493,14 +502,14 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
   const int r0 = sb_lbdm(p, 0);
   double F[12];
   int64_t rb[12];
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
   for (int i = 0; i < 12; ++i) { F[i] = 0.0; rb[i] = io.rowptr[io.dofs[r0 + i]]; }
   if (is_band && inside) {
     /* <xi_i . xi_m c>: symmetric, 78 pairs x 45 FMAs on warp-uniform constants */
     int pair = 0;
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
     for (int i = 0; i < 12; ++i)
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
       for (int m = i; m < 12; ++m, ++pair) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
@@ -518,9 +527,9 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
         }
       }
     /* <div xi_i delta_w> + <xi_i . j dc/dchi lam_l> */
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
     for (int i = 0; i < 12; ++i) {
-#pragma unroll (SP ? 1 : 3)
+#pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         double d = 0.0;
 #pragma unroll
@@ -538,9 +547,9 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
     /* polynomial mass block: Poisson <psi.E> (scale 1) or the out-of-subdomain
        penalty <j.xi> c2 (poisson_drift_diffusion1.py1:288-289)               */
     const double sc = (is_band ? M.ext_j_coef : 1.0) * g.iad;
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
     for (int i = 0; i < 12; ++i)
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
       for (int m = i; m < 12; ++m) {
         const double v = sc * (g.G11 * T.Mhat[i][m][0] + g.G12 * T.Mhat[i][m][1]
                                + g.G22 * T.Mhat[i][m][2]);
@@ -553,9 +562,9 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
       }
     if (!is_band) {
       /* - <div psi_i phi> */
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
       for (int i = 0; i < 12; ++i)
-#pragma unroll (SP ? 1 : 3)
+#pragma unroll 1
         for (int l = 0; l < 3; ++l) {
           const double dv = -g.sdet * T.Dhat[i][l];
           F[i] += dv * sl[l];
@@ -564,7 +573,7 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
     }
   }
   if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 12, F);
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
   for (int i = 0; i < 12; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 
@@ -581,12 +590,12 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
   const int r0 = sb_ldg(p, 0);
   double F[3] = {0.0, 0.0, 0.0};
   int64_t rb[3];
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
   for (int i = 0; i < 3; ++i) rb[i] = io.rowptr[io.dofs[r0 + i]];
   if (inside) {
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
     for (int i = 0; i < 3; ++i) {
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
       for (int m = 0; m < 12; ++m) {            /* <v_i div j> */
         const double dv = g.sdet * T.Dhat[m][i];
         F[i] += dv * fl[m];
@@ -594,9 +603,9 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
       }
 #pragma unroll
       for (int t = 0; t < 3; ++t) F[i] += coef * T.G1[i][t] * mom1[t];
-#pragma unroll (SP ? 1 : 8)
+#pragma unroll 1
       for (int q = 0; q < NQ; ++q)
-#pragma unroll (SP ? 1 : 3)
+#pragma unroll 1
         for (int l = 0; l < 3; ++l) {
           double v = 0.0;
 #pragma unroll
@@ -607,9 +616,9 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
   } else {
     /* out-of-subdomain penalty <delta_w v> c1 (:285-286) */
     const double c1 = M.ext_w_coef * g.adet;
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
     for (int i = 0; i < 3; ++i)
-#pragma unroll (SP ? 1 : 3)
+#pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         const double v = c1 * T.M1[i][l];
         F[i] += v * sl[l];
@@ -617,7 +626,7 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
       }
   }
   if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 3, F);
-#pragma unroll (SP ? 1 : 12)
+#pragma unroll 1
   for (int i = 0; i < 3; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 

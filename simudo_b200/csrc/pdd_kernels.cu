@@ -117,10 +117,10 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
  * per-cell index data and the scatter.  NB = number of bands with dofs
  * (compile-time so every per-band array stays in registers); SP = the cell has
  * Dirichlet dofs (rare; kept on a compact rolled code path).                  */
-template <int NB, bool SP>
+template <int NB>
 __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev& st,
                                               double* vals, double* b, int64_t c, SbIO& io,
-                                              int nb0, int nb1) {
+                                              int nb0, int nb1, const bool sp) {
   const int nb = pl.nb;                       /* bands entering rho */
   const int L = pl.L;
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
@@ -154,9 +154,8 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
   const bool std_rule = same_rule && (c_M.quad_m_super == 11);
   bool inside_k[SB_MAX_BANDS] = {false, false, false, false};
 
-#pragma unroll
-  for (int k = 0; k < SB_MAX_BANDS; ++k) {
-    if (k >= nb) break;
+#pragma unroll 1
+  for (int k = 0; k < nb; ++k) {
     const SbBandK K = sb_band_consts(c_M, tp, k);
     const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
     const bool dd = inside && (k < NB);
@@ -216,8 +215,12 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
           jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
         }
       }
-      sb_rows_flux<SP>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
-                       pl.natbc_row, st.natbc_values, nb0, nb1);
+      if (sp)
+        sb_rows_flux<true>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+                           pl.natbc_row, st.natbc_values, nb0, nb1);
+      else
+        sb_rows_flux<false>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+                            pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
 
@@ -227,14 +230,18 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
     sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k,
                       st.thmeq ? st.thmeq + c * 6 : nullptr,
                       st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < NB; ++k) {
       double fl[12];
 #pragma unroll
       for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
       const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-      sb_rows_scalar<SP, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
-                                 mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
+      if (sp)
+        sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
+                                     mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
+      else
+        sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
+                                      mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
 
@@ -245,10 +252,17 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
     double fl[12];
 #pragma unroll
     for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
-    sb_rows_scalar<SP, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
-                               pl.natbc_row, st.natbc_values, nb0, nb1);
-    sb_rows_flux<SP>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
-                     pl.natbc_row, st.natbc_values, nb0, nb1);
+    if (sp) {
+      sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
+                                   pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<true>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+                         pl.natbc_row, st.natbc_values, nb0, nb1);
+    } else {
+      sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
+                                    pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<false>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+                          pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
   }
 }
 
@@ -273,8 +287,7 @@ k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
     io.bcidx = pl.sp_bcidx + (int64_t)sp * L;
     nb0 = pl.sp_nat_begin[sp]; nb1 = pl.sp_nat_begin[sp + 1];
   }
-  if (io.mlo | io.mhi) assemble_cell<NB, true>(pl, st, vals, b, c, io, nb0, nb1);
-  else assemble_cell<NB, false>(pl, st, vals, b, c, io, nb0, nb1);
+  assemble_cell<NB>(pl, st, vals, b, c, io, nb0, nb1, (io.mlo | io.mhi) != 0);
 }
 
 /* ------------------------------------------------------------------------- */
