@@ -78,6 +78,10 @@ SB_HD int sb_local_facet(int l) {
   return (r >= 3 && r < 12) ? (r - 3) / 3 : -1;
 }
 
+SB_HD constexpr int sb_sym21(int r, int s) {      /* packed index of the (r, s) pair, 6 x 6 symmetric */
+  return (r <= s) ? (r * 6 - (r * (r - 1)) / 2 + (s - r)) : (s * 6 - (s * (s - 1)) / 2 + (r - s));
+}
+
 /* Per (cell, band) constants hoisted out of the quadrature loops. */
 struct SbBandK {
   int kind, const_mob;
@@ -491,90 +495,115 @@ SB_HD void sb_add_natbc(const int32_t* nat_row, const double* nat_val, int b0, i
  * indices compile-time: table operands become constant-bank immediates, rank
  * loads get immediate offsets) and kept rolled on the rare Dirichlet path.    */
 
-/* ---- rows psi (Poisson) / xi^k (band k): BDM test functions ------------------ */
+/* ---- rows psi (Poisson) / xi^k (band k): BDM test functions ------------------ *
+ * One row at a time, nothing indexed dynamically except the row itself:
+ *   <xi_i . xi_m c> = iad sum_{b,s} GY_i[b][s] C[m][b][s],
+ *   GY_i = G (C_i W),  W_rs = int c pi_r pi_s = sum_t G22u[rs][t] mC[t]
+ * (orthonormal Dubiner basis: W = identity reproduces the plain BDM mass
+ * matrix, used for the Poisson <psi.E> block and the out-of-subdomain penalty
+ * <j.xi> c2, poisson_drift_diffusion1.py1:288-289).
+ *   <xi_i . j dc/dchi lam_l> = iad sum_{a,r} C_i[a][r] V_a[r][l],
+ *   V_a[r][l] = sum_t G21[r][l][t] Q_a[t].
+ * mode 0: Poisson psi rows; 1: band inside its subdomain; 2: band outside.    */
 template <bool SP>
 SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
-                        const SbCellGeom& g, int p, bool is_band, bool inside,
+                        const SbCellGeom& g, int p, int mode,
                         const double* mC, const double* Q,
                         const double* fl /*[12] flux dofs*/, const double* sl /*[3] scalar dofs*/,
-                        const double* jumpf /*[3] or NULL*/,
+                        double jump0, double jump1, double jump2,
                         const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
   const int r0 = sb_lbdm(p, 0);
-  double F[12];
-  int64_t rb[12];
-#pragma unroll 1
-  for (int i = 0; i < 12; ++i) { F[i] = 0.0; rb[i] = io.rowptr[io.dofs[r0 + i]]; }
-  if (is_band && inside) {
-    /* <xi_i . xi_m c>: symmetric, 78 pairs x 45 FMAs on warp-uniform constants */
-    int pair = 0;
-#pragma unroll 1
-    for (int i = 0; i < 12; ++i)
-#pragma unroll 1
-      for (int m = i; m < 12; ++m, ++pair) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  double W[21];
+  double V[2][6][3];
+  if (mode == 1) {
 #pragma unroll
-        for (int t = 0; t < 15; ++t) {
-          a0 += mC[t] * T.TB[pair][0][t];
-          a1 += mC[t] * T.TB[pair][1][t];
-          a2 += mC[t] * T.TB[pair][2][t];
-        }
-        const double v = (g.G11 * a0 + g.G12 * a1 + g.G22 * a2) * g.iad;
-        F[i] += v * fl[m];
-        sb_emit<SP>(io, rb[i], r0 + i, r0 + m, v, F[i]);
-        if (m != i) {
-          F[m] += v * fl[i];
-          sb_emit<SP>(io, rb[m], r0 + m, r0 + i, v, F[m]);
-        }
-      }
-    /* <div xi_i delta_w> + <xi_i . j dc/dchi lam_l> */
-#pragma unroll 1
-    for (int i = 0; i < 12; ++i) {
-#pragma unroll 1
-      for (int l = 0; l < 3; ++l) {
-        double d = 0.0;
+    for (int e = 0; e < 21; ++e) {
+      double v = 0.0;
 #pragma unroll
-        for (int t = 0; t < 10; ++t)
-          d += T.TD[i][l][0][t] * Q[t] + T.TD[i][l][1][t] * Q[10 + t];
-        d *= g.iad;
-        const double dv = g.sdet * T.Dhat[i][l];
-        F[i] += dv * sl[l];
-        sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(p, l), dv + d, F[i]);
-        sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(0, l), d, F[i]);
-      }
-      if (jumpf && i < 9) F[i] -= jumpf[i / 3] * T.trI[i % 3];   /* facet dofs only */
+      for (int t = 0; t < 15; ++t) v += T.G22u[e][t] * mC[t];
+      W[e] = v;
     }
-  } else {
-    /* polynomial mass block: Poisson <psi.E> (scale 1) or the out-of-subdomain
-       penalty <j.xi> c2 (poisson_drift_diffusion1.py1:288-289)               */
-    const double sc = (is_band ? M.ext_j_coef : 1.0) * g.iad;
-#pragma unroll 1
-    for (int i = 0; i < 12; ++i)
-#pragma unroll 1
-      for (int m = i; m < 12; ++m) {
-        const double v = sc * (g.G11 * T.Mhat[i][m][0] + g.G12 * T.Mhat[i][m][1]
-                               + g.G22 * T.Mhat[i][m][2]);
-        F[i] += v * fl[m];
-        sb_emit<SP>(io, rb[i], r0 + i, r0 + m, v, F[i]);
-        if (m != i) {
-          F[m] += v * fl[i];
-          sb_emit<SP>(io, rb[m], r0 + m, r0 + i, v, F[m]);
-        }
-      }
-    if (!is_band) {
-      /* - <div psi_i phi> */
-#pragma unroll 1
-      for (int i = 0; i < 12; ++i)
-#pragma unroll 1
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
         for (int l = 0; l < 3; ++l) {
-          const double dv = -g.sdet * T.Dhat[i][l];
-          F[i] += dv * sl[l];
-          sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(0, l), dv, F[i]);
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * Q[a * 10 + t];
+          V[a][r][l] = v;
         }
-    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int s2 = r; s2 < 6; ++s2) W[sb_sym21(r, s2)] = (r == s2) ? 1.0 : 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) V[a][r][l] = 0.0;
   }
-  if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 12, F);
+  const double sc = (mode == 2 ? M.ext_j_coef : 1.0) * g.iad;
+  const double divsign = (mode == 0) ? -g.sdet : g.sdet;   /* -<div psi phi> | +<div xi dw> */
 #pragma unroll 1
-  for (int i = 0; i < 12; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
+  for (int i = 0; i < 12; ++i) {
+    double Ci[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ci[a][r] = T.bdmC[i][a][r];
+    /* GY[b][s] = sum_a G_ab sum_r C_i[a][r] W_rs */
+    double GY[2][6];
+#pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+      double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        y0 += Ci[0][r] * W[sb_sym21(r, s2)];
+        y1 += Ci[1][r] * W[sb_sym21(r, s2)];
+      }
+      GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
+      GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
+    }
+    const int li = r0 + i;
+    const int64_t rowbase = io.rowptr[io.dofs[li]];
+    double Fi = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      double v = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2)
+        v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
+      Fi += v * fl[m];
+      sb_emit<SP>(io, rowbase, li, r0 + m, v, Fi);
+    }
+    if (mode != 2) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double dv = divsign * T.Dhat[i][l];
+        Fi += dv * sl[l];
+        if (mode == 1) {
+          double d = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
+          d *= g.iad;
+          sb_emit<SP>(io, rowbase, li, sb_ldg(p, l), dv + d, Fi);
+          sb_emit<SP>(io, rowbase, li, sb_ldg(0, l), d, Fi);
+        } else {
+          sb_emit<SP>(io, rowbase, li, sb_ldg(0, l), dv, Fi);
+        }
+      }
+    }
+    if (mode == 1 && i < 9) {                      /* base_w jump: facet dofs only */
+      const double jf = (i < 3) ? jump0 : (i < 6 ? jump1 : jump2);
+      Fi -= jf * T.trI[i % 3];
+    }
+    if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, li, 1, &Fi);
+    sb_put_row<SP>(io, li, Fi);
+  }
 }
 
 /* ---- rows of the DG1 test functions: w (Poisson, p = 0) or v^k (p = 1 + k) ---- *

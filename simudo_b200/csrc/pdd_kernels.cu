@@ -215,11 +215,14 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
           jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
         }
       }
+      const int mode = inside ? 1 : 2;
       if (sp)
-        sb_rows_flux<true>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+        sb_rows_flux<true>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
+                           jumpf[0], jumpf[1], jumpf[2],
                            pl.natbc_row, st.natbc_values, nb0, nb1);
       else
-        sb_rows_flux<false>(c_T, c_M, io, g, 1 + k, true, inside, mC, Q, fl, dgv[1 + k], jumpf,
+        sb_rows_flux<false>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
+                            jumpf[0], jumpf[1], jumpf[2],
                             pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
@@ -255,19 +258,22 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
     if (sp) {
       sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
                                    pl.natbc_row, st.natbc_values, nb0, nb1);
-      sb_rows_flux<true>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+      sb_rows_flux<true>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
                          pl.natbc_row, st.natbc_values, nb0, nb1);
     } else {
       sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
                                     pl.natbc_row, st.natbc_values, nb0, nb1);
-      sb_rows_flux<false>(c_T, c_M, io, g, 0, false, true, nullptr, nullptr, fl, dgv[0], nullptr,
+      sb_rows_flux<false>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
                           pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
 }
 
+#ifndef SB_MIN_BLOCKS
+#define SB_MIN_BLOCKS 2
+#endif
 template <int NB>
-__global__ void __launch_bounds__(SB_TILE)
+__global__ void __launch_bounds__(SB_TILE, SB_MIN_BLOCKS)
 k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;

@@ -28,11 +28,8 @@ typedef struct SbRule {
 
 typedef struct SbTables {
   double bdmC[12][2][6];  /* BDM2 nodal basis in Dubiner P2                      */
-  /* int c psi_i . psi_m = iad * sum_t m_t (G11 TB[.][0][t] + G12 TB[.][1][t]
-     + G22 TB[.][2][t]) for the moment vector m_t of c against Dubiner P4       */
-  double TB[SB_NPAIR][3][15];
-  /* int c' (psi_i . g) lam_l = iad * sum_a sum_t TD[i][l][a][t] Q_a[t]          */
-  double TD[12][3][2][10];
+  double G22u[21][15];    /* int Psi_t pi_r pi_s, (r<=s) packed                  */
+  double G21[6][3][10];   /* int Psi_t pi_r lam_l                                */
   double G11[3][3][6];    /* int Psi_t lam_i lam_j                               */
   double G1[3][3];        /* int Psi_t lam_i                                     */
   double Mhat[12][12][3]; /* int psi_i^a psi_j^b: (11, 12+21, 22)                */

@@ -23,8 +23,8 @@ class SbRule(C.Structure):
 
 class SbTables(C.Structure):
     _fields_ = [('bdmC', ((C.c_double * 6) * 2) * 12),
-                ('TB', ((C.c_double * 15) * 3) * 78),
-                ('TD', (((C.c_double * 10) * 2) * 3) * 12),
+                ('G22u', (C.c_double * 15) * 21),
+                ('G21', ((C.c_double * 10) * 3) * 6),
                 ('G11', ((C.c_double * 6) * 3) * 3),
                 ('G1', (C.c_double * 3) * 3),
                 ('Mhat', ((C.c_double * 3) * 12) * 12),
@@ -61,19 +61,9 @@ def pack_tables(model):
     T = reference_tables()
     t = SbTables()
     _set(t.bdmC, T.bdm_C)
-    Cb = T.bdm_C                                           # [12, 2, 6]
-    # A^{ab}_{im,t} = sum_rs C[i,a,r] C[m,b,s] G22[r,s,t]
-    A = np.einsum('iar,mbs,rst->imabt', Cb, Cb, T.G22)
-    TB = np.zeros((78, 3, 15))
-    pair = 0
-    for i in range(12):
-        for m in range(i, 12):
-            TB[pair, 0] = A[i, m, 0, 0]
-            TB[pair, 1] = A[i, m, 0, 1] + A[i, m, 1, 0]
-            TB[pair, 2] = A[i, m, 1, 1]
-            pair += 1
-    _set(t.TB, TB)
-    _set(t.TD, np.einsum('iar,rlt->ilat', Cb, T.G21))
+    iu = [(r, s) for r in range(6) for s in range(r, 6)]
+    _set(t.G22u, np.stack([T.G22[r, s] for r, s in iu]))
+    _set(t.G21, T.G21)
     _set(t.G11, T.G11)
     _set(t.G1, T.G1)
     M = T.bdm_mass
