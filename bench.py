@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument('--nx', type=int, default=708, help='x points of the product mesh')
     ap.add_argument('--ny', type=int, default=708, help='y points per rank strip')
     ap.add_argument('--kind', default='ib', choices=['ib', 'pn'])
+    ap.add_argument('--pattern', default='structural', choices=['structural', 'dolfin'],
+                    help='CSR layout: structural non-zeros only (native) or dolfin dense cell blocks')
     ap.add_argument('--cpu-cells', type=int, default=40000,
                     help='cells of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -106,10 +108,10 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def make_problem(kind, nx, ny):
+def make_problem(kind, nx, ny, pattern='structural'):
     from simudo_b200 import synthetic as syn
     mk = syn.ib_problem if kind == 'ib' else syn.pn_problem
-    pa = mk(nx=nx, ny=ny)
+    pa = mk(nx=nx, ny=ny, pattern=pattern)
     st = syn.synthetic_state(pa)
     return pa, st
 
@@ -200,7 +202,7 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
 
     from simudo_b200.fem.assembly import AssemblyPlan
-    pa, st = make_problem(args.kind, args.nx, args.ny)
+    pa, st = make_problem(args.kind, args.nx, args.ny, args.pattern)
     plan = AssemblyPlan(pa, device=dev)
     plan.set_profiling(True)
     T = plan.tensor
@@ -318,7 +320,8 @@ def run_b200(args):
                          '(BASELINE configs[3])' % (args.kind, len(np.unique(pa.mesh.coordinates[:, 0])), args.ny),
                 cells_per_gpu=pa.n_cells, dofs_per_gpu=pa.N, nnz_per_gpu=pa.csr.nnz,
                 sub_problems=pa.P, local_dofs=pa.L, optical_fields=pa.model.n_fields,
-                pattern='dolfin dense cell blocks', numbering=pa.numbering,
+                pattern=('structural non-zeros of the dolfin cell blocks' if pa.pattern == 'structural'
+                         else 'dolfin dense cell blocks'), numbering=pa.numbering,
                 parallelism='y-strips x%d, NCCL halo exchange' % world if world > 1 else 'single GPU',
                 l2='inputs (%.0f MB) and outputs (%.1f GB) far exceed the 126 MB L2'
                    % (h2d / 1e6, (alg_bytes) / 1e9),

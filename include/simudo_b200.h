@@ -120,13 +120,12 @@ typedef struct sb_problem {
   const uint8_t* h_cell_jump_mask;/* [n_cells][3] bit b set: base_w jump term of   */
                                   /* band b on this (interior) facet, and this     */
                                   /* cell is its '+' side                          */
-  const int64_t* h_rowptr;        /* [N+1] dolfin-pattern CSR row pointers         */
-  /* position of local column j inside a row of class k (0: rows owned by the    */
-  /* cell alone; 1..3: rows of the dofs on local facet 0..2, shared with the     */
-  /* neighbour): vals index = rowptr[row] + patterns[cell_pattern[c]][k][j];     */
-  /* 0xFF = entry absent from a compacted pattern                                */
+  const int64_t* h_rowptr;        /* [N+1] CSR row pointers (dolfin or structural) */
+  /* position of local entry (i, j) inside global row cell_dofs[c][i]:           */
+  /* vals index = rowptr[row] + patterns[cell_pattern[c]][i][j]; 0xFF = the      */
+  /* entry is absent (structural zero dropped from a compacted pattern)          */
   int64_t n_patterns;
-  const uint8_t* h_patterns;      /* [n_patterns][4][L]                            */
+  const uint8_t* h_patterns;      /* [n_patterns][L][L]                            */
   const int32_t* h_cell_pattern;  /* [n_cells]                                     */
   const double*  h_tag_params;    /* [n_tags][SB_TAG_STRIDE]                       */
   /* essential (Dirichlet) conditions: constrained global dofs, sorted ascending   */

@@ -422,7 +422,7 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
 struct SbIO {
   int L;
   const int32_t* dofs;       /* [L] global dofs of this cell                */
-  const uint8_t* pat;        /* [4][L] rank pattern of this cell            */
+  const uint8_t* pat;        /* [L][L] rank pattern of this cell            */
   const int64_t* rowptr;
   const double* u;
   const double* bc_values;
@@ -464,7 +464,7 @@ SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, do
   }
   if (!io.vals) return;
   const int fi = sb_local_facet(i);
-  const int rk = io.pat[(fi + 1) * io.L + j];
+  const int rk = io.pat[i * io.L + j];
   if (rk == 0xFF) return;                 /* not in a compacted pattern */
   double* dst = io.vals + rowbase + rk;
   /* two cells add into the same slot only for (facet dof, facet dof) pairs of

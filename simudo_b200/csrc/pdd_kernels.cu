@@ -52,7 +52,7 @@ struct PlanDev {
   const int32_t* cell_neighbors;
   const uint8_t* cell_jump_mask;
   const int64_t* rowptr;
-  const uint8_t* patterns;       /* [n_patterns][4][L]                       */
+  const uint8_t* patterns;       /* [n_patterns][L][L]                       */
   const int32_t* cell_pattern;   /* [n_cells]                                */
   const double* tag_params;
   const int32_t* cell_special;   /* [n_cells] -1 or special index            */
@@ -94,7 +94,7 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
   if (c >= pl.n_cells) return;
   const int L = pl.L;
   const int32_t* dofs = pl.cell_dofs + c * L;
-  const uint8_t* rf = pl.patterns + ((int64_t)pl.cell_pattern[c] * 4 + 1) * L;
+  const uint8_t* pat = pl.patterns + (int64_t)pl.cell_pattern[c] * L * L;
   for (int p = 0; p < pl.P; ++p)
     for (int f = 0; f < 3; ++f)
       for (int k = 0; k < 3; ++k) {
@@ -104,7 +104,7 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
         if (vals) {
           const int64_t r0 = pl.rowptr[row];
           for (int k2 = 0; k2 < 3; ++k2) {
-            const uint8_t rk = rf[f * L + sb_lbdm(p, 3 * f + k2)];
+            const uint8_t rk = pat[li * L + sb_lbdm(p, 3 * f + k2)];
             if (rk != 0xFF) vals[r0 + rk] = 0.0;
           }
         }
@@ -281,7 +281,7 @@ k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
   SbIO io;
   io.L = L;
   io.dofs = pl.cell_dofs + c * L;
-  io.pat = pl.patterns + (int64_t)pl.cell_pattern[c] * 4 * L;
+  io.pat = pl.patterns + (int64_t)pl.cell_pattern[c] * L * L;
   io.rowptr = pl.rowptr;
   io.u = st.u; io.bc_values = st.bc_values;
   io.vals = vals; io.b = b;
@@ -303,8 +303,7 @@ __global__ void k_colidx(PlanDev pl, int32_t* col) {
   const int32_t* dofs = pl.cell_dofs + c * L;
   for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
     const int i = e / L, j = e % L;
-    const int fi = sb_local_facet(i);
-    const uint8_t rk = pl.patterns[((int64_t)pl.cell_pattern[c] * 4 + fi + 1) * L + j];
+    const uint8_t rk = pl.patterns[((int64_t)pl.cell_pattern[c] * L + i) * L + j];
     if (rk != 0xFF) col[pl.rowptr[dofs[i]] + rk] = dofs[j];
   }
 }
@@ -501,7 +500,7 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   UP(cell_neighbors, pr->h_cell_neighbors, nc * 3);
   UP(cell_jump_mask, pr->h_cell_jump_mask, nc * 3);
   UP(rowptr, pr->h_rowptr, N + 1);
-  UP(patterns, pr->h_patterns, pr->n_patterns * 4 * L);
+  UP(patterns, pr->h_patterns, pr->n_patterns * L * L);
   UP(cell_pattern, pr->h_cell_pattern, nc);
   UP(tag_params, pr->h_tag_params, (size_t)model->n_tags * SB_TAG_STRIDE);
   UP(tables, &pl->tables, 1);

@@ -28,7 +28,7 @@ position map.
 """
 import numpy as np
 
-__all__ = ['local_layout', 'build_cell_dofs', 'CsrStructure']
+__all__ = ['local_layout', 'build_cell_dofs', 'structural_mask', 'CsrStructure']
 
 
 def local_layout(P):
@@ -80,104 +80,176 @@ def build_cell_dofs(mesh, P, numbering='b200'):
     return np.ascontiguousarray(cd.astype(np.int32)), N
 
 
-class CsrStructure(object):
-    """Row pointers + per-cell rank tables of the dolfin-pattern CSR.
+def structural_mask(P):
+    """S[i, j] = True iff local entry (i, j) of the element tensor can be
+    non-zero for the Poisson / drift-diffusion form:
 
-    ``rowptr[N+1]`` int64; ``rank_own[Nc, L]`` uint8 = position of local
-    column j in a row owned by this cell alone; ``rank_fac[Nc, 3, L]`` uint8 =
-    position of local column j in the rows of the dofs on local facet f
-    (shared with the neighbour across f, if any).  Position in ``vals`` of
-    local entry (i, j) of cell c is ``rowptr[cell_dofs[c, i]] + rank``.
-    ``patterns[npat, 4, L]`` / ``cell_pattern[Nc]``: the same tables
-    de-duplicated (class 0 = own rows, 1..3 = rows on local facet 0..2).
+    * w   rows (Poisson DG1):  E, phi, every delta_w_k
+    * psi rows (Poisson BDM2): E, phi
+    * v^k rows (band DG1):     j_k, phi, every delta_w_l
+    * xi^k rows (band BDM2):   j_k, delta_w_k, phi
+    """
+    L = 15 * P
+    S = np.zeros((L, L), dtype=bool)
+    dg = lambda p: slice(15 * p, 15 * p + 3)
+    bdm = lambda p: slice(15 * p + 3, 15 * p + 15)
+    for p in range(P):
+        S[dg(p), bdm(p)] = True
+        S[dg(p), dg(0)] = True
+        for q in range(1, P):
+            S[dg(p), dg(q)] = True
+        S[bdm(p), bdm(p)] = True
+        S[bdm(p), dg(p)] = True
+        S[bdm(p), dg(0)] = True
+    return S
+
+
+class CsrStructure(object):
+    """Row pointers + rank patterns of the fixed CSR.
+
+    ``pattern='dolfin'``     dolfin's sparsity (Appendix A11): the full L x L
+                             product of every cell's dofs.
+    ``pattern='structural'`` the same matrix with the structural zeros of the
+                             form dropped (``structural_mask``): what the
+                             device path stores natively -- rows become
+                             contiguous runs of values that are all written.
+
+    ``rowptr[N+1]`` int64.  The position in ``vals`` of local entry (i, j) of
+    cell c is ``rowptr[cell_dofs[c, i]] + patterns[cell_pattern[c], i, j]``
+    (0xFF = absent).  Because DG1 and BDM2 have no vertex dofs a row is shared
+    by at most two cells, and the rank tables of all cells fall into a
+    handful of distinct patterns (8 on a product mesh).
     """
 
-    def __init__(self, mesh, cell_dofs, P, N):
+    def __init__(self, mesh, cell_dofs, P, N, pattern='dolfin'):
         mesh.init()
-        self.P, self.N = P, N
+        self.P, self.N, self.pattern = P, N, pattern
         L = 15 * P
         self.L = L
         nc = mesh.num_cells
-        cd = np.asarray(cell_dofs)
-        lay = local_layout(P)
-        is_facet_local = np.zeros(L, dtype=bool)
-        is_facet_local[lay['facet'].ravel()] = True
+        cd = np.asarray(cell_dofs).astype(np.int64)
+        self._cd = cd
+        self._mesh = mesh
+        if pattern == 'dolfin':
+            S = np.ones((L, L), dtype=bool)
+        elif pattern == 'structural':
+            S = structural_mask(P)
+        else:
+            raise ValueError(pattern)
+        self.mask = S
+        nbr = mesh.cell_to_cells_adjacency_via_facet().astype(np.int64)   # [Nc, 3]
+        # local facet number of the shared facet inside the neighbour
+        fl_of = np.full((nc, 3), -1, dtype=np.int64)
+        fc, fl = mesh.facet_cells, mesh.facet_local.astype(np.int64)
+        interior = fc[:, 1] >= 0
+        fl_of[fc[interior, 0], fl[interior, 0]] = fl[interior, 1]
+        fl_of[fc[interior, 1], fl[interior, 1]] = fl[interior, 0]
+        self._nbr, self._fl_of = nbr, fl_of
 
-        # rows owned by a single cell: rank within the cell's sorted dofs
-        order = np.argsort(cd, axis=1, kind='stable')
-        rank_own = np.empty((nc, L), dtype=np.uint8)
-        np.put_along_axis(rank_own, order,
-                          np.broadcast_to(np.arange(L, dtype=np.uint8), (nc, L)), axis=1)
-
-        rank_fac = np.repeat(rank_own[:, None, :], 3, axis=1)
-        fc = mesh.facet_cells
-        fl = mesh.facet_local
-        interior = np.nonzero(fc[:, 1] >= 0)[0]
-        rowlen = np.full(N, L, dtype=np.int64)
-        if interior.size:
-            c0, c1 = fc[interior, 0], fc[interior, 1]
-            both = np.concatenate([cd[c0], cd[c1]], axis=1)         # [nfi, 2L]
-            o = np.argsort(both, axis=1, kind='stable')
-            vs = np.take_along_axis(both, o, axis=1)
-            newv = np.ones(vs.shape, dtype=np.int64)
-            newv[:, 0] = 0
-            newv[:, 1:] = vs[:, 1:] != vs[:, :-1]
-            rs = np.cumsum(newv, axis=1)
-            r = np.empty_like(rs)
-            np.put_along_axis(r, o, rs, axis=1)
-            ncols = rs[:, -1] + 1
-            rank_fac[c0, fl[interior, 0].astype(np.int64), :] = r[:, :L].astype(np.uint8)
-            rank_fac[c1, fl[interior, 1].astype(np.int64), :] = r[:, L:].astype(np.uint8)
-            # row lengths of the shared facet dofs
-            for p in range(P):
-                for k in range(3):
-                    rows = cd[c0, lay['facet'][p, :, k][fl[interior, 0].astype(np.int64)]]
-                    rowlen[rows] = ncols
-        self.rank_own = rank_own
-        self.rank_fac = np.ascontiguousarray(rank_fac)
-        # cells with identical rank tables share one pattern (a product mesh has
-        # a handful): the kernels look ranks up in this small table
-        tab = np.concatenate([rank_own[:, None, :], self.rank_fac], axis=1).reshape(nc, 4 * L)
-        pats, inv = np.unique(tab, axis=0, return_inverse=True)
-        self.patterns = np.ascontiguousarray(pats.reshape(-1, 4, L))
+        rowlen = np.zeros(N, dtype=np.int64)
+        sig = np.zeros(nc, dtype=np.uint64)
+        mult = np.uint64(0x9E3779B97F4A7C15)
+        allc = np.arange(nc)
+        with np.errstate(over='ignore'):
+            for i in range(L):
+                rep = self._row_type_representative(i)
+                if rep != i:
+                    # the three dofs of one (sub-problem, entity) share one column set
+                    rowlen[cd[:, i]] = rowlen[cd[:, rep]]
+                    continue
+                ranks, nrow = self._ranks_of_row(i, allc)
+                rowlen[cd[:, i]] = nrow
+                h = np.zeros(nc, dtype=np.uint64)
+                for col in range(ranks.shape[1]):
+                    h = h * mult + ranks[:, col].astype(np.uint64) + np.uint64(1)
+                sig = sig * np.uint64(0xC2B2AE3D27D4EB4F) + h
+        usig, first, inv = np.unique(sig, return_index=True, return_inverse=True)
         self.cell_pattern = np.ascontiguousarray(inv.reshape(-1).astype(np.int32))
+        pats = np.full((len(usig), L, L), 0xFF, dtype=np.uint8)
+        reps = first.astype(np.int64)
+        for i in range(L):
+            ranks, _ = self._ranks_of_row(i, reps)
+            pats[:, i, S[i]] = ranks.astype(np.uint8)
+        self.patterns = np.ascontiguousarray(pats)
         self.rowptr = np.zeros(N + 1, dtype=np.int64)
         np.cumsum(rowlen, out=self.rowptr[1:])
         self.nnz = int(self.rowptr[-1])
-        self._mesh = mesh
-        self._cd = cd
+        if self.patterns.shape[0] > 4096:
+            raise ValueError('too many distinct rank patterns for this mesh/numbering')
+
+    @staticmethod
+    def _row_type_representative(i):
+        """First local dof of the (sub-problem, entity) group local dof i belongs to."""
+        p, r = divmod(i, 15)
+        return 15 * p + (0 if r < 3 else 3 + 3 * ((r - 3) // 3))
+
+    def _row_facet(self, i):
+        r = i % 15
+        return (r - 3) // 3 if 3 <= r < 12 else -1
+
+    def _ranks_of_row(self, i, cells):
+        """Rank of each structural column of local row i inside its global row,
+        for the given cells: ``(ranks[len(cells), n_i], row_length[len(cells)])``."""
+        cd, L, S = self._cd, self.L, self.mask
+        cols = np.nonzero(S[i])[0]
+        own = cd[cells][:, cols]                              # [n, n_i]
+        f = self._row_facet(i)
+        n = len(cells)
+        if f < 0:
+            order = np.argsort(own, axis=1, kind='stable')
+            ranks = np.empty_like(order)
+            np.put_along_axis(ranks, order,
+                              np.broadcast_to(np.arange(len(cols)), own.shape), axis=1)
+            return ranks, np.full(n, len(cols), dtype=np.int64)
+        nb = self._nbr[cells, f]
+        has = nb >= 0
+        # the same global row seen from the neighbour: same sub-problem and facet
+        # dof number, on the neighbour's local facet fl_of
+        p, k = i // 15, (i % 15 - 3) % 3
+        other = np.full_like(own, np.iinfo(np.int64).max)
+        if has.any():
+            f2 = self._fl_of[cells[has], f]
+            i2 = 15 * p + 3 + 3 * f2 + k
+            # structural columns of a BDM row depend on the sub-problem only,
+            # up to which facet block is "its own": S rows of one sub-problem's
+            # BDM dofs are identical
+            assert (S[i2] == S[i]).all()
+            other[has] = cd[nb[has]][:, cols]
+        both = np.concatenate([own, other], axis=1)            # [n, 2 n_i]
+        o = np.argsort(both, axis=1, kind='stable')
+        vs = np.take_along_axis(both, o, axis=1)
+        newv = np.ones(vs.shape, dtype=np.int64)
+        newv[:, 0] = 0
+        newv[:, 1:] = vs[:, 1:] != vs[:, :-1]
+        rs = np.cumsum(newv, axis=1)
+        r = np.empty_like(rs)
+        np.put_along_axis(r, o, rs, axis=1)
+        valid = vs != np.iinfo(np.int64).max
+        nrow = (newv * valid).sum(axis=1) + 1
+        return r[:, :len(cols)], nrow
+
+    # -- views used by tests, the oracle driver and exports ----------------------
+    def entry_positions(self, cells=None):
+        """pos[c, i, j] into vals, -1 where absent (small meshes / tests only)."""
+        cd, L = self._cd, self.L
+        if cells is None:
+            cells = np.arange(cd.shape[0])
+        pat = self.patterns[self.cell_pattern[cells]].astype(np.int64)     # [n, L, L]
+        pos = self.rowptr[cd[cells]][:, :, None] + pat
+        pos[pat == 0xFF] = -1
+        return pos
 
     def column_indices(self):
         """Materialise ``colidx[nnz]`` (int32) -- for export / solvers / tests."""
         cd, L = self._cd, self.L
-        P = self.P
-        lay = local_layout(P)
         col = np.full(self.nnz, -1, dtype=np.int32)
         nc = cd.shape[0]
-        is_fac = np.zeros(L, dtype=np.int64) - 1
-        for f in range(3):
-            is_fac[lay['facet'][:, f, :].ravel()] = f
-        for i in range(L):
-            rows = cd[:, i].astype(np.int64)
-            f = is_fac[i]
-            ranks = self.rank_own if f < 0 else self.rank_fac[:, f, :]
-            pos = self.rowptr[rows][:, None] + ranks.astype(np.int64)
-            col[pos.ravel()] = cd.ravel()
+        step = max(1, (1 << 22) // (L * L))
+        for c0 in range(0, nc, step):
+            cells = np.arange(c0, min(nc, c0 + step))
+            pos = self.entry_positions(cells)
+            cols = np.broadcast_to(cd[cells][:, None, :], pos.shape)
+            ok = pos >= 0
+            col[pos[ok]] = cols[ok]
         assert (col >= 0).all()
         return col
-
-    def entry_positions(self, cells=None):
-        """pos[c, i, j] into vals (small meshes / tests only)."""
-        cd, L, P = self._cd, self.L, self.P
-        lay = local_layout(P)
-        if cells is None:
-            cells = np.arange(cd.shape[0])
-        pos = np.empty((len(cells), L, L), dtype=np.int64)
-        is_fac = np.zeros(L, dtype=np.int64) - 1
-        for f in range(3):
-            is_fac[lay['facet'][:, f, :].ravel()] = f
-        for i in range(L):
-            f = is_fac[i]
-            ranks = self.rank_own[cells] if f < 0 else self.rank_fac[cells, f, :]
-            pos[:, i, :] = self.rowptr[cd[cells, i].astype(np.int64)][:, None] + ranks
-        return pos

@@ -17,7 +17,7 @@ __all__ = ['ProblemArrays']
 
 class ProblemArrays(object):
     def __init__(self, mesh, cell_tag, model, tag_params, numbering='b200',
-                 jump_facet_mask=None, bc_dofs=None, natbc=None):
+                 jump_facet_mask=None, bc_dofs=None, natbc=None, pattern='structural'):
         """
         mesh:        simudo_b200.mesh.Mesh
         cell_tag:    [Nc] int row index into tag_params
@@ -40,7 +40,8 @@ class ProblemArrays(object):
         self.cell_vertices = np.ascontiguousarray(
             mesh.coordinates[mesh.cells], dtype=np.float64)        # [Nc,3,2]
         self.cell_dofs, self.N = build_cell_dofs(mesh, self.P, numbering)
-        self.csr = CsrStructure(mesh, self.cell_dofs, self.P, self.N)
+        self.pattern = pattern
+        self.csr = CsrStructure(mesh, self.cell_dofs, self.P, self.N, pattern=pattern)
         self.cell_neighbors = np.ascontiguousarray(
             mesh.cell_to_cells_adjacency_via_facet(), dtype=np.int32)
         nc = mesh.num_cells

@@ -42,7 +42,8 @@ def _boundary_setup(mesh, pa_P, cell_dofs_fn=None):
     return left, right, horiz
 
 
-def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=True):
+def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=True,
+               pattern='structural'):
     """2D Si pn junction: CB + VB Boltzmann bands, SRH (BASELINE config 1/3)."""
     Xs = _graded(nx, length, [length / 2])
     Ys = np.linspace(0.0, height, ny)
@@ -74,14 +75,14 @@ def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=Tr
     nf = mesh.num_facets
     jmask = np.full(nf, 0b11, dtype=np.uint8)
     pa = ProblemArrays(mesh, cell_tag, model, tp, numbering=numbering,
-                       jump_facet_mask=jmask)
+                       jump_facet_mask=jmask, pattern=pattern)
     if with_bcs:
         _attach_bcs(pa, mesh, n_dof_bands=2, minority_left=[0], minority_right=[1])
     return pa
 
 
 def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
-               const_mobility=True):
+               const_mobility=True, pattern='structural'):
     """Four-layer FSF/p/IB/n intermediate-band cell (BASELINE config 2/4):
     CB, IB, VB; two Shockley-Read traps, radiative CV, radiative CI/IV with
     absorption, three optical fields."""
@@ -152,7 +153,7 @@ def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
     both_I = interior & (cell_tag[fc[:, 0]] == 2) & (cell_tag[np.maximum(fc[:, 1], 0)] == 2)
     jmask[both_I] |= 0b010
     pa = ProblemArrays(mesh, cell_tag, model, tp, numbering=numbering,
-                       jump_facet_mask=jmask)
+                       jump_facet_mask=jmask, pattern=pattern)
     if with_bcs:
         _attach_bcs(pa, mesh, n_dof_bands=3, minority_left=[0], minority_right=[2],
                     extra_all=[1])

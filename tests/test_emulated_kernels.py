@@ -11,15 +11,15 @@ import hotpath_cases as hc
 from simudo_b200 import synthetic as syn
 
 
-@pytest.mark.parametrize('maker,nx,ny,numbering,bcs', [
-    (syn.pn_problem, 5, 3, 'b200', True),
-    (syn.pn_problem, 4, 2, 'ufc', True),
-    (syn.ib_problem, 6, 3, 'b200', True),
-    (syn.ib_problem, 5, 2, 'ufc', False),
-    (syn.pn_problem, 34, 3, 'b200', True),      # > 1 CTA tile, ragged last tile
+@pytest.mark.parametrize('maker,nx,ny,numbering,bcs,pattern', [
+    (syn.pn_problem, 5, 3, 'b200', True, 'structural'),
+    (syn.pn_problem, 4, 2, 'ufc', True, 'dolfin'),
+    (syn.ib_problem, 6, 3, 'b200', True, 'dolfin'),
+    (syn.ib_problem, 5, 2, 'ufc', False, 'structural'),
+    (syn.pn_problem, 34, 3, 'b200', True, 'structural'),   # > 1 CTA, ragged last CTA
 ])
-def test_assembly_parity_emulated(emulated_lib, maker, nx, ny, numbering, bcs):
-    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs)
+def test_assembly_parity_emulated(emulated_lib, maker, nx, ny, numbering, bcs, pattern):
+    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)
 
 
 def test_thermal_equilibrium_mode_emulated(emulated_lib):

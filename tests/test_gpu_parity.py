@@ -19,18 +19,21 @@ import hotpath_cases as hc          # noqa: E402
 from simudo_b200 import synthetic as syn   # noqa: E402
 
 
-@pytest.mark.parametrize('maker,nx,ny,numbering,bcs', [
-    (syn.pn_problem, 5, 3, 'b200', True),
-    (syn.pn_problem, 4, 2, 'ufc', True),
-    (syn.pn_problem, 67, 2, 'b200', True),      # config-1 size (132 cells)
-    (syn.ib_problem, 6, 3, 'b200', True),
-    (syn.ib_problem, 5, 2, 'ufc', False),
-    (syn.ib_problem, 279, 2, 'b200', True),     # config-2 size (556 cells)
-    (syn.pn_problem, 40, 33, 'b200', True),     # 2 496 cells, many tiles
-    (syn.ib_problem, 30, 21, 'b200', True),
+@pytest.mark.parametrize('maker,nx,ny,numbering,bcs,pattern', [
+    (syn.pn_problem, 5, 3, 'b200', True, 'structural'),
+    (syn.pn_problem, 4, 2, 'ufc', True, 'dolfin'),
+    (syn.pn_problem, 67, 2, 'b200', True, 'dolfin'),       # config-1 size (132 cells)
+    (syn.pn_problem, 67, 2, 'ufc', True, 'structural'),
+    (syn.ib_problem, 6, 3, 'b200', True, 'dolfin'),
+    (syn.ib_problem, 5, 2, 'ufc', False, 'structural'),
+    (syn.ib_problem, 279, 2, 'b200', True, 'structural'),  # config-2 size (556 cells)
+    (syn.ib_problem, 279, 2, 'ufc', True, 'dolfin'),
+    (syn.pn_problem, 40, 33, 'b200', True, 'structural'),  # 2 496 cells, many CTAs
+    (syn.ib_problem, 30, 21, 'b200', True, 'structural'),
+    (syn.ib_problem, 30, 21, 'b200', True, 'dolfin'),
 ])
-def test_assembly_parity(maker, nx, ny, numbering, bcs):
-    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs)
+def test_assembly_parity(maker, nx, ny, numbering, bcs, pattern):
+    hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)
 
 
 def test_thermal_equilibrium_mode():

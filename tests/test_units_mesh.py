@@ -119,7 +119,7 @@ def test_csr_structure_is_dolfin_dense_cell_pattern(numbering):
     P = 3
     cd, N = build_cell_dofs(m, P, numbering)
     assert sorted(np.unique(cd)) == list(range(N))
-    S = CsrStructure(m, cd, P, N)
+    S = CsrStructure(m, cd, P, N, 'dolfin')
     L = 15 * P
     rows = np.repeat(cd, L, axis=1).ravel()
     cols = np.tile(cd, (1, L)).ravel()
@@ -140,3 +140,23 @@ def test_ufc_numbering_layout():
     assert (cd[:, 3] == 3 * nc + 3 * m.cell_facets[:, 0]).all()   # BDM facet 0 dof 0
     assert (cd[:, 12] == 3 * nc + 3 * nf + 3 * np.arange(nc)).all()
     assert (cd[:, 15] == 6 * nc + 3 * nf + 3 * np.arange(nc)).all()
+
+
+@pytest.mark.parametrize('numbering', ['ufc', 'b200'])
+def test_structural_pattern_is_the_masked_dolfin_pattern(numbering):
+    import scipy.sparse as sp
+    from simudo_b200.fem.dofmap import structural_mask
+    m = Product2DMesh(np.linspace(0, 1, 5), np.linspace(0, 1, 4)).mesh
+    P = 4
+    cd, N = build_cell_dofs(m, P, numbering)
+    S = CsrStructure(m, cd, P, N, 'structural')
+    mask = structural_mask(P)
+    # per-cell structural entries (1116 for an IB cell)
+    assert mask.sum() == 3 * (12 + 3 + 9) + 12 * 15 + 3 * (3 * (12 + 3 + 9) + 12 * 18)
+    ii, jj = np.nonzero(mask)
+    A = sp.coo_matrix((np.ones(cd.shape[0] * len(ii)), (cd[:, ii].ravel(), cd[:, jj].ravel())),
+                      shape=(N, N)).tocsr()
+    A.sort_indices()
+    assert (A.indptr == S.rowptr).all()
+    assert (A.indices == S.column_indices()).all()
+    assert S.patterns.shape[0] <= 16
