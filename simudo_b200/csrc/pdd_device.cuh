@@ -258,13 +258,6 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBand
   }
 }
 
-/* run-time sized rule (non-default quadrature degrees): one out-of-line copy */
-SB_NOINLINE void sb_phaseA_generic(const SbRule& R, bool do_rho, bool do_dd, const SbBandK& K,
-                                   double chi0, double chix, double chiy, const double (*gc)[6],
-                                   double* mC, double* Q, double* mR, double* mRx) {
-  sb_phaseA_band<0>(R, do_rho, do_dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-}
-
 /* ------------------------------------------------------------------------- *
  * phase B: generation terms of all bands at the points of the g-rule.
  * ------------------------------------------------------------------------- */
@@ -436,7 +429,6 @@ struct SbIO {
   const int32_t* bcidx;      /* [L] index into bc_values | -1 (special cells) */
   uint64_t mlo;              /* constrained local dofs, bits 0..63          */
   uint32_t mhi;              /* bits 64..74                                 */
-  bool special;              /* the cell has Dirichlet dofs (rare)           */
   double* vals;              /* may be NULL                                 */
   double* b;                 /* may be NULL                                 */
 };
@@ -460,26 +452,16 @@ SB_HD double sb_lift_value(const SbIO& io, int j) {
  * symmetric rule; Fi is the residual accumulator of row i
  * and receives the x0 lifting in program order (bit-reproducible).  With
  * compile-time (i, j) every facet test folds away.                            */
-/* rare path: cell with Dirichlet dofs (out of line to keep the hot code small) */
-SB_NOINLINE void sb_emit_special(const SbIO& io, int64_t rowbase, int i, int j, double val,
-                                 double* Fi) {
-  if (sb_is_bc(io, i)) {
-    val = (i == j) ? 1.0 : 0.0;
-  } else if (sb_is_bc(io, j)) {
-    *Fi -= val * sb_lift_value(io, j);
-    val = 0.0;
-  }
-  if (!io.vals) return;
-  const int fi = sb_local_facet(i);
-  const int rk = io.pat[i * io.L + j];
-  if (rk == 0xFF) return;
-  double* dst = io.vals + rowbase + rk;
-  if (fi >= 0 && sb_local_facet(j) == fi) SB_ATOMIC_ADD(dst, val);
-  else *dst = val;
-}
-
+template <bool SP>
 SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, double& Fi) {
-  if (io.special) { sb_emit_special(io, rowbase, i, j, val, &Fi); return; }
+  if (SP) {
+    if (sb_is_bc(io, i)) {
+      val = (i == j) ? 1.0 : 0.0;
+    } else if (sb_is_bc(io, j)) {
+      Fi -= val * sb_lift_value(io, j);
+      val = 0.0;
+    }
+  }
   if (!io.vals) return;
   const int fi = sb_local_facet(i);
   const int rk = io.pat[i * io.L + j];
@@ -492,9 +474,10 @@ SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, do
 }
 
 /* final residual value of local row i */
+template <bool SP>
 SB_HD void sb_put_row(const SbIO& io, int i, double F) {
   if (!io.b) return;
-  if (io.special && sb_is_bc(io, i)) F = sb_lift_value(io, i);
+  if (SP && sb_is_bc(io, i)) F = sb_lift_value(io, i);
   double* dst = io.b + io.dofs[i];
   if (sb_local_facet(i) >= 0) SB_ATOMIC_ADD(dst, F); else *dst = F;
 }
@@ -522,7 +505,8 @@ SB_HD void sb_add_natbc(const int32_t* nat_row, const double* nat_val, int b0, i
  *   <xi_i . j dc/dchi lam_l> = iad sum_{a,r} C_i[a][r] V_a[r][l],
  *   V_a[r][l] = sum_t G21[r][l][t] Q_a[t].
  * mode 0: Poisson psi rows; 1: band inside its subdomain; 2: band outside.    */
-SB_NOINLINE void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
+template <bool SP>
+SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
                         const SbCellGeom& g, int p, int mode,
                         const double* mC, const double* Q,
                         const double* fl /*[12] flux dofs*/, const double* sl /*[3] scalar dofs*/,
@@ -594,7 +578,7 @@ SB_NOINLINE void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& 
       for (int s2 = 0; s2 < 6; ++s2)
         v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
       Fi += v * fl[m];
-      sb_emit(io, rowbase, li, r0 + m, v, Fi);
+      sb_emit<SP>(io, rowbase, li, r0 + m, v, Fi);
     }
     if (mode != 2) {
 #pragma unroll
@@ -606,10 +590,10 @@ SB_NOINLINE void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& 
 #pragma unroll
           for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
           d *= g.iad;
-          sb_emit(io, rowbase, li, sb_ldg(p, l), dv + d, Fi);
-          sb_emit(io, rowbase, li, sb_ldg(0, l), d, Fi);
+          sb_emit<SP>(io, rowbase, li, sb_ldg(p, l), dv + d, Fi);
+          sb_emit<SP>(io, rowbase, li, sb_ldg(0, l), d, Fi);
         } else {
-          sb_emit(io, rowbase, li, sb_ldg(0, l), dv, Fi);
+          sb_emit<SP>(io, rowbase, li, sb_ldg(0, l), dv, Fi);
         }
       }
     }
@@ -618,7 +602,7 @@ SB_NOINLINE void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& 
       Fi -= jf * T.trI[i % 3];
     }
     if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, li, 1, &Fi);
-    sb_put_row(io, li, Fi);
+    sb_put_row<SP>(io, li, Fi);
   }
 }
 
@@ -626,8 +610,8 @@ SB_NOINLINE void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& 
  * coef: multiplies the moment terms (-adet for rho, -s e adet for g)
  * mom1[3]: P1 moments of the source (rho/eps | g_k)
  * momJ[q][6]: P2 moments of d source / d (phi | delta_w_q-1), q < NQ          */
-template <int NQ>
-SB_NOINLINE void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
+template <bool SP, int NQ>
+SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
                           const SbCellGeom& g, int p, bool inside,
                           const double* fl /*[12] flux dofs of p*/, const double* sl /*[3]*/,
                           double coef, const double* mom1, const double* momJ,
@@ -644,7 +628,7 @@ SB_NOINLINE void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO
       for (int m = 0; m < 12; ++m) {            /* <v_i div j> */
         const double dv = g.sdet * T.Dhat[m][i];
         F[i] += dv * fl[m];
-        sb_emit(io, rb[i], r0 + i, sb_lbdm(p, m), dv, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, sb_lbdm(p, m), dv, F[i]);
       }
 #pragma unroll
       for (int t = 0; t < 3; ++t) F[i] += coef * T.G1[i][t] * mom1[t];
@@ -655,7 +639,7 @@ SB_NOINLINE void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO
           double v = 0.0;
 #pragma unroll
           for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
-          sb_emit(io, rb[i], r0 + i, sb_ldg(q, l), coef * v, F[i]);
+          sb_emit<SP>(io, rb[i], r0 + i, sb_ldg(q, l), coef * v, F[i]);
         }
     }
   } else {
@@ -667,12 +651,12 @@ SB_NOINLINE void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO
       for (int l = 0; l < 3; ++l) {
         const double v = c1 * T.M1[i][l];
         F[i] += v * sl[l];
-        sb_emit(io, rb[i], r0 + i, r0 + l, v, F[i]);
+        sb_emit<SP>(io, rb[i], r0 + i, r0 + l, v, F[i]);
       }
   }
   if (nb1 > nb0) sb_add_natbc(nat_row, nat_val, nb0, nb1, r0, 3, F);
 #pragma unroll 1
-  for (int i = 0; i < 3; ++i) sb_put_row(io, r0 + i, F[i]);
+  for (int i = 0; i < 3; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 
 #endif /* SB_PDD_DEVICE_CUH */

@@ -120,7 +120,7 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
 template <int NB>
 __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev& st,
                                               double* vals, double* b, int64_t c, SbIO& io,
-                                              int nb0, int nb1) {
+                                              int nb0, int nb1, const bool sp) {
   const int nb = pl.nb;                       /* bands entering rho */
   const int L = pl.L;
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
@@ -196,10 +196,10 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
         sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
     } else if (same_rule) {
       if (rho || dd)
-        sb_phaseA_generic(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+        sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
     } else {
-      if (rho) sb_phaseA_generic(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-      if (dd) sb_phaseA_generic(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+      if (rho) sb_phaseA_band<0>(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+      if (dd) sb_phaseA_band<0>(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
     }
 #pragma unroll
     for (int t = 0; t < SB_NRX; ++t) { mX[1 + k][t] = mRx[t]; mX[0][t] += mRx[t]; }
@@ -216,8 +216,14 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
         }
       }
       const int mode = inside ? 1 : 2;
-      sb_rows_flux(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
-                   jumpf[0], jumpf[1], jumpf[2], pl.natbc_row, st.natbc_values, nb0, nb1);
+      if (sp)
+        sb_rows_flux<true>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
+                           jumpf[0], jumpf[1], jumpf[2],
+                           pl.natbc_row, st.natbc_values, nb0, nb1);
+      else
+        sb_rows_flux<false>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
+                            jumpf[0], jumpf[1], jumpf[2],
+                            pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
 
@@ -233,8 +239,12 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
 #pragma unroll
       for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
       const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-      sb_rows_scalar<1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
-                             mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
+      if (sp)
+        sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
+                                     mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
+      else
+        sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
+                                      mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
     }
   }
 
@@ -245,10 +255,17 @@ __device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev&
     double fl[12];
 #pragma unroll
     for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
-    sb_rows_scalar<1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
-                           pl.natbc_row, st.natbc_values, nb0, nb1);
-    sb_rows_flux(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
-                 pl.natbc_row, st.natbc_values, nb0, nb1);
+    if (sp) {
+      sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
+                                   pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<true>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
+                         pl.natbc_row, st.natbc_values, nb0, nb1);
+    } else {
+      sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
+                                    pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<false>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
+                          pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
   }
 }
 
@@ -276,8 +293,7 @@ k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
     io.bcidx = pl.sp_bcidx + (int64_t)sp * L;
     nb0 = pl.sp_nat_begin[sp]; nb1 = pl.sp_nat_begin[sp + 1];
   }
-  io.special = (io.mlo | io.mhi) != 0;
-  assemble_cell<NB>(pl, st, vals, b, c, io, nb0, nb1);
+  assemble_cell<NB>(pl, st, vals, b, c, io, nb0, nb1, (io.mlo | io.mhi) != 0);
 }
 
 /* ------------------------------------------------------------------------- */
