@@ -202,6 +202,29 @@ int sb_surface_flux(sb_plan* plan, const double* d_u, int32_t p,
                     const int8_t* d_facet_local, const double* d_facet_sign,
                     double* d_out, void* stream);
 
+/* ---- Newton linear solve ------------------------------------------------------------
+ * Replaces PETScLUSolver("mumps").solve(A, Qdu, b) (simudo/fem/newton_solver.py:
+ * 124-181) for product meshes that are thin in y: banded LU with partial pivoting
+ * in the ordering h_perm (new index of each dof, e.g. by x-position of its mesh
+ * entity), with row/column equilibration.  cuDSS is not available in this image;
+ * sb_band_create returns SB_ERR_UNSUPPORTED when the band storage would exceed
+ * max_band_bytes (> 0).  One CTA per system, `batch` systems per call.            */
+typedef struct sb_band_solver sb_band_solver;
+int  sb_band_create(int64_t n, const int64_t* h_rowptr, const int32_t* h_colidx,
+                    const int32_t* h_perm, int32_t batch, int64_t max_band_bytes,
+                    sb_band_solver** out);
+void sb_band_destroy(sb_band_solver* s);
+int  sb_band_info(const sb_band_solver* s, int64_t* n, int32_t* kl, int32_t* ku);
+/* iterative-refinement steps (default 2): residual b - A x in double-double, correction
+ * through the stored factors.  Needed because a Newton row mixes entries of size 1 and
+ * 1e28: the weakly determined minority quasi-Fermi modes are lost in a plain double
+ * solve (MUMPS does the analogous work through its MC64 scaling, ICNTL(6)=5).      */
+int  sb_band_set_refinement(sb_band_solver* s, int32_t steps);
+/* d_vals [nsys][vstride] CSR values, d_b / d_x [nsys][n]; h_info (host, optional):
+ * 0 = ok, j+1 = zero pivot in column j (synchronises the stream when given).        */
+int  sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_t vstride,
+                   const double* d_b, double* d_x, int32_t* h_info, void* stream);
+
 /* ---- measurement ------------------------------------------------------------------
  * CUDA-event timing (on the launching stream) of the dominant kernel of the last
  * sb_assemble call; sb_plan_last_kernel_ms synchronises on that event.            */

@@ -196,7 +196,8 @@ def rebase_w(pa, u, base_w, band, bc_cells=(), bc_avg=()):
 
 
 def newton_metrics(u, du, b, tol, rel_tol, abs_tol):
-    """newton_solver.py:79-122."""
+    """newton_solver.py:79-122; ``u`` is the solution *after* the update, which is
+    what the reference's lazily evaluated norms see (:306-317, :346-352)."""
     with np.errstate(divide='ignore', invalid='ignore'):
         r = np.abs(du / u)
         ok = ~np.isnan(r)

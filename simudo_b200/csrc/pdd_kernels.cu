@@ -29,7 +29,8 @@
 __constant__ SbTables c_T;
 __constant__ sb_model c_M;
 
-static thread_local char g_err[512] = "";
+thread_local char g_sb_err[512] = "";   /* shared with band_solver.cu */
+#define g_err g_sb_err
 static std::atomic<long long> g_launches{0};
 static const void* g_tables_owner = nullptr;
 
@@ -346,18 +347,21 @@ __global__ void k_newton_update(int64_t N, double* u, const double* du, const do
        i += (int64_t)gridDim.x * blockDim.x) {
     const double ui = u[i], di = du[i];
     const double bi = b ? b[i] : 0.0;
-    if (isnan(ui) || isnan(bi)) nanf = 1.0;
-    const double ab = fabs(bi), ad = fabs(di);
-    if (ab > bmax || isnan(ab)) bmax = isnan(ab) ? bmax : ab;
-    if (ad > dmax) dmax = ad;
-    const double r = fabs(di / ui);
-    if (!isnan(r)) { rsum += r * r; cnt += 1.0; }
-    const double cc = ad / (fabs(ui) * rel_tol + abs_tol * (tol ? tol[i] : 1.0));
-    if (cc > cmax) cmax = cc;
-    if (isnan(cc) || isnan(ad)) nanf = fmax(nanf, isnan(ad) ? 2.0 : nanf);
     double step = di;
     if (max_du > 0.0) step = fmin(fmax(step, -max_du), max_du);
-    u[i] = ui - omega * step;
+    const double un = ui - omega * step;
+    u[i] = un;
+    /* the reference evaluates its metrics after the update, i.e. against the
+       new u_ (newton_solver.py:306-317 then :94-117) */
+    if (isnan(un) || isnan(bi)) nanf = 1.0;
+    const double ab = fabs(bi), ad = fabs(di);
+    if (ab > bmax) bmax = ab;
+    if (ad > dmax) dmax = ad;
+    const double r = fabs(di / un);
+    if (!isnan(r)) { rsum += r * r; cnt += 1.0; }
+    const double cc = ad / (fabs(un) * rel_tol + abs_tol * (tol ? tol[i] : 1.0));
+    if (cc > cmax) cmax = cc;
+    if (isnan(ad)) nanf = 1.0;
   }
   __shared__ double sh[6][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

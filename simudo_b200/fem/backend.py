@@ -1,0 +1,116 @@
+"""CUDA backend of the Newton hot loop.
+
+Owns the device-resident state of one lowered problem and implements the
+calls ``NewtonSolver`` makes per iteration
+(``simudo/fem/newton_solver.py:319-326``): assemble (A, b), linear solve,
+update + metrics, plus the rebasing hook and the terminal-current functional.
+The device copy of the solution is the single source of truth during
+``solve()``; host copies are made only when a hook / the stepper asks
+("data ownership").  No CPU fallback: constructing this
+backend without a CUDA device raises.
+"""
+import numpy as np
+import torch
+
+from .assembly import AssemblyPlan
+from .linear_solver import BandSolver
+
+__all__ = ['CudaBackend']
+
+
+class CudaBackend(object):
+    name = 'cuda'
+
+    def __init__(self, pa, device=None):
+        self.pa = pa
+        self.plan = AssemblyPlan(pa, device=device)
+        self.device = self.plan.device
+        T = self.plan.tensor
+        self.T = T
+        self.u = None
+        self.base_w = None
+        self.thmeq = None
+        self.phi_opt = None
+        self.bc_values = None
+        self.natbc = None
+        self.vals = self.plan.new_values()
+        self.b = self.plan.new_vector()
+        self.du = self.plan.new_vector()
+        self._solver = None
+        self._metrics = torch.zeros(6, dtype=torch.float64, device=self.device)
+
+    # -- state ----------------------------------------------------------------
+    def set_state(self, u, base_w, thmeq, phi_opt):
+        T = self.T
+        self.u = T(u).clone()
+        self.base_w = None if base_w is None else T(base_w).clone()
+        self.thmeq = None if thmeq is None else T(thmeq).clone()
+        self.phi_opt = None if phi_opt is None else T(phi_opt).clone()
+
+    def set_u(self, u):
+        self.u = self.T(u).clone()
+
+    def set_phi_opt(self, phi_opt):
+        self.phi_opt = self.T(phi_opt).clone()
+
+    def get_u(self):
+        return self.u.cpu().numpy()
+
+    def get_base_w(self):
+        return self.base_w.cpu().numpy()
+
+    def get_du(self):
+        return self.du.cpu().numpy()
+
+    def get_b(self):
+        return self.b.cpu().numpy()
+
+    def set_bc_values(self, v):
+        self.bc_values = self.T(v) if len(v) else None
+
+    def set_natbc_values(self, v):
+        self.natbc = self.T(self.plan.natbc_device_order(v)) if len(v) else None
+
+    # -- hot loop ----------------------------------------------------------------
+    def assemble(self):
+        self.plan.assemble(self.u, self.base_w, self.thmeq, self.phi_opt, self.bc_values,
+                           self.natbc, self.vals, self.b)
+
+    def solve(self):
+        if self._solver is None:
+            self._solver = BandSolver(self.pa, self.device)
+        self._solver.solve(self.vals, self.b, self.du)
+
+    def newton_update(self, tol, omega, max_du, rel_tol, abs_tol):
+        if not isinstance(tol, torch.Tensor):
+            tol = self.T(tol)
+            self._tol = tol
+        out = self.plan.newton_update(self.u, self.du, self.b, tol, omega, max_du, rel_tol,
+                                      abs_tol, self._metrics).cpu().numpy()
+        return dict(b_norm=float(out[0]), du_norm=float(out[1]),
+                    rel_du_norm=float(np.sqrt(out[2])) if out[5] > 0 else float('nan'),
+                    combined_du_norm=float(out[3]), has_nans=bool(out[4] > 0))
+
+    def rebase(self, band, ohmic, thm_avg):
+        if ohmic is None:
+            self.plan.rebase_w(self.u, self.base_w, band)
+            return
+        cache = ohmic.setdefault('_dev', {})
+        if 'cells' not in cache:
+            T = self.T
+            cache['cells'] = T(ohmic['cells'], torch.int32)
+            cache['dof_a'] = T(ohmic['dof_a'], torch.int64)
+            cache['dof_b'] = T(ohmic['dof_b'], torch.int64)
+            cache['inv'] = T(ohmic['inv'], torch.int64)
+            cache['w'] = T(ohmic['w'])
+            cache['thm'] = T(thm_avg)
+        # contact value e (phi_thmeq - phi), facet average of the P1 potential
+        phi_avg = 0.5 * (self.u[cache['dof_a']] + self.u[cache['dof_b']]) * cache['w']
+        avg = cache['thm'] - torch.zeros_like(cache['thm']).index_add_(0, cache['inv'], phi_avg)
+        self.plan.rebase_w(self.u, self.base_w, band, cache['cells'], avg)
+
+    def surface_flux(self, p, cells, locals_):
+        T = self.T
+        out = self.plan.surface_flux(self.u, p, T(cells, torch.int32), T(locals_, torch.int8),
+                                     T(np.ones(len(cells)))).cpu().numpy()
+        return float(out[0]), float(out[1])

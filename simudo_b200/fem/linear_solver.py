@@ -1,0 +1,91 @@
+"""On-device linear solve of the Newton systems.
+
+Replaces ``NewtonSolution.do_linear_solve`` -> ``PETScLUSolver("mumps")``
+(``simudo/fem/newton_solver.py:124-181``).  cuDSS is not installed in this
+image, so the solver is the hand-written banded LU of
+``csrc/band_solver.cu``: dofs are ordered by the x-position of their mesh
+entity, which makes the Jacobian of a (thin) product mesh banded.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+__all__ = ['x_major_permutation', 'BandSolver']
+
+
+def x_major_permutation(pa):
+    """New index of each dof when dofs are sorted by the x-coordinate of the
+    mesh entity (cell centroid / facet midpoint) carrying them."""
+    mesh = pa.mesh
+    lay = pa.layout()
+    xkey = np.zeros(pa.N)
+    cx = pa.cell_vertices[:, :, 0].mean(axis=1)
+    fx = mesh.facet_midpoints()[:, 0]
+    for p in range(pa.P):
+        for i in range(3):
+            xkey[pa.cell_dofs[:, lay['dg'][p][i]]] = cx
+            xkey[pa.cell_dofs[:, lay['interior'][p][i]]] = cx
+        for f in range(3):
+            for k in range(3):
+                xkey[pa.cell_dofs[:, lay['facet'][p][f][k]]] = fx[mesh.cell_facets[:, f]]
+    order = np.argsort(xkey, kind='stable')
+    perm = np.empty(pa.N, dtype=np.int32)
+    perm[order] = np.arange(pa.N, dtype=np.int32)
+    return perm
+
+
+class BandSolver(object):
+    """Banded LU with partial pivoting + equilibration, one CTA per system."""
+
+    def __init__(self, pa, device, batch=1, max_band_bytes=8 << 30):
+        self.lib = _lib.get()
+        self.pa = pa
+        self.device = torch.device(device)
+        self.n = pa.N
+        self.batch = batch
+        rowptr = np.ascontiguousarray(pa.csr.rowptr)
+        colidx = np.ascontiguousarray(pa.csr.column_indices())
+        perm = np.ascontiguousarray(x_major_permutation(pa))
+        h = C.c_void_p()
+        _lib.check(self.lib.sb_band_create(
+            pa.N, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p),
+            perm.ctypes.data_as(C.c_void_p), batch, max_band_bytes, C.byref(h)))
+        self._h = h
+        kl, ku, n = C.c_int32(), C.c_int32(), C.c_int64()
+        self.lib.sb_band_info(h, C.byref(n), C.byref(kl), C.byref(ku))
+        self.kl, self.ku = kl.value, ku.value
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            try:
+                self.lib.sb_band_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def solve(self, vals, b, x=None, check=True, stream=None):
+        """x = A^{-1} b; ``vals`` [nsys, nnz] or [nnz], ``b`` [nsys, n] or [n].
+        Raises RuntimeError on a singular matrix (as PETSc/MUMPS would)."""
+        nsys = 1 if vals.dim() == 1 else vals.shape[0]
+        if x is None:
+            x = torch.empty_like(b)
+        info = (C.c_int32 * nsys)()
+        st = None
+        if stream is not None:
+            st = C.c_void_p(stream.cuda_stream)
+        elif self.device.type == 'cuda':
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.sb_band_solve(
+            self._h, nsys, C.c_void_p(vals.data_ptr()), vals.shape[-1],
+            C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()),
+            C.cast(info, C.c_void_p) if check else None, st))
+        if check:
+            bad = [i for i in range(nsys) if info[i] != 0]
+            if bad:
+                raise RuntimeError('simudo_b200: singular Jacobian in banded LU '
+                                   '(zero pivot at column %d)' % (info[bad[0]] - 1))
+        return x

@@ -1,0 +1,1 @@
+from .output_writer import (OutputWriter, MetaExtractorBandInfo, MetaExtractorIntegrals)

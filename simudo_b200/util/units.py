@@ -391,9 +391,8 @@ class UnitRegistry(object):
         if cached is not None:
             return cached
         src = text.strip().replace('^', '**')
-        # implicit multiplication: "300 K", "1e4 cm", ") cm"
-        src = re.sub(r'(?<=[0-9.)])\s+(?=[A-Za-z_µ(])', '*', src)
-        src = re.sub(r'(?<=[A-Za-z_µ)])\s+(?=[A-Za-z_µ(])', '*', src)
+        # implicit multiplication: "300 K", "1e4 cm", ") cm", "3.2e19 1/cm^3"
+        src = re.sub(r'(?<=[0-9A-Za-z_µ.)])\s+(?=[0-9A-Za-z_µ(.])', '*', src)
         try:
             tree = ast.parse(src, mode='eval')
         except SyntaxError as e:

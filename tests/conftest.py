@@ -37,7 +37,8 @@ EMUL_SO = os.path.join(EMUL_DIR, 'libsimudo_b200_emul.so')
 def build_emulation_library():
     """g++ build of csrc/pdd_kernels.cu against tests/emul/cuda_emul.h."""
     src = os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_kernels.cu')
-    deps = [src, os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_device.cuh'),
+    src2 = os.path.join(ROOT, 'simudo_b200', 'csrc', 'band_solver.cu')
+    deps = [src, src2, os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_device.cuh'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_tables.h'),
             os.path.join(ROOT, 'include', 'simudo_b200.h'),
             os.path.join(EMUL_DIR, 'cuda_emul.h')]
@@ -45,7 +46,7 @@ def build_emulation_library():
             or os.path.getmtime(EMUL_SO) < max(os.path.getmtime(d) for d in deps)):
         subprocess.check_call(
             ['g++', '-std=c++20', '-O2', '-fPIC', '-shared', '-pthread',
-             '-DSB_EMUL_BUILD', '-I', EMUL_DIR, '-x', 'c++', src, '-o', EMUL_SO])
+             '-DSB_EMUL_BUILD', '-I', EMUL_DIR, '-x', 'c++', src, src2, '-o', EMUL_SO])
     return EMUL_SO
 
 

@@ -157,7 +157,8 @@ def newton_update_parity():
     du[::34] = 0.0
     b = rng.standard_normal(pa.N)
     tol = pa.tolerance_vector([1e-6] * pa.P, [1e-4] + [1e-10] * (pa.P - 1))
-    ref = orc_mod.newton_metrics(u, du, b, tol, 1e-4, 1.0)
+    expect = u - 0.5 * np.clip(du, -2e-3, 2e-3)
+    ref = orc_mod.newton_metrics(expect, du, b, tol, 1e-4, 1.0)
     T = plan.tensor
     ud = T(u).clone()
     out = plan.newton_update(ud, T(du), T(b), T(tol), 0.5, 2e-3, 1e-4, 1.0).cpu().numpy()
@@ -167,7 +168,6 @@ def newton_update_parity():
         not np.isfinite(ref['rel_du_norm'])
     assert abs(out[3] - ref['combined_du_norm']) <= 1e-15 * ref['combined_du_norm']
     assert out[4] == 0.0
-    expect = u - 0.5 * np.clip(du, -2e-3, 2e-3)
     assert np.abs(ud.cpu().numpy() - expect).max() == 0.0
     # NaN poisoning is detected, not raised (newton_solver.py:84-89)
     u2 = u.copy(); u2[5] = np.nan

@@ -52,3 +52,25 @@ def test_newton_update_emulated(emulated_lib):
 
 def test_surface_flux_emulated(emulated_lib):
     hc.surface_flux_parity()
+
+
+def test_band_solver_with_refinement_emulated(emulated_lib):
+    """Banded LU + double-double refinement vs scipy on a Newton matrix."""
+    import numpy as np
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from parity_util import run_plan
+    from simudo_b200.fem.assembly import AssemblyPlan
+    from simudo_b200.fem.linear_solver import BandSolver
+    pa = syn.pn_problem(nx=12, ny=2)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    vals, b = run_plan(plan, st)
+    bs = BandSolver(pa, 'cpu')
+    assert bs.kl < 60 and bs.ku < 60
+    x = bs.solve(vals, b).numpy()
+    A = sp.csr_matrix((vals.numpy(), pa.csr.column_indices(), pa.csr.rowptr),
+                      shape=(pa.N, pa.N))
+    r = A @ x - b.numpy()
+    rs = 1.0 / np.abs(A).max(axis=1).toarray().ravel()
+    assert np.abs(rs * r).max() < 1e-12 * np.abs(rs * b.numpy()).max() + 1e-20
