@@ -32,6 +32,9 @@ sys.path.insert(0, ROOT)
 METRIC = 'jacobian_residual_assembly_dof_per_s'
 UNIT = 'DOF/s'
 BYTES_PER_CELL = {'ib': 10396, 'pn': 7424}
+# dram__bytes_read.sum + dram__bytes_write.sum of k_assemble per cell from the committed
+# `ncu --set full` capture (profiles/r1_v6_k_assemble_summary.csv, 80 396 IB cells)
+NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): (611141888 + 1022995000) / 80396.0}
 
 
 def parse_args():
@@ -172,21 +175,6 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def halo_exchange(dist, rank, world, send_lo, send_hi, recv_lo, recv_hi):
-    """Ghost exchange between neighbouring y-strips (no-op at world 1)."""
-    if world == 1:
-        return
-    ops = []
-    if rank > 0:
-        ops.append(dist.P2POp(dist.isend, send_lo, rank - 1))
-        ops.append(dist.P2POp(dist.irecv, recv_lo, rank - 1))
-    if rank < world - 1:
-        ops.append(dist.P2POp(dist.isend, send_hi, rank + 1))
-        ops.append(dist.P2POp(dist.irecv, recv_hi, rank + 1))
-    for r in dist.batch_isend_irecv(ops):
-        r.wait()
-
-
 def run_b200(args):
     import torch
     rank = int(os.environ.get('RANK', '0'))
@@ -218,16 +206,13 @@ def run_b200(args):
     nat = T(plan.natbc_device_order(st['natbc_values']))
     vals = plan.new_values()
     b = plan.new_vector()
-    # interface data of a strip: 3 P doubles per interface facet + n_bands per ghost cell
-    nface = args.nx - 1
-    halo_n = nface * (3 * pa.P + pa.model.n_bands)
-    s_lo = torch.zeros(halo_n, dtype=torch.float64, device=dev)
-    s_hi = torch.zeros_like(s_lo)
-    r_lo = torch.zeros_like(s_lo)
-    r_hi = torch.zeros_like(s_lo)
+    # ghost exchange across the strip interfaces (simudo_b200/parallel.py)
+    from simudo_b200.parallel import StripHalo
+    halo = StripHalo(pa, rank, world, dev)
 
     def step_device():
-        halo_exchange(dist, rank, world, s_lo, s_hi, r_lo, r_hi)
+        if world > 1:
+            halo.step(dist, d['u'], d['base_w'])
         plan.assemble(d['u'], d.get('base_w'), d.get('thmeq_phi'), d.get('phi_opt'),
                       bcv, nat, vals, b)
 
@@ -322,12 +307,14 @@ def run_b200(args):
                 sub_problems=pa.P, local_dofs=pa.L, optical_fields=pa.model.n_fields,
                 pattern=('structural non-zeros of the dolfin cell blocks' if pa.pattern == 'structural'
                          else 'dolfin dense cell blocks'), numbering=pa.numbering,
-                parallelism='y-strips x%d, NCCL halo exchange' % world if world > 1 else 'single GPU',
+                parallelism=('y-strips x%d, NCCL ghost exchange %d B/rank/step' % (world, halo.bytes_per_exchange)) if world > 1 else 'single GPU',
                 l2='inputs (%.0f MB) and outputs (%.1f GB) far exceed the 126 MB L2'
                    % (h2d / 1e6, (alg_bytes) / 1e9),
                 finite=finite),
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                          frac=achieved / peak, traffic=None,
+                          frac=achieved / peak,
+                          traffic=(NCU_DRAM_BYTES_PER_CELL[(args.kind, args.pattern)] * pa.n_cells
+                                   if (args.kind, args.pattern) in NCU_DRAM_BYTES_PER_CELL else None),
                           kernel='k_assemble', kernel_ms=k_ms,
                           algorithmic_bytes=alg_bytes, peak_source=peak_kind),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d,
