@@ -274,8 +274,7 @@ SB_HD int sb_gen_sign(const sb_model& M, int p, int k) {
 /* Shockley-Read kernel G = expm1(x) u_R F c and its partials
  * (electro_optical_process.py:294-312), hand-derived.                     */
 SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff,
-                      const SbBandsAtPoint& B, double scale,
-                      double& g, double& dphi, double* dw) {
+                      const SbBandsAtPoint& B, double& g, double& dphi, double* dw) {
   const int IB = M.proc_trap[p];
   const int RB = (M.proc_dst[p] == IB) ? M.proc_src[p] : M.proc_dst[p];
   const double beta = 1.0 / tp[SB_TP_KT];
@@ -285,77 +284,74 @@ SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff,
   const double F = same ? (N_I - B.u[IB]) : B.u[IB];
   const double dF = same ? -B.du[IB] : B.du[IB];
   const double x = sR * (B.w[RB] - B.w[IB]) * beta;
-  const double ex = exp(x), em = expm1(x);
-  const double cs = coeff * scale;
-  g += cs * em * B.u[RB] * F;
-  dphi += cs * em * (B.du[RB] * F + B.u[RB] * dF);
-  dw[RB] += cs * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
-  dw[IB] += cs * B.u[RB] * (-ex * sR * beta * F + em * dF);
+  const double em = expm1(x), ex = em + 1.0;
+  g += coeff * em * B.u[RB] * F;
+  dphi += coeff * em * (B.du[RB] * F + B.u[RB] * dF);
+  dw[RB] += coeff * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
+  dw[IB] += coeff * B.u[RB] * (-ex * sR * beta * F + em * dF);
 }
 
-/* g_k and its partials w.r.t. phi and every w_l at one point */
-SB_NOINLINE void sb_generation(const sb_model& M, const double* tp, int k,
-                         const SbBandsAtPoint& B, const double* phi_clip,
-                         double& g, double& dphi, double* dw) {
+/* One process at one point: G_p (positive = the destination band gains
+ * carriers) and its partials w.r.t. phi and every w_l.  Band k then receives
+ * sign(p, k) * G_p (TwoBandEOPMixin, electro_optical_process.py:193-205).    */
+SB_HD void sb_process_point(const sb_model& M, const double* tp, int p,
+                            const SbBandsAtPoint& B, const double* phi_clip,
+                            double& g, double& dphi, double* dw) {
   g = 0.0; dphi = 0.0;
+#pragma unroll
   for (int l = 0; l < SB_MAX_BANDS; ++l) dw[l] = 0.0;
   const double beta = 1.0 / tp[SB_TP_KT];
-  for (int p = 0; p < M.n_procs; ++p) {
-    const int sgi = sb_gen_sign(M, p, k);
-    if (!sgi) continue;
-    const double sg = (double)sgi;
-    const double* pp = tp + SB_TP_PROC0 + 8 * p;
-    const int dst = M.proc_dst[p], src = M.proc_src[p];
-    switch (M.proc_kind[p]) {
-      case SB_PROC_SRH: {
-        const double D = (B.u[dst] + pp[SB_TPP_P2]) * pp[SB_TPP_P1]
-                       + (B.u[src] + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
-        const double r = (B.u[src] * B.u[dst] - B.u0[src] * B.u0[dst]) / D;
-        const double dr_dst = (B.u[src] - r * pp[SB_TPP_P1]) / D * B.du[dst];
-        const double dr_src = (B.u[dst] - r * pp[SB_TPP_P0]) / D * B.du[src];
-        g -= sg * r;
-        dw[dst] -= sg * dr_dst;
-        dw[src] -= sg * dr_src;
-        dphi -= sg * (dr_dst + dr_src);
-      } break;
-      case SB_PROC_SR_TRAP:
-        sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, sg, g, dphi, dw);
-        break;
-      case SB_PROC_RAD_BB: {
-        double S = 0.0;
-        for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-        g += sg * S;
-        if (M.proc_radiative[p]) {
-          const double x = beta * (B.w[dst] - B.w[src]);
-          const double ex = exp(x);
-          g -= sg * pp[SB_TPP_P0] * expm1(x);
-          dw[dst] -= sg * pp[SB_TPP_P0] * beta * ex;
-          dw[src] += sg * pp[SB_TPP_P0] * beta * ex;
-        }
-      } break;
-      case SB_PROC_RAD_IB: {
-        const int IB = M.proc_trap[p];
-        const int RB = (dst == IB) ? src : dst;
-        const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
-        const bool same = (M.band_sign[IB] == M.band_sign[RB]);
-        const double Fa = same ? B.u[IB] : (N_I - B.u[IB]);
-        const double dFa = same ? B.du[IB] : -B.du[IB];
-        double S = 0.0;
-        for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-        g += sg * S * Fa;
-        dw[IB] += sg * S * dFa;
-        dphi += sg * S * dFa;
-        if (M.proc_radiative[p])
-          sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, sg, g, dphi, dw);
-      } break;
-      default: break;
-    }
+  const double* pp = tp + SB_TP_PROC0 + 8 * p;
+  const int dst = M.proc_dst[p], src = M.proc_src[p];
+  switch (M.proc_kind[p]) {
+    case SB_PROC_SRH: {
+      const double D = (B.u[dst] + pp[SB_TPP_P2]) * pp[SB_TPP_P1]
+                     + (B.u[src] + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
+      const double r = (B.u[src] * B.u[dst] - B.u0[src] * B.u0[dst]) / D;
+      const double dr_dst = (B.u[src] - r * pp[SB_TPP_P1]) / D * B.du[dst];
+      const double dr_src = (B.u[dst] - r * pp[SB_TPP_P0]) / D * B.du[src];
+      g = -r;
+      dw[dst] = -dr_dst;
+      dw[src] -= dr_src;
+      dphi = -(dr_dst + dr_src);
+    } break;
+    case SB_PROC_SR_TRAP:
+      sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, g, dphi, dw);
+      break;
+    case SB_PROC_RAD_BB: {
+      double S = 0.0;
+      for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+      g = S;
+      if (M.proc_radiative[p]) {
+        const double x = beta * (B.w[dst] - B.w[src]);
+        const double em = expm1(x), ex = em + 1.0;
+        g -= pp[SB_TPP_P0] * em;
+        dw[dst] -= pp[SB_TPP_P0] * beta * ex;
+        dw[src] += pp[SB_TPP_P0] * beta * ex;
+      }
+    } break;
+    case SB_PROC_RAD_IB: {
+      const int IB = M.proc_trap[p];
+      const int RB = (dst == IB) ? src : dst;
+      const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
+      const bool same = (M.band_sign[IB] == M.band_sign[RB]);
+      const double Fa = same ? B.u[IB] : (N_I - B.u[IB]);
+      const double dFa = same ? B.du[IB] : -B.du[IB];
+      double S = 0.0;
+      for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+      g = S * Fa;
+      dw[IB] = S * dFa;
+      dphi = S * dFa;
+      if (M.proc_radiative[p])
+        sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, g, dphi, dw);
+    } break;
+    default: break;
   }
 }
 
-/* Moments of g_k, dg_k/dphi, dg_k/dw_l for every band k at once (each point's
- * band data is evaluated once).  dgv[p][3]: P1 nodal values of (phi |
- * delta_w_l); w0[l]: base_w of the cell; inside[k]: cell in band k's subdomain.
+/* Moments of g_k, dg_k/dphi, dg_k/dw_l for every band k at once: per point each
+ * band's density and each process are evaluated once.  dgv[p][3]: P1 nodal
+ * values of (phi | delta_w_l); w0[l]: base_w of the cell.
  * out mG[k][.]: [0..2] g (P1), [3..8] d/dphi (P2), [9+6l ..] d/dw_l (P2).       */
 template <int NB>
 SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
@@ -398,20 +394,40 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
       for (int a = 0; a < 6; ++a) v += pf[a] * n2[a];
       phi_clip[f] = v < 0.0 ? 0.0 : v;      /* optical.py:201-203 */
     }
+    /* pointwise totals per band */
+    double gk[NB > 0 ? NB : 1], dphik[NB > 0 ? NB : 1], dwk[NB > 0 ? NB : 1][SB_MAX_BANDS];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      gk[k] = 0.0; dphik[k] = 0.0;
+#pragma unroll
+      for (int l = 0; l < SB_MAX_BANDS; ++l) dwk[k][l] = 0.0;
+    }
+#pragma unroll 1
+    for (int p = 0; p < M.n_procs; ++p) {
+      double g, dphi, dw[SB_MAX_BANDS];
+      sb_process_point(M, tp, p, B, phi_clip, g, dphi, dw);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const int sgi = sb_gen_sign(M, p, k);
+        if (!sgi) continue;
+        const double sg = (double)sgi;
+        gk[k] += sg * g; dphik[k] += sg * dphi;
+#pragma unroll
+        for (int l = 0; l < NB; ++l) dwk[k][l] += sg * dw[l];
+      }
+    }
     const double* wp = T.gwpsi[n];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       if (!inside[k]) continue;
-      double g, dphi, dw[SB_MAX_BANDS];
-      sb_generation(M, tp, k, B, phi_clip, g, dphi, dw);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) mG[k][t] += wp[t] * g;
+      for (int t = 0; t < 3; ++t) mG[k][t] += wp[t] * gk[k];
 #pragma unroll
-      for (int t = 0; t < 6; ++t) mG[k][3 + t] += wp[t] * dphi;
+      for (int t = 0; t < 6; ++t) mG[k][3 + t] += wp[t] * dphik[k];
 #pragma unroll
       for (int l = 0; l < NB; ++l)
 #pragma unroll
-        for (int t = 0; t < 6; ++t) mG[k][9 + 6 * l + t] += wp[t] * dw[l];
+        for (int t = 0; t < 6; ++t) mG[k][9 + 6 * l + t] += wp[t] * dwk[k][l];
     }
   }
 }

@@ -63,6 +63,7 @@ struct PlanDev {
   const int32_t* sp_nat_begin;   /* [n_special+1]                            */
   const int32_t* natbc_row;      /* sorted by cell                           */
   const SbTables* tables;        /* global copy for lane-varying indexing    */
+  double* scratch;               /* [(nb*44 + nb_dof*SB_NG)][n_cells] moments  */
 };
 
 struct sb_plan {
@@ -113,172 +114,144 @@ __global__ void k_zero_shared(PlanDev pl, double* vals, double* b) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* One thread = one cell.  All table operands are warp-uniform (constant bank),
- * moments live in registers; the only memory traffic is the nodal gather, the
- * per-cell index data and the scatter.  NB = number of bands with dofs
- * (compile-time so every per-band array stays in registers); SP = the cell has
- * Dirichlet dofs (rare; kept on a compact rolled code path).                  */
-template <int NB>
-__device__ __forceinline__ void assemble_cell(const PlanDev& pl, const StateDev& st,
-                                              double* vals, double* b, int64_t c, SbIO& io,
-                                              int nb0, int nb1, const bool sp) {
-  const int nb = pl.nb;                       /* bands entering rho */
+/* The assembly is three launches with small code footprints and independent
+ * occupancy instead of one fused kernel (the fused variant spent a third of
+ * its cycles waiting for instructions, profiles/README.md):
+ *   k_moments     thread = (cell, band):   phase A, coefficient moments
+ *   k_generation  thread = cell:           phase B, generation moments
+ *   k_rows        thread = (cell, sub-problem): phase C, entries + scatter
+ * Moments travel through an L2-friendly scratch array laid out [moment][cell]
+ * so that both the producer and the consumer access it coalesced.            */
+#define SB_NMOMA (SB_NMC + SB_NQ + SB_NRX + SB_NR)     /* 44 per (cell, band) */
+
+__device__ __forceinline__ double* momA_ptr(const PlanDev& pl, int k, int64_t c) {
+  return pl.scratch + (int64_t)k * SB_NMOMA * pl.n_cells + c;
+}
+__device__ __forceinline__ double* momG_ptr(const PlanDev& pl, int k, int64_t c) {
+  return pl.scratch + ((int64_t)pl.nb * SB_NMOMA + (int64_t)k * SB_NG) * pl.n_cells + c;
+}
+
+__global__ void __launch_bounds__(SB_TILE)
+k_moments(PlanDev pl, StateDev st, int nblk) {
+  const int k = blockIdx.x / nblk;
+  const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
   const int L = pl.L;
+  const bool has_dofs = k < pl.nb_dof;
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-  const int32_t* dofs = io.dofs;
-  (void)L;
+  const int32_t* dofs = pl.cell_dofs + c * L;
+  const SbBandK K = sb_band_consts(c_M, tp, k);
+  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+  const bool dd = inside && has_dofs;
+  double phi[3], dw[3] = {0.0, 0.0, 0.0}, w0 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) phi[i] = st.u[dofs[i]];
+  double gc[2][6];
+  if (has_dofs) {
+    w0 = st.base_w[(int64_t)k * pl.n_cells + c];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dw[i] = st.u[dofs[sb_ldg(1 + k, i)]];
+  }
+  if (dd) {
+    double jc[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      const double fm = st.u[dofs[sb_lbdm(1 + k, m)]];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) jc[a][r] += fm * c_T.bdmC[m][a][r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
+      gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
+    }
+  }
+  const double chi0 = phi[0] + dw[0] + w0;
+  const double chix = (phi[1] - phi[0]) + (dw[1] - dw[0]);
+  const double chiy = (phi[2] - phi[0]) + (dw[2] - dw[0]);
+  double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX], mR[SB_NR] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int t = 0; t < SB_NMC; ++t) mC[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+  const bool rho = (K.N != 0.0);
+  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
+  if (same_rule && c_M.quad_m_super == 11) {
+    if (rho || dd) sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+  } else if (same_rule) {
+    if (rho || dd) sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+  } else {
+    if (rho) sb_phaseA_band<0>(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    if (dd) sb_phaseA_band<0>(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+  }
+  double* o = momA_ptr(pl, k, c);
+  const int64_t nc = pl.n_cells;
+  if (dd) {
+#pragma unroll
+    for (int t = 0; t < SB_NMC; ++t) o[(int64_t)t * nc] = mC[t];
+#pragma unroll
+    for (int t = 0; t < SB_NQ; ++t) o[(int64_t)(SB_NMC + t) * nc] = Q[t];
+  }
+#pragma unroll
+  for (int t = 0; t < SB_NRX; ++t) o[(int64_t)(SB_NMC + SB_NQ + t) * nc] = mRx[t];
+#pragma unroll
+  for (int t = 0; t < SB_NR; ++t) o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc] = mR[t];
+}
 
-  /* nodal values of the DG1 fields phi, delta_w_k and base_w */
+template <int NB>
+__global__ void __launch_bounds__(SB_TILE)
+k_generation(PlanDev pl, StateDev st) {
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  const int L = pl.L;
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const int32_t* dofs = pl.cell_dofs + c * L;
   double dgv[1 + SB_MAX_BANDS][3];
   double w0[SB_MAX_BANDS];
+  bool inside_k[SB_MAX_BANDS];
 #pragma unroll
   for (int i = 0; i < 3; ++i) dgv[0][i] = st.u[dofs[i]];
 #pragma unroll
   for (int k = 0; k < SB_MAX_BANDS; ++k) {
-    w0[k] = 0.0;
+    w0[k] = 0.0; inside_k[k] = false;
 #pragma unroll
     for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
     if (k < NB) {
       w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
+      inside_k[k] = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
 #pragma unroll
       for (int i = 0; i < 3; ++i) dgv[1 + k][i] = st.u[dofs[sb_ldg(1 + k, i)]];
     }
   }
-  double mR[SB_NR] = {0.0, 0.0, 0.0};
-  double mX[1 + SB_MAX_BANDS][SB_NRX];      /* [0] = sum over bands, [1+k] = band k */
+  double mG[NB > 0 ? NB : 1][SB_NG];
+  sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k, st.thmeq ? st.thmeq + c * 6 : nullptr,
+                    st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
+  const int64_t nc = pl.n_cells;
 #pragma unroll
-  for (int q = 0; q < 1 + SB_MAX_BANDS; ++q)
+  for (int k = 0; k < NB; ++k) {
+    double* o = momG_ptr(pl, k, c);
 #pragma unroll
-    for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
-  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
-  const bool std_rule = same_rule && (c_M.quad_m_super == 11);
-  bool inside_k[SB_MAX_BANDS] = {false, false, false, false};
-
-#pragma unroll 1
-  for (int k = 0; k < nb; ++k) {
-    const SbBandK K = sb_band_consts(c_M, tp, k);
-    const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
-    const bool dd = inside && (k < NB);
-    inside_k[k] = inside;
-    double fl[12];
-    double gc[2][6];
-    if (k < NB) {
-#pragma unroll
-      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
-    }
-    if (dd) {
-      double jc[2][6];
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
-#pragma unroll
-      for (int m = 0; m < 12; ++m)
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int r = 0; r < 6; ++r) jc[a][r] += fl[m] * c_T.bdmC[m][a][r];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
-        gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
-      }
-    }
-    const double chi0 = dgv[0][0] + dgv[1 + k][0] + w0[k];
-    const double chix = (dgv[0][1] - dgv[0][0]) + (dgv[1 + k][1] - dgv[1 + k][0]);
-    const double chiy = (dgv[0][2] - dgv[0][0]) + (dgv[1 + k][2] - dgv[1 + k][0]);
-    double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX];
-    const bool rho = (K.N != 0.0);
-#pragma unroll
-    for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
-    if (std_rule) {
-      if (rho || dd)
-        sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-    } else if (same_rule) {
-      if (rho || dd)
-        sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-    } else {
-      if (rho) sb_phaseA_band<0>(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-      if (dd) sb_phaseA_band<0>(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-    }
-#pragma unroll
-    for (int t = 0; t < SB_NRX; ++t) { mX[1 + k][t] = mRx[t]; mX[0][t] += mRx[t]; }
-    if (k < NB) {
-      /* base_w jump term on interior facets where this cell is the '+' side */
-      double jumpf[3];
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        jumpf[f] = 0.0;
-        if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
-          const int64_t cn = pl.cell_neighbors[c * 3 + f];
-          const double ref_out = (f == 1) ? -1.0 : 1.0;
-          jumpf[f] = (st.base_w[(int64_t)k * pl.n_cells + cn] - w0[k]) * ref_out * g.sdet;
-        }
-      }
-      const int mode = inside ? 1 : 2;
-      if (sp)
-        sb_rows_flux<true>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
-                           jumpf[0], jumpf[1], jumpf[2],
-                           pl.natbc_row, st.natbc_values, nb0, nb1);
-      else
-        sb_rows_flux<false>(c_T, c_M, io, g, 1 + k, mode, mC, Q, fl, dgv[1 + k],
-                            jumpf[0], jumpf[1], jumpf[2],
-                            pl.natbc_row, st.natbc_values, nb0, nb1);
-    }
-  }
-
-  /* generation moments (all bands at once) + continuity rows v^k */
-  if (NB > 0) {
-    double mG[NB > 0 ? NB : 1][SB_NG];
-    sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k,
-                      st.thmeq ? st.thmeq + c * 6 : nullptr,
-                      st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG);
-#pragma unroll 1
-    for (int k = 0; k < NB; ++k) {
-      double fl[12];
-#pragma unroll
-      for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(1 + k, m)]];
-      const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-      if (sp)
-        sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
-                                     mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
-      else
-        sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 1 + k, inside_k[k], fl, dgv[1 + k], coef,
-                                      mG[k], mG[k] + 3, pl.natbc_row, st.natbc_values, nb0, nb1);
-    }
-  }
-
-  /* Poisson rows */
-  {
-    /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
-    mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
-    double fl[12];
-#pragma unroll
-    for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(0, m)]];
-    if (sp) {
-      sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
-                                   pl.natbc_row, st.natbc_values, nb0, nb1);
-      sb_rows_flux<true>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
-                         pl.natbc_row, st.natbc_values, nb0, nb1);
-    } else {
-      sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 0, true, fl, dgv[0], -g.adet, mR, &mX[0][0],
-                                    pl.natbc_row, st.natbc_values, nb0, nb1);
-      sb_rows_flux<false>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, dgv[0], 0.0, 0.0, 0.0,
-                          pl.natbc_row, st.natbc_values, nb0, nb1);
-    }
+    for (int t = 0; t < 9 + 6 * NB; ++t) o[(int64_t)t * nc] = mG[k][t];
   }
 }
 
-#ifndef SB_MIN_BLOCKS
-#define SB_MIN_BLOCKS 2
-#endif
 template <int NB>
-__global__ void __launch_bounds__(SB_TILE, SB_MIN_BLOCKS)
-k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
-  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+__global__ void __launch_bounds__(SB_TILE)
+k_rows(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
+  const int p = blockIdx.x / nblk;
+  const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
   const int L = pl.L;
+  const int64_t nc = pl.n_cells;
   SbIO io;
   io.L = L;
   io.dofs = pl.cell_dofs + c * L;
@@ -288,13 +261,103 @@ k_assemble(PlanDev pl, StateDev st, double* vals, double* b) {
   io.vals = vals; io.b = b;
   io.mlo = 0; io.mhi = 0; io.bcidx = nullptr;
   int nb0 = 0, nb1 = 0;
-  const int32_t sp = pl.cell_special[c];
-  if (sp >= 0) {
-    io.mlo = pl.sp_mask_lo[sp]; io.mhi = pl.sp_mask_hi[sp];
-    io.bcidx = pl.sp_bcidx + (int64_t)sp * L;
-    nb0 = pl.sp_nat_begin[sp]; nb1 = pl.sp_nat_begin[sp + 1];
+  const int32_t spc = pl.cell_special[c];
+  if (spc >= 0) {
+    io.mlo = pl.sp_mask_lo[spc]; io.mhi = pl.sp_mask_hi[spc];
+    io.bcidx = pl.sp_bcidx + (int64_t)spc * L;
+    nb0 = pl.sp_nat_begin[spc]; nb1 = pl.sp_nat_begin[spc + 1];
   }
-  assemble_cell<NB>(pl, st, vals, b, c, io, nb0, nb1, (io.mlo | io.mhi) != 0);
+  const bool sp = (io.mlo | io.mhi) != 0;
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const int32_t* dofs = io.dofs;
+  double fl[12], sl[3];
+#pragma unroll
+  for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(p, m)]];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sl[i] = st.u[dofs[sb_ldg(p, i)]];
+
+  if (p == 0) {
+    /* Poisson rows: rho moments summed over the bands */
+    double mR[SB_NR] = {0.0, 0.0, 0.0};
+    double mX[1 + SB_MAX_BANDS][SB_NRX];
+#pragma unroll
+    for (int q = 0; q < 1 + SB_MAX_BANDS; ++q)
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
+    for (int k = 0; k < pl.nb; ++k) {
+      const double* o = momA_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) {
+        const double v = o[(int64_t)(SB_NMC + SB_NQ + t) * nc];
+        mX[0][t] += v;
+        if (k < NB) mX[1 + k][t] = v;
+      }
+#pragma unroll
+      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc];
+    }
+    /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
+    mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
+    if (sp) {
+      sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, 0, true, fl, sl, -g.adet, mR, &mX[0][0],
+                                   pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<true>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, sl, 0.0, 0.0, 0.0,
+                         pl.natbc_row, st.natbc_values, nb0, nb1);
+    } else {
+      sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, 0, true, fl, sl, -g.adet, mR, &mX[0][0],
+                                    pl.natbc_row, st.natbc_values, nb0, nb1);
+      sb_rows_flux<false>(c_T, c_M, io, g, 0, 0, nullptr, nullptr, fl, sl, 0.0, 0.0, 0.0,
+                          pl.natbc_row, st.natbc_values, nb0, nb1);
+    }
+    return;
+  }
+
+  const int k = p - 1;
+  const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+  {
+    double mC[SB_NMC], Q[SB_NQ];
+    if (inside) {
+      const double* o = momA_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < SB_NMC; ++t) mC[t] = o[(int64_t)t * nc];
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NMC + t) * nc];
+    }
+    /* base_w jump term on interior facets where this cell is the '+' side */
+    double jumpf[3];
+    const double w0 = st.base_w[(int64_t)k * nc + c];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      jumpf[f] = 0.0;
+      if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
+        const int64_t cn = pl.cell_neighbors[c * 3 + f];
+        const double ref_out = (f == 1) ? -1.0 : 1.0;
+        jumpf[f] = (st.base_w[(int64_t)k * nc + cn] - w0) * ref_out * g.sdet;
+      }
+    }
+    const int mode = inside ? 1 : 2;
+    if (sp)
+      sb_rows_flux<true>(c_T, c_M, io, g, p, mode, mC, Q, fl, sl, jumpf[0], jumpf[1], jumpf[2],
+                         pl.natbc_row, st.natbc_values, nb0, nb1);
+    else
+      sb_rows_flux<false>(c_T, c_M, io, g, p, mode, mC, Q, fl, sl, jumpf[0], jumpf[1], jumpf[2],
+                          pl.natbc_row, st.natbc_values, nb0, nb1);
+  }
+  {
+    double mG[SB_NG];
+    if (inside) {
+      const double* o = momG_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = o[(int64_t)t * nc];
+    }
+    const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+    if (sp)
+      sb_rows_scalar<true, 1 + NB>(c_T, c_M, io, g, p, inside, fl, sl, coef, mG, mG + 3,
+                                   pl.natbc_row, st.natbc_values, nb0, nb1);
+    else
+      sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, p, inside, fl, sl, coef, mG, mG + 3,
+                                    pl.natbc_row, st.natbc_values, nb0, nb1);
+  }
 }
 
 /* ------------------------------------------------------------------------- */
@@ -573,6 +636,10 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   const double* tmp = nullptr;
   if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc, &tmp);
   pl->tmp_cells = const_cast<double*>(tmp);
+  const double* scr = nullptr;
+  if (rc == SB_OK)
+    rc = upload<double>(pl, nullptr, (size_t)nc * ((size_t)model->n_bands * 44 + (size_t)nbd * SB_NG), &scr);
+  d.scratch = const_cast<double*>(scr);
 #undef UP
   if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }
   *out = pl;
@@ -618,17 +685,28 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
 #endif
   const unsigned nblk = (unsigned)((nc + SB_TILE - 1) / SB_TILE);
+  int nl = 2;
+  if (pl->d.nb > 0) {
+    SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk);
+    ++nl;
+  }
+  const unsigned nrow = nblk * (unsigned)pl->d.P;
   switch (pl->d.nb_dof) {
-    case 0: SB_LAUNCH(k_assemble<0>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
-    case 1: SB_LAUNCH(k_assemble<1>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
-    case 2: SB_LAUNCH(k_assemble<2>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
-    case 3: SB_LAUNCH(k_assemble<3>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
-    default: SB_LAUNCH(k_assemble<4>, nblk, SB_TILE, 0, s, pl->d, sd, d_vals, d_b); break;
+    case 0: SB_LAUNCH(k_rows<0>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); break;
+    case 1: SB_LAUNCH(k_generation<1>, nblk, SB_TILE, 0, s, pl->d, sd);
+            SB_LAUNCH(k_rows<1>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+    case 2: SB_LAUNCH(k_generation<2>, nblk, SB_TILE, 0, s, pl->d, sd);
+            SB_LAUNCH(k_rows<2>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+    case 3: SB_LAUNCH(k_generation<3>, nblk, SB_TILE, 0, s, pl->d, sd);
+            SB_LAUNCH(k_rows<3>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+    default: SB_LAUNCH(k_generation<4>, nblk, SB_TILE, 0, s, pl->d, sd);
+             SB_LAUNCH(k_rows<4>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
   }
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
 #endif
-  g_launches += 2;
+  g_launches += nl;
+
   CUDA_TRY(cudaGetLastError());
   return SB_OK;
 }
