@@ -675,4 +675,179 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
   for (int i = 0; i < 3; ++i) sb_put_row<SP>(io, r0 + i, F[i]);
 }
 
+/* ========================================================================= *
+ * Fast row path: cells without Dirichlet dofs / natural-BC rows (all but the
+ * boundary layer), compile-time sub-problem PS.  Ranks come from the packed
+ * emission-order table patk[pattern][row][32] (two 16-byte loads per row):
+ *   BDM row: [0..11] BDM cols of PS, [12..14] DG cols of PS, [15..17] DG cols of 0
+ *   DG  row: [0..11] BDM cols of PS, [12 + 3 q + l] DG col l of sub-problem q
+ * ========================================================================= */
+struct SbFastIO {
+  const int32_t* dofs;
+  const uint8_t* patk;       /* [L][32] packed ranks of this cell's pattern */
+  const int64_t* rowptr;
+  double* vals;
+  double* b;
+};
+
+struct SbRanks { uint32_t w[8]; };
+
+SB_HD SbRanks sb_load_ranks(const uint8_t* patk, int li) {
+  SbRanks r;
+  const uint4* q = reinterpret_cast<const uint4*>(patk + li * 32);
+  const uint4 a = q[0], b = q[1];
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  return r;
+}
+SB_HD int sb_rank(const SbRanks& r, int e) { return (int)((r.w[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+
+SB_HD void sb_store(double* vals, int64_t rowbase, int rk, double v, bool shared_slot) {
+  if (!vals || rk == 0xFF) return;
+  double* dst = vals + rowbase + rk;
+  if (shared_slot) SB_ATOMIC_ADD(dst, v); else *dst = v;
+}
+
+/* BDM rows of sub-problem PS; MODE 0: Poisson psi rows, 1: band inside its
+ * subdomain, 2: band outside (see sb_rows_flux for the algebra)               */
+template <int PS, int MODE>
+SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastIO& io,
+                             const SbCellGeom& g, const double* mC, const double* Q,
+                             const double* fl, const double* sl,
+                             double jump0, double jump1, double jump2) {
+  constexpr int r0 = 15 * PS + 3;
+  double W[21];
+  double V[2][6][3];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 21; ++e) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < 15; ++t) v += T.G22u[e][t] * mC[t];
+      W[e] = v;
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * Q[a * 10 + t];
+          V[a][r][l] = v;
+        }
+  }
+  const double sc = (MODE == 2 ? M.ext_j_coef : 1.0) * g.iad;
+  const double divsign = (MODE == 0) ? -g.sdet : g.sdet;
+#pragma unroll 1
+  for (int i = 0; i < 12; ++i) {
+    double Ci[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ci[a][r] = T.bdmC[i][a][r];
+    double GY[2][6];
+#pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+      double y0, y1;
+      if (MODE == 1) {
+        y0 = 0.0; y1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          y0 += Ci[0][r] * W[sb_sym21(r, s2)];
+          y1 += Ci[1][r] * W[sb_sym21(r, s2)];
+        }
+      } else {                       /* W = identity: plain BDM mass matrix */
+        y0 = Ci[0][s2]; y1 = Ci[1][s2];
+      }
+      GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
+      GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
+    }
+    const int li = r0 + i;
+    const int fi = (i < 9) ? i / 3 : -1;
+    const int64_t rowbase = io.rowptr[io.dofs[li]];
+    const SbRanks rk = sb_load_ranks(io.patk, li);
+    double Fi = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      double v = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2)
+        v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
+      Fi += v * fl[m];
+      sb_store(io.vals, rowbase, sb_rank(rk, m), v, (m < 9) && (m / 3 == fi));
+    }
+    if (MODE != 2) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double dv = divsign * T.Dhat[i][l];
+        Fi += dv * sl[l];
+        if (MODE == 1) {
+          double d = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
+          d *= g.iad;
+          sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv + d, false);
+          sb_store(io.vals, rowbase, sb_rank(rk, 15 + l), d, false);
+        } else {
+          sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv, false);
+        }
+      }
+    }
+    if (MODE == 1 && i < 9) {
+      const double jf = (i < 3) ? jump0 : (i < 6 ? jump1 : jump2);
+      Fi -= jf * T.trI[i % 3];
+    }
+    if (io.b) {
+      double* dst = io.b + io.dofs[li];
+      if (fi >= 0) SB_ATOMIC_ADD(dst, Fi); else *dst = Fi;
+    }
+  }
+}
+
+/* DG1 rows of sub-problem PS (w for PS = 0, v^k otherwise) */
+template <int PS, int NQ>
+SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFastIO& io,
+                               const SbCellGeom& g, bool inside, const double* fl,
+                               const double* sl, double coef, const double* mom1,
+                               const double* momJ) {
+  constexpr int r0 = 15 * PS;
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i) {
+    const int li = r0 + i;
+    const int64_t rowbase = io.rowptr[io.dofs[li]];
+    const SbRanks rk = sb_load_ranks(io.patk, li);
+    double Fi = 0.0;
+    if (inside) {
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        const double dv = g.sdet * T.Dhat[m][i];
+        Fi += dv * fl[m];
+        sb_store(io.vals, rowbase, sb_rank(rk, m), dv, false);
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) Fi += coef * T.G1[i][t] * mom1[t];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
+          sb_store(io.vals, rowbase, sb_rank(rk, 12 + 3 * q + l), coef * v, false);
+        }
+    } else {
+      const double c1 = M.ext_w_coef * g.adet;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double v = c1 * T.M1[i][l];
+        Fi += v * sl[l];
+        sb_store(io.vals, rowbase, sb_rank(rk, 12 + 3 * PS + l), v, false);
+      }
+    }
+    if (io.b) io.b[io.dofs[li]] = Fi;
+  }
+}
+
 #endif /* SB_PDD_DEVICE_CUH */

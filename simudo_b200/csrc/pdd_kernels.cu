@@ -55,6 +55,9 @@ struct PlanDev {
   const int64_t* rowptr;
   const uint8_t* patterns;       /* [n_patterns][L][L]                       */
   const int32_t* cell_pattern;   /* [n_cells]                                */
+  const uint8_t* patk;           /* [n_patterns][L][32] packed emission-order ranks */
+  const int32_t* sp_cells;       /* [n_special] cells with Dirichlet / natural-BC rows */
+  int64_t n_special;
   const double* tag_params;
   const int32_t* cell_special;   /* [n_cells] -1 or special index            */
   const uint64_t* sp_mask_lo;
@@ -244,12 +247,14 @@ k_generation(PlanDev pl, StateDev st) {
   }
 }
 
+/* boundary layer: cells with Dirichlet dofs or natural-BC rows (generic path) */
 template <int NB>
 __global__ void __launch_bounds__(SB_TILE)
-k_rows(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
+k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
   const int p = blockIdx.x / nblk;
-  const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
-  if (c >= pl.n_cells) return;
+  const int64_t is = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
+  if (is >= pl.n_special) return;
+  const int64_t c = pl.sp_cells[is];
   const int L = pl.L;
   const int64_t nc = pl.n_cells;
   SbIO io;
@@ -357,6 +362,111 @@ k_rows(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
     else
       sb_rows_scalar<false, 1 + NB>(c_T, c_M, io, g, p, inside, fl, sl, coef, mG, mG + 3,
                                     pl.natbc_row, st.natbc_values, nb0, nb1);
+  }
+}
+
+/* interior cells (no Dirichlet dofs, no natural-BC rows): compile-time
+ * sub-problem, packed ranks, no boundary logic */
+template <int NB, int PS>
+__global__ void __launch_bounds__(SB_TILE)
+k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  if (pl.cell_special[c] >= 0) return;           /* handled by k_rows_special */
+  const int L = pl.L;
+  const int64_t nc = pl.n_cells;
+  SbFastIO io;
+  io.dofs = pl.cell_dofs + c * L;
+  io.patk = pl.patk + (int64_t)pl.cell_pattern[c] * L * 32;
+  io.rowptr = pl.rowptr;
+  io.vals = vals; io.b = b;
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const int32_t* dofs = io.dofs;
+  double fl[12], sl[3];
+#pragma unroll
+  for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(PS, m)]];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sl[i] = st.u[dofs[sb_ldg(PS, i)]];
+  if (PS == 0) {
+    double mR[SB_NR] = {0.0, 0.0, 0.0};
+    double mX[1 + SB_MAX_BANDS][SB_NRX];
+#pragma unroll
+    for (int q = 0; q < 1 + SB_MAX_BANDS; ++q)
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SB_MAX_BANDS; ++k) {
+      if (k >= pl.nb) break;
+      const double* o = momA_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) {
+        const double v = o[(int64_t)(SB_NMC + SB_NQ + t) * nc];
+        mX[0][t] += v;
+        if (k < NB) mX[1 + k][t] = v;
+      }
+#pragma unroll
+      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc];
+    }
+    mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
+    sb_rows_scalar_fast<0, 1 + NB>(c_T, c_M, io, g, true, fl, sl, -g.adet, mR, &mX[0][0]);
+    sb_rows_flux_fast<0, 0>(c_T, c_M, io, g, nullptr, nullptr, fl, sl, 0.0, 0.0, 0.0);
+  } else {
+    constexpr int k = PS > 0 ? PS - 1 : 0;
+    const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+    if (inside) {
+      double mC[SB_NMC], Q[SB_NQ];
+      const double* o = momA_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < SB_NMC; ++t) mC[t] = o[(int64_t)t * nc];
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NMC + t) * nc];
+      double jumpf[3];
+      const double w0 = st.base_w[(int64_t)k * nc + c];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        jumpf[f] = 0.0;
+        if ((pl.cell_jump_mask[c * 3 + f] >> k) & 1) {
+          const int64_t cn = pl.cell_neighbors[c * 3 + f];
+          const double ref_out = (f == 1) ? -1.0 : 1.0;
+          jumpf[f] = (st.base_w[(int64_t)k * nc + cn] - w0) * ref_out * g.sdet;
+        }
+      }
+      sb_rows_flux_fast<PS, 1>(c_T, c_M, io, g, mC, Q, fl, sl, jumpf[0], jumpf[1], jumpf[2]);
+      double mG[SB_NG];
+      const double* og = momG_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = og[(int64_t)t * nc];
+      const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+      sb_rows_scalar_fast<PS, 1 + NB>(c_T, c_M, io, g, true, fl, sl, coef, mG, mG + 3);
+    } else {
+      sb_rows_flux_fast<PS, 2>(c_T, c_M, io, g, nullptr, nullptr, fl, sl, 0.0, 0.0, 0.0);
+      sb_rows_scalar_fast<PS, 1 + NB>(c_T, c_M, io, g, false, fl, sl, 0.0, nullptr, nullptr);
+    }
+  }
+}
+
+/* launch k_rows_fast<NB, PS> for PS = 0 .. NB */
+template <int NB, int PS>
+struct RowsLauncher {
+  static void go(const PlanDev& d, const StateDev& sd, double* vals, double* b, unsigned nblk,
+                 cudaStream_t s) {
+    SB_LAUNCH((k_rows_fast<NB, PS>), nblk, SB_TILE, 0, s, d, sd, vals, b);
+    RowsLauncher<NB, PS - 1>::go(d, sd, vals, b, nblk, s);
+  }
+};
+template <int NB>
+struct RowsLauncher<NB, -1> {
+  static void go(const PlanDev&, const StateDev&, double*, double*, unsigned, cudaStream_t) {}
+};
+
+template <int NB>
+static void launch_rows(const PlanDev& d, const StateDev& sd, double* vals, double* b,
+                        unsigned nblk, cudaStream_t s) {
+  RowsLauncher<NB, NB>::go(d, sd, vals, b, nblk, s);
+  if (d.n_special > 0) {
+    const unsigned nsb = (unsigned)((d.n_special + SB_TILE - 1) / SB_TILE);
+    SB_LAUNCH(k_rows_special<NB>, nsb * (unsigned)d.P, SB_TILE, 0, s, d, sd, vals, b, (int)nsb);
   }
 }
 
@@ -628,6 +738,30 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   }
   pl->n_bc = pr->n_bc; pl->n_natbc = pr->n_natbc;
   UP(cell_special, special.data(), nc);
+  {
+    /* packed emission-order ranks for the fast row kernels */
+    const int64_t np = pr->n_patterns;
+    const int Pn = pr->P;
+    std::vector<uint8_t> patk((size_t)np * L * 32, 0xFF);
+    for (int64_t q = 0; q < np; ++q)
+      for (int li = 0; li < L; ++li) {
+        const uint8_t* row = pr->h_patterns + ((size_t)q * L + li) * L;
+        uint8_t* o = patk.data() + ((size_t)q * L + li) * 32;
+        const int p = li / 15, r = li % 15;
+        for (int e = 0; e < 12; ++e) o[e] = row[15 * p + 3 + e];
+        if (r < 3) {
+          for (int qq = 0; qq < Pn; ++qq)
+            for (int l = 0; l < 3; ++l) o[12 + 3 * qq + l] = row[15 * qq + l];
+        } else {
+          for (int l = 0; l < 3; ++l) { o[12 + l] = row[15 * p + l]; o[15 + l] = row[l]; }
+        }
+      }
+    UP(patk, patk.data(), patk.size());
+    std::vector<int32_t> spc;
+    for (int64_t c = 0; c < nc; ++c) if (special[c] >= 0) spc.push_back((int32_t)c);
+    UP(sp_cells, spc.data(), spc.size());
+    d.n_special = (int64_t)spc.size();
+  }
   UP(sp_mask_lo, mlo.data(), mlo.size());
   UP(sp_mask_hi, mhi.data(), mhi.size());
   UP(sp_bcidx, bcidx.data(), bcidx.size());
@@ -690,18 +824,18 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
     SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk);
     ++nl;
   }
-  const unsigned nrow = nblk * (unsigned)pl->d.P;
   switch (pl->d.nb_dof) {
-    case 0: SB_LAUNCH(k_rows<0>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); break;
+    case 0: launch_rows<0>(pl->d, sd, d_vals, d_b, nblk, s); break;
     case 1: SB_LAUNCH(k_generation<1>, nblk, SB_TILE, 0, s, pl->d, sd);
-            SB_LAUNCH(k_rows<1>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+            launch_rows<1>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
     case 2: SB_LAUNCH(k_generation<2>, nblk, SB_TILE, 0, s, pl->d, sd);
-            SB_LAUNCH(k_rows<2>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+            launch_rows<2>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
     case 3: SB_LAUNCH(k_generation<3>, nblk, SB_TILE, 0, s, pl->d, sd);
-            SB_LAUNCH(k_rows<3>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+            launch_rows<3>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
     default: SB_LAUNCH(k_generation<4>, nblk, SB_TILE, 0, s, pl->d, sd);
-             SB_LAUNCH(k_rows<4>, nrow, SB_TILE, 0, s, pl->d, sd, d_vals, d_b, (int)nblk); ++nl; break;
+             launch_rows<4>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
   }
+  nl += pl->d.P + (pl->d.n_special > 0 ? 1 : 0) - 1;
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
 #endif

@@ -31,6 +31,7 @@
 #define __launch_bounds__(...)
 
 struct dim3e { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 static thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;
 
 typedef int cudaError_t;
