@@ -716,6 +716,12 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
                              const double* fl, const double* sl,
                              double jump0, double jump1, double jump2) {
   constexpr int r0 = 15 * PS + 3;
+  /* row bases are two dependent global loads (dof index, row pointer): fetch the
+     first group now and the next group one group ahead of its use */
+  int32_t dn[3];
+  int64_t rbn[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { dn[r] = io.dofs[r0 + r]; rbn[r] = io.rowptr[dn[r]]; }
   double W[21];
   double V[2][6][3];
   if (MODE == 1) {
@@ -741,67 +747,80 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
   const double sc = (MODE == 2 ? M.ext_j_coef : 1.0) * g.iad;
   const double divsign = (MODE == 0) ? -g.sdet : g.sdet;
 #pragma unroll 1
-  for (int i = 0; i < 12; ++i) {
-    double Ci[2][6];
+  for (int grp = 0; grp < 4; ++grp) {          /* facet 0, 1, 2, interior */
+    int32_t dcur[3];
+    int64_t rb[3];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int r = 0; r < 3; ++r) { dcur[r] = dn[r]; rb[r] = rbn[r]; }
+    if (grp < 3) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) Ci[a][r] = T.bdmC[i][a][r];
-    double GY[2][6];
-#pragma unroll
-    for (int s2 = 0; s2 < 6; ++s2) {
-      double y0, y1;
-      if (MODE == 1) {
-        y0 = 0.0; y1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          y0 += Ci[0][r] * W[sb_sym21(r, s2)];
-          y1 += Ci[1][r] * W[sb_sym21(r, s2)];
-        }
-      } else {                       /* W = identity: plain BDM mass matrix */
-        y0 = Ci[0][s2]; y1 = Ci[1][s2];
+      for (int r = 0; r < 3; ++r) {
+        dn[r] = io.dofs[r0 + 3 * (grp + 1) + r];
+        rbn[r] = io.rowptr[dn[r]];
       }
-      GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
-      GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
     }
-    const int li = r0 + i;
-    const int fi = (i < 9) ? i / 3 : -1;
-    const int64_t rowbase = io.rowptr[io.dofs[li]];
-    const SbRanks rk = sb_load_ranks(io.patk, li);
-    double Fi = 0.0;
+    const int fi = (grp < 3) ? grp : -1;
+    const double jf = (grp == 0) ? jump0 : (grp == 1 ? jump1 : jump2);
 #pragma unroll
-    for (int m = 0; m < 12; ++m) {
-      double v = 0.0;
+    for (int r3 = 0; r3 < 3; ++r3) {
+      const int i = 3 * grp + r3;
+      double Ci[2][6];
 #pragma unroll
-      for (int s2 = 0; s2 < 6; ++s2)
-        v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
-      Fi += v * fl[m];
-      sb_store(io.vals, rowbase, sb_rank(rk, m), v, (m < 9) && (m / 3 == fi));
-    }
-    if (MODE != 2) {
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int l = 0; l < 3; ++l) {
-        const double dv = divsign * T.Dhat[i][l];
-        Fi += dv * sl[l];
+        for (int r = 0; r < 6; ++r) Ci[a][r] = T.bdmC[i][a][r];
+      double GY[2][6];
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2) {
+        double y0, y1;
         if (MODE == 1) {
-          double d = 0.0;
+          y0 = 0.0; y1 = 0.0;
 #pragma unroll
-          for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
-          d *= g.iad;
-          sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv + d, false);
-          sb_store(io.vals, rowbase, sb_rank(rk, 15 + l), d, false);
-        } else {
-          sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv, false);
+          for (int r = 0; r < 6; ++r) {
+            y0 += Ci[0][r] * W[sb_sym21(r, s2)];
+            y1 += Ci[1][r] * W[sb_sym21(r, s2)];
+          }
+        } else {                       /* W = identity: plain BDM mass matrix */
+          y0 = Ci[0][s2]; y1 = Ci[1][s2];
+        }
+        GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
+        GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
+      }
+      const int li = r0 + i;
+      const int64_t rowbase = rb[r3];
+      const SbRanks rk = sb_load_ranks(io.patk, li);
+      double Fi = 0.0;
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        double v = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < 6; ++s2)
+          v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
+        Fi += v * fl[m];
+        sb_store(io.vals, rowbase, sb_rank(rk, m), v, (m < 9) && (m / 3 == fi));
+      }
+      if (MODE != 2) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const double dv = divsign * T.Dhat[i][l];
+          Fi += dv * sl[l];
+          if (MODE == 1) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
+            d *= g.iad;
+            sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv + d, false);
+            sb_store(io.vals, rowbase, sb_rank(rk, 15 + l), d, false);
+          } else {
+            sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv, false);
+          }
         }
       }
-    }
-    if (MODE == 1 && i < 9) {
-      const double jf = (i < 3) ? jump0 : (i < 6 ? jump1 : jump2);
-      Fi -= jf * T.trI[i % 3];
-    }
-    if (io.b) {
-      double* dst = io.b + io.dofs[li];
-      if (fi >= 0) SB_ATOMIC_ADD(dst, Fi); else *dst = Fi;
+      if (MODE == 1 && grp < 3) Fi -= jf * T.trI[r3];     /* base_w jump: facet dofs */
+      if (io.b) {
+        double* dst = io.b + dcur[r3];
+        if (fi >= 0) SB_ATOMIC_ADD(dst, Fi); else *dst = Fi;
+      }
     }
   }
 }
@@ -813,10 +832,14 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
                                const double* sl, double coef, const double* mom1,
                                const double* momJ) {
   constexpr int r0 = 15 * PS;
-#pragma unroll 1
+  int32_t dd[3];
+  int64_t rbs[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { dd[r] = io.dofs[r0 + r]; rbs[r] = io.rowptr[dd[r]]; }
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int li = r0 + i;
-    const int64_t rowbase = io.rowptr[io.dofs[li]];
+    const int64_t rowbase = rbs[i];
     const SbRanks rk = sb_load_ranks(io.patk, li);
     double Fi = 0.0;
     if (inside) {
@@ -846,7 +869,7 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
         sb_store(io.vals, rowbase, sb_rank(rk, 12 + 3 * PS + l), v, false);
       }
     }
-    if (io.b) io.b[io.dofs[li]] = Fi;
+    if (io.b) io.b[dd[i]] = Fi;
   }
 }
 

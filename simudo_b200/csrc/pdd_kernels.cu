@@ -134,12 +134,49 @@ __device__ __forceinline__ double* momG_ptr(const PlanDev& pl, int k, int64_t c)
   return pl.scratch + ((int64_t)pl.nb * SB_NMOMA + (int64_t)k * SB_NG) * pl.n_cells + c;
 }
 
-__global__ void __launch_bounds__(SB_TILE)
-k_moments(PlanDev pl, StateDev st, int nblk) {
+#ifndef SB_MB_MOM
+#define SB_MB_MOM 2
+#endif
+#ifndef SB_MB_GEN
+#define SB_MB_GEN 2
+#endif
+#ifndef SB_MB_ROWS
+#define SB_MB_ROWS 2
+#endif
+/* zero the (facet dof, facet dof) Jacobian slots of sub-problem p on the facets this
+ * cell owns (boundary facet, or lower cell index of the pair): both cells of a facet
+ * atomically add into them later in the stream */
+__device__ __forceinline__ void zero_shared_slots(const PlanDev& pl, int64_t c, int p, double* vals) {
+  const int L = pl.L;
+  const int32_t* dofs = pl.cell_dofs + c * L;
+  const uint8_t* patk = pl.patk + (int64_t)pl.cell_pattern[c] * L * 32;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    const int64_t cn = pl.cell_neighbors[c * 3 + f];
+    if (cn >= 0 && cn < c) continue;
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const int li = sb_lbdm(p, 3 * f + kk);
+      const int64_t r0 = pl.rowptr[dofs[li]];
+#pragma unroll
+      for (int k2 = 0; k2 < 3; ++k2) {
+        const uint8_t rk = patk[li * 32 + 3 * f + k2];
+        if (rk != 0xFF) vals[r0 + rk] = 0.0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SB_TILE, SB_MB_MOM)
+k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   const int k = blockIdx.x / nblk;
   const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
   const int L = pl.L;
+  if (vals) {
+    if (k < pl.nb_dof) zero_shared_slots(pl, c, 1 + k, vals);
+    if (k == 0) zero_shared_slots(pl, c, 0, vals);
+  }
   const bool has_dofs = k < pl.nb_dof;
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
@@ -211,7 +248,7 @@ k_moments(PlanDev pl, StateDev st, int nblk) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(SB_TILE)
+__global__ void __launch_bounds__(SB_TILE, SB_MB_GEN)
 k_generation(PlanDev pl, StateDev st) {
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
@@ -368,7 +405,7 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
 /* interior cells (no Dirichlet dofs, no natural-BC rows): compile-time
  * sub-problem, packed ranks, no boundary logic */
 template <int NB, int PS>
-__global__ void __launch_bounds__(SB_TILE)
+__global__ void __launch_bounds__(SB_TILE, SB_MB_ROWS)
 k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
@@ -814,14 +851,17 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
   StateDev sd{st->d_u, st->d_base_w, st->d_thmeq_phi, st->d_phi_opt, st->d_bc_values,
               st->d_natbc_values};
   const int64_t nc = pl->d.n_cells;
-  SB_LAUNCH(k_zero_shared, (unsigned)((nc + 255) / 256), 256, 0, s, pl->d, d_vals, d_b);
+  /* residual: facet rows receive two atomic adds -> start from zero (one memset) */
+  if (d_b) CUDA_TRY(cudaMemsetAsync(d_b, 0, (size_t)pl->d.N * sizeof(double), s));
+  if (pl->d.nb == 0)     /* no band => no k_moments launch to carry the slot zeroing */
+    SB_LAUNCH(k_zero_shared, (unsigned)((nc + 255) / 256), 256, 0, s, pl->d, d_vals, (double*)nullptr);
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
 #endif
   const unsigned nblk = (unsigned)((nc + SB_TILE - 1) / SB_TILE);
-  int nl = 2;
+  int nl = 1;
   if (pl->d.nb > 0) {
-    SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk);
+    SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk, d_vals);
     ++nl;
   }
   switch (pl->d.nb_dof) {
