@@ -685,9 +685,12 @@ SB_HD void sb_rows_scalar(const SbTables& T, const sb_model& M, const SbIO& io,
 struct SbFastIO {
   const int32_t* dofs;
   const uint8_t* patk;       /* [L][32] packed ranks of this cell's pattern */
-  const int64_t* rowptr;
   double* vals;
   double* b;
+  /* per (entity) group of this sub-problem: 0 DG rows, 1..3 facets, 4 interior */
+  int64_t rb[5];             /* vals offset of the group's first row            */
+  int32_t rl[5];             /* row length (the 3 rows of a group are adjacent) */
+  int32_t d0[5];             /* global dof of the group's first row             */
 };
 
 struct SbRanks { uint32_t w[8]; };
@@ -716,12 +719,6 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
                              const double* fl, const double* sl,
                              double jump0, double jump1, double jump2) {
   constexpr int r0 = 15 * PS + 3;
-  /* row bases are two dependent global loads (dof index, row pointer): fetch the
-     first group now and the next group one group ahead of its use */
-  int32_t dn[3];
-  int64_t rbn[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) { dn[r] = io.dofs[r0 + r]; rbn[r] = io.rowptr[dn[r]]; }
   double W[21];
   double V[2][6][3];
   if (MODE == 1) {
@@ -747,23 +744,14 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
   const double sc = (MODE == 2 ? M.ext_j_coef : 1.0) * g.iad;
   const double divsign = (MODE == 0) ? -g.sdet : g.sdet;
 #pragma unroll 1
-  for (int grp = 0; grp < 4; ++grp) {          /* facet 0, 1, 2, interior */
-    int32_t dcur[3];
-    int64_t rb[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) { dcur[r] = dn[r]; rb[r] = rbn[r]; }
-    if (grp < 3) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        dn[r] = io.dofs[r0 + 3 * (grp + 1) + r];
-        rbn[r] = io.rowptr[dn[r]];
-      }
-    }
+  for (int i = 0; i < 12; ++i) {
+    const int grp = i / 3, r3 = i - 3 * grp;   /* facet 0, 1, 2, interior */
+    const int64_t gbase = grp == 0 ? io.rb[1] : (grp == 1 ? io.rb[2] : (grp == 2 ? io.rb[3] : io.rb[4]));
+    const int32_t glen = grp == 0 ? io.rl[1] : (grp == 1 ? io.rl[2] : (grp == 2 ? io.rl[3] : io.rl[4]));
+    const int32_t gdof = grp == 0 ? io.d0[1] : (grp == 1 ? io.d0[2] : (grp == 2 ? io.d0[3] : io.d0[4]));
     const int fi = (grp < 3) ? grp : -1;
     const double jf = (grp == 0) ? jump0 : (grp == 1 ? jump1 : jump2);
-#pragma unroll
-    for (int r3 = 0; r3 < 3; ++r3) {
-      const int i = 3 * grp + r3;
+    {
       double Ci[2][6];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -787,7 +775,7 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
         GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
       }
       const int li = r0 + i;
-      const int64_t rowbase = rb[r3];
+      const int64_t rowbase = gbase + (int64_t)r3 * glen;
       const SbRanks rk = sb_load_ranks(io.patk, li);
       double Fi = 0.0;
 #pragma unroll
@@ -818,7 +806,7 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
       }
       if (MODE == 1 && grp < 3) Fi -= jf * T.trI[r3];     /* base_w jump: facet dofs */
       if (io.b) {
-        double* dst = io.b + dcur[r3];
+        double* dst = io.b + (gdof + r3);
         if (fi >= 0) SB_ATOMIC_ADD(dst, Fi); else *dst = Fi;
       }
     }
@@ -832,14 +820,10 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
                                const double* sl, double coef, const double* mom1,
                                const double* momJ) {
   constexpr int r0 = 15 * PS;
-  int32_t dd[3];
-  int64_t rbs[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) { dd[r] = io.dofs[r0 + r]; rbs[r] = io.rowptr[dd[r]]; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int li = r0 + i;
-    const int64_t rowbase = rbs[i];
+    const int64_t rowbase = io.rb[0] + (int64_t)i * io.rl[0];
     const SbRanks rk = sb_load_ranks(io.patk, li);
     double Fi = 0.0;
     if (inside) {
@@ -869,7 +853,7 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
         sb_store(io.vals, rowbase, sb_rank(rk, 12 + 3 * PS + l), v, false);
       }
     }
-    if (io.b) io.b[dd[i]] = Fi;
+    if (io.b) io.b[io.d0[0] + i] = Fi;
   }
 }
 

@@ -57,6 +57,9 @@ struct PlanDev {
   const int32_t* cell_pattern;   /* [n_cells]                                */
   const uint8_t* patk;           /* [n_patterns][L][32] packed emission-order ranks */
   const int32_t* sp_cells;       /* [n_special] cells with Dirichlet / natural-BC rows */
+  const int64_t* rowbase;        /* [5P][n_cells] vals offset of the first row of each
+                                    (sub-problem, entity) group: DG, facet 0..2, interior */
+  const uint16_t* rowlen;        /* [5P][n_cells] length of the rows of that group     */
   int64_t n_special;
   const double* tag_params;
   const int32_t* cell_special;   /* [n_cells] -1 or special index            */
@@ -415,8 +418,13 @@ k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
   SbFastIO io;
   io.dofs = pl.cell_dofs + c * L;
   io.patk = pl.patk + (int64_t)pl.cell_pattern[c] * L * 32;
-  io.rowptr = pl.rowptr;
   io.vals = vals; io.b = b;
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    io.rb[e] = pl.rowbase[(int64_t)(5 * PS + e) * nc + c];
+    io.rl[e] = pl.rowlen[(int64_t)(5 * PS + e) * nc + c];
+    io.d0[e] = io.dofs[15 * PS + (e == 0 ? 0 : 3 * e)];
+  }
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
   const int32_t* dofs = io.dofs;
@@ -794,6 +802,34 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
         }
       }
     UP(patk, patk.data(), patk.size());
+    /* coalesced row bases: the 3 dofs of one (sub-problem, entity) are consecutive in
+       both supported numberings, so one offset + one length serve 3 rows */
+    {
+      const int ng = 5 * Pn;
+      std::vector<int64_t> rbase((size_t)ng * nc);
+      std::vector<uint16_t> rlen((size_t)ng * nc);
+      bool ok = true;
+      for (int64_t c = 0; c < nc && ok; ++c)
+        for (int gq = 0; gq < ng; ++gq) {
+          const int p = gq / 5, e = gq % 5;
+          const int li0 = 15 * p + (e == 0 ? 0 : 3 * e);
+          const int32_t* dd = pr->h_cell_dofs + c * L + li0;
+          const int64_t r0 = pr->h_rowptr[dd[0]];
+          const int64_t len = pr->h_rowptr[dd[0] + 1] - r0;
+          if (dd[1] != dd[0] + 1 || dd[2] != dd[0] + 2 || len > 65535 ||
+              pr->h_rowptr[dd[0] + 2] - pr->h_rowptr[dd[0] + 1] != len ||
+              pr->h_rowptr[dd[0] + 3] - pr->h_rowptr[dd[0] + 2] != len) { ok = false; break; }
+          rbase[(size_t)gq * nc + c] = r0;
+          rlen[(size_t)gq * nc + c] = (uint16_t)len;
+        }
+      if (!ok) {
+        snprintf(g_err, sizeof g_err, "dof numbering must keep the three dofs of each mesh entity "
+                 "consecutive (the 'ufc' and 'b200' numberings do)");
+        sb_plan_destroy(pl); return SB_ERR_UNSUPPORTED;
+      }
+      UP(rowbase, rbase.data(), rbase.size());
+      UP(rowlen, rlen.data(), rlen.size());
+    }
     std::vector<int32_t> spc;
     for (int64_t c = 0; c < nc; ++c) if (special[c] >= 0) spc.push_back((int32_t)c);
     UP(sp_cells, spc.data(), spc.size());
