@@ -25,6 +25,7 @@
 #include "pdd_device.cuh"
 
 #define SB_TILE 128                /* threads (= cells) per CTA */
+#define SB_MAX_SMEM_PATTERNS 16
 
 __constant__ SbTables c_T;
 __constant__ sb_model c_M;
@@ -55,6 +56,7 @@ struct PlanDev {
   const int64_t* rowptr;
   const uint8_t* patterns;       /* [n_patterns][L][L]                       */
   const int32_t* cell_pattern;   /* [n_cells]                                */
+  int64_t n_patterns;
   const uint8_t* patk;           /* [n_patterns][L][32] packed emission-order ranks */
   const int32_t* sp_cells;       /* [n_special] cells with Dirichlet / natural-BC rows */
   const int64_t* rowbase;        /* [5P][n_cells] vals offset of the first row of each
@@ -410,14 +412,29 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
 template <int NB, int PS>
 __global__ void __launch_bounds__(SB_TILE, SB_MB_ROWS)
 k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
+  /* packed ranks of this sub-problem's 15 rows for every pattern, staged in shared
+     memory (a product mesh has 8 patterns -> 3.8 KB) */
+  __align__(16) __shared__ uint8_t s_patk[SB_MAX_SMEM_PATTERNS][15][32];
+  const int L = pl.L;
+  const bool stage = pl.n_patterns <= SB_MAX_SMEM_PATTERNS;
+  if (stage) {
+    const int nw = (int)pl.n_patterns * 15 * 8;            /* 32-bit words */
+    for (int w = threadIdx.x; w < nw; w += SB_TILE) {
+      const int q = w / 120, rem = w % 120, r = rem / 8, e = rem % 8;
+      reinterpret_cast<uint32_t*>(&s_patk[q][r][0])[e] =
+          reinterpret_cast<const uint32_t*>(pl.patk + ((int64_t)q * L + 15 * PS + r) * 32)[e];
+    }
+  }
+  __syncthreads();
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
   if (pl.cell_special[c] >= 0) return;           /* handled by k_rows_special */
-  const int L = pl.L;
   const int64_t nc = pl.n_cells;
   SbFastIO io;
   io.dofs = pl.cell_dofs + c * L;
-  io.patk = pl.patk + (int64_t)pl.cell_pattern[c] * L * 32;
+  /* io.patk is indexed with the cell-local row li = 15 PS + r */
+  io.patk = stage ? (&s_patk[pl.cell_pattern[c]][0][0] - 15 * PS * 32)
+                  : (pl.patk + (int64_t)pl.cell_pattern[c] * L * 32);
   io.vals = vals; io.b = b;
 #pragma unroll
   for (int e = 0; e < 5; ++e) {
@@ -786,6 +803,7 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   {
     /* packed emission-order ranks for the fast row kernels */
     const int64_t np = pr->n_patterns;
+    d.n_patterns = np;
     const int Pn = pr->P;
     std::vector<uint8_t> patk((size_t)np * L * 32, 0xFF);
     for (int64_t q = 0; q < np; ++q)
