@@ -32,9 +32,10 @@ sys.path.insert(0, ROOT)
 METRIC = 'jacobian_residual_assembly_dof_per_s'
 UNIT = 'DOF/s'
 BYTES_PER_CELL = {'ib': 10396, 'pn': 7424}
-# dram__bytes_read.sum + dram__bytes_write.sum of k_assemble per cell from the committed
-# `ncu --set full` capture (profiles/r1_v6_k_assemble_summary.csv, 80 396 IB cells)
-NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): (611141888 + 1022995000) / 80396.0}
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one assembly pass,
+# per cell, from the committed `ncu --set full` capture (profiles/r1_split_kernels_summary.csv,
+# 320 396 IB cells)
+NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): 7.148e9 / 320396.0}
 
 
 def parse_args():
@@ -315,7 +316,9 @@ def run_b200(args):
                           frac=achieved / peak,
                           traffic=(NCU_DRAM_BYTES_PER_CELL[(args.kind, args.pattern)] * pa.n_cells
                                    if (args.kind, args.pattern) in NCU_DRAM_BYTES_PER_CELL else None),
-                          kernel='k_assemble', kernel_ms=k_ms,
+                          kernel='assembly pass = k_moments + k_generation + k_rows_fast x P + '
+                                 'k_rows_special (CUDA events around the pass inside sb_assemble)',
+                          kernel_ms=k_ms,
                           algorithmic_bytes=alg_bytes, peak_source=peak_kind),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),
