@@ -62,3 +62,48 @@ def test_strip_halo_exchange_and_sharding_world2():
     assert np.all(r0['ghost_below'] == 0.0)   # rank 0 has nobody below
     assert r0['shard'] == [0, 2, 4, 6] and r1['shard'] == [1, 3, 5]
     assert r0['tmax'] == r1['tmax'] == 4.0
+
+
+def _ensemble_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from functools import partial
+    from oracle_backend import OracleBackend
+    from simudo_b200.example import sweep_ensemble as se
+    from simudo_b200.sweep import run_ensemble
+    mem = se.members(3)
+    run = partial(se.run_member, backend_factory=OracleBackend, voltages=[0.0, 0.3, 0.6])
+    res, times = run_ensemble(mem, run, dist)
+    q.put(dict(rank=rank, res=res, n_times=len(times)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sweep_ensemble_sharded_equals_serial_world2():
+    """config 5 host logic: members dealt to 2 ranks, gathered tables identical
+    to a serial run; no data-path collective involved."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ensemble_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=600) for _ in procs], key=lambda d: d['rank'])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0]['res'] == out[1]['res'] and out[0]['n_times'] == 2
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from functools import partial
+    from oracle_backend import OracleBackend
+    from simudo_b200.example import sweep_ensemble as se
+    from simudo_b200.sweep import run_ensemble
+    serial, _ = run_ensemble(se.members(3), partial(se.run_member, backend_factory=OracleBackend,
+                                                    voltages=[0.0, 0.3, 0.6]))
+    assert serial == out[0]['res']
+    # heavier doping -> larger built-in potential -> smaller forward current at 0.6 V
+    j06 = [dict((round(v, 2), j) for v, j in r)[0.6] for r in serial]
+    assert j06[0] > j06[2] > 0
