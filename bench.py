@@ -275,6 +275,7 @@ def run_b200(args):
     for _ in range(min(args.steps, 5)):
         step_device()
         kernel_ms.append(plan.last_kernel_ms())
+    stage_ms = plan.last_stage_ms()
     k_ms = float(np.mean(kernel_ms))
     # end-to-end through the public API with host buffers
     for _ in range(2):
@@ -318,7 +319,7 @@ def run_b200(args):
                                    if (args.kind, args.pattern) in NCU_DRAM_BYTES_PER_CELL else None),
                           kernel='assembly pass = k_moments + k_generation + k_rows_fast x P + '
                                  'k_rows_special (CUDA events around the pass inside sb_assemble)',
-                          kernel_ms=k_ms,
+                          kernel_ms=k_ms, stage_ms=stage_ms,
                           algorithmic_bytes=alg_bytes, peak_source=peak_kind),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / args.steps),

@@ -230,6 +230,9 @@ int  sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_
  * sb_assemble call; sb_plan_last_kernel_ms synchronises on that event.            */
 int sb_plan_set_profiling(sb_plan* plan, int on);
 int sb_plan_last_kernel_ms(sb_plan* plan, double* ms);
+/* the same pass split by stage: ms4 = {k_moments, k_generation, k_rows_fast x P,
+ * k_rows_special}                                                                  */
+int sb_plan_last_stage_ms(sb_plan* plan, double* ms4);
 
 /* layout of the packed reference tables expected in sb_problem.h_tables */
 int64_t sb_tables_size(void);

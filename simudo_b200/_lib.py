@@ -21,7 +21,7 @@ EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
             'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
-            'sb_plan_last_kernel_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
+            'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
             'sb_band_solve', 'sb_band_set_refinement']
 
 
@@ -74,6 +74,8 @@ def _declare(lib):
     lib.sb_plan_set_profiling.restype = C.c_int
     lib.sb_plan_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.sb_plan_last_kernel_ms.restype = C.c_int
+    lib.sb_plan_last_stage_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.sb_plan_last_stage_ms.restype = C.c_int
     lib.sb_band_create.argtypes = [i64, vp, vp, vp, i32, i64, C.POINTER(vp)]
     lib.sb_band_create.restype = C.c_int
     lib.sb_band_destroy.argtypes = [vp]

@@ -28,6 +28,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/simudo_b200.h"
 #include "pdd_tables.h"
 
@@ -112,15 +113,60 @@ SB_HD SbBandK sb_band_consts(const sb_model& M, const double* tp, int k) {
 /* IB with filling-dependent mobility mu = mu0 [(1-f) - 1/2 f^0.33 (1-f)^1.33]
  * (poisson_drift_diffusion1.py1:228-231); out of line: pow() is bulky and this
  * is the rarely used model (use_constant_mobility = False)                  */
-SB_NOINLINE void sb_ib_fill_mobility(double mob, double N, double dd_scale, double sbeta,
-                                     double f, double omf, double* c, double* dc) {
+struct SbCdc { double c, dc; };     /* by value: out-pointers would force a stack round trip */
+SB_NOINLINE SbCdc sb_ib_fill_mobility(double mob, double N, double dd_scale, double sbeta,
+                                      double f, double omf) {
   const double df = -sbeta * f * omf;       /* df/dchi */
   const double fa = pow(f, 0.33), ob = pow(omf, 1.33);
   const double mu = mob * (omf - 0.5 * fa * ob);
   const double dmu = mob * (-df - 0.5 * (0.33 * fa / f * df * ob
                                           + fa * 1.33 * ob / omf * (-df)));
-  *c = dd_scale / (mu * N * f);
-  *dc = -(*c) * (dmu / mu + df / f);
+  SbCdc r;
+  r.c = dd_scale / (mu * N * f);
+  r.dc = -r.c * (dmu / mu + df / f);
+  return r;
+}
+
+/* exp(x) and exp(-x) from one range reduction: x = k ln2 + r, |r| <= ln2/2,
+ * exp(+-r) = E(r^2) +- r O(r^2) (Taylor to degree 13, truncation 4e-18 relative;
+ * the even and odd chains are independent, half the dependency depth of a
+ * Horner exp), scaled by 2^(+-k) built from the exponent bits.  x is clamped to
+ * +-700 (no inf / denormal paths).  Replaces exp() + a division per point.  */
+SB_HD double sb_pow2i(int k) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double((1023 + k) << 20, 0);
+#else
+  const uint64_t u = (uint64_t)(1023 + k) << 52;
+  double d;
+  memcpy(&d, &u, sizeof d);
+  return d;
+#endif
+}
+SB_HD void sb_exp_pair(double x, double& ep, double& em) {
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double magic = 6755399441055744.0;            /* 1.5 * 2^52 */
+  const double t = fma(x, 1.4426950408889634074, magic);
+#ifdef __CUDA_ARCH__
+  const int k = __double2loint(t);
+#else
+  uint64_t tb;
+  memcpy(&tb, &t, sizeof tb);
+  const int k = (int)(uint32_t)(tb & 0xFFFFFFFFu);
+#endif
+  const double kf = t - magic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double z = r * r;
+  double E = 1.0 / 479001600.0, O = 1.0 / 6227020800.0;
+  E = fma(E, z, 1.0 / 3628800.0);  O = fma(O, z, 1.0 / 39916800.0);
+  E = fma(E, z, 1.0 / 40320.0);    O = fma(O, z, 1.0 / 362880.0);
+  E = fma(E, z, 1.0 / 720.0);      O = fma(O, z, 1.0 / 5040.0);
+  E = fma(E, z, 1.0 / 24.0);       O = fma(O, z, 1.0 / 120.0);
+  E = fma(E, z, 0.5);              O = fma(O, z, 1.0 / 6.0);
+  E = fma(E, z, 1.0);              O = fma(O, z, 1.0);
+  const double ro = r * O;
+  ep = (E + ro) * sb_pow2i(k);
+  em = (E - ro) * sb_pow2i(-k);
 }
 
 /* Pointwise band quantities at chi = e phi + w (band statistics
@@ -128,9 +174,10 @@ SB_NOINLINE void sb_ib_fill_mobility(double mob, double N, double dd_scale, doub
  *   su = s u / eps, dsu = d(su)/dchi, c = dd_scale / (mu u), dc = dc/dchi   */
 SB_HD void sb_band_point(const SbBandK& K, double chi,
                          double& su, double& dsu, double& c, double& dc) {
-  const double e = exp(K.sbeta * (chi - K.E));
+  double e, einv;
+  sb_exp_pair(K.sbeta * (chi - K.E), e, einv);
   if (K.kind == SB_BAND_NONDEGENERATE) {
-    const double ue = K.N_eps / e;            /* u / eps */
+    const double ue = K.N_eps * einv;         /* u / eps */
     su = K.s * ue;
     dsu = -K.beta * ue;
     c = K.cinv * e;
@@ -144,7 +191,8 @@ SB_HD void sb_band_point(const SbBandK& K, double chi,
       c = K.cinv * (1.0 + e);
       dc = K.cinv * K.sbeta * e;
     } else {
-      sb_ib_fill_mobility(K.mob, K.N, K.dd_scale, K.sbeta, f, omf, &c, &dc);
+      const SbCdc r = sb_ib_fill_mobility(K.mob, K.N, K.dd_scale, K.sbeta, f, omf);
+      c = r.c; dc = r.dc;
     }
   }
 }
@@ -783,7 +831,7 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
         double v = 0.0;
 #pragma unroll
         for (int s2 = 0; s2 < 6; ++s2)
-          v += GY[0][s2] * T.bdmC[m][0][s2] + GY[1][s2] * T.bdmC[m][1][s2];
+          v = fma(GY[1][s2], T.bdmC[m][1][s2], fma(GY[0][s2], T.bdmC[m][0][s2], v));
         Fi += v * fl[m];
         sb_store(io.vals, rowbase, sb_rank(rk, m), v, (m < 9) && (m / 3 == fi));
       }
@@ -795,7 +843,7 @@ SB_HD void sb_rows_flux_fast(const SbTables& T, const sb_model& M, const SbFastI
           if (MODE == 1) {
             double d = 0.0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
+            for (int r = 0; r < 6; ++r) d = fma(Ci[1][r], V[1][r][l], fma(Ci[0][r], V[0][r][l], d));
             d *= g.iad;
             sb_store(io.vals, rowbase, sb_rank(rk, 12 + l), dv + d, false);
             sb_store(io.vals, rowbase, sb_rank(rk, 15 + l), d, false);

@@ -22,9 +22,9 @@
 #include <algorithm>
 #include <atomic>
 
+#define SB_TILE 128                /* threads (= cells) per CTA */
 #include "pdd_device.cuh"
 
-#define SB_TILE 128                /* threads (= cells) per CTA */
 #define SB_MAX_SMEM_PATTERNS 16
 
 __constant__ SbTables c_T;
@@ -57,6 +57,7 @@ struct PlanDev {
   const uint8_t* patterns;       /* [n_patterns][L][L]                       */
   const int32_t* cell_pattern;   /* [n_cells]                                */
   int64_t n_patterns;
+  int stage_patk;                /* rank tables fit the shared-memory staging area */
   const uint8_t* patk;           /* [n_patterns][L][32] packed emission-order ranks */
   const int32_t* sp_cells;       /* [n_special] cells with Dirichlet / natural-BC rows */
   const int64_t* rowbase;        /* [5P][n_cells] vals offset of the first row of each
@@ -82,7 +83,8 @@ struct sb_plan {
   int64_t n_bc, n_natbc, n_special;
   double* tmp_cells;             /* [n_cells] scratch for rebase             */
 #ifndef SB_EMUL_BUILD
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   /* around k_assemble when profiling */
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   /* around the assembly pass when profiling */
+  cudaEvent_t evs[3] = {nullptr, nullptr, nullptr};  /* after moments, generation, fast rows */
 #endif
   int profiling = 0;
 };
@@ -140,7 +142,7 @@ __device__ __forceinline__ double* momG_ptr(const PlanDev& pl, int k, int64_t c)
 }
 
 #ifndef SB_MB_MOM
-#define SB_MB_MOM 2
+#define SB_MB_MOM 3
 #endif
 #ifndef SB_MB_GEN
 #define SB_MB_GEN 2
@@ -153,20 +155,24 @@ __device__ __forceinline__ double* momG_ptr(const PlanDev& pl, int k, int64_t c)
  * atomically add into them later in the stream */
 __device__ __forceinline__ void zero_shared_slots(const PlanDev& pl, int64_t c, int p, double* vals) {
   const int L = pl.L;
-  const int32_t* dofs = pl.cell_dofs + c * L;
+  const int64_t nc = pl.n_cells;
   const uint8_t* patk = pl.patk + (int64_t)pl.cell_pattern[c] * L * 32;
 #pragma unroll
   for (int f = 0; f < 3; ++f) {
     const int64_t cn = pl.cell_neighbors[c * 3 + f];
     if (cn >= 0 && cn < c) continue;
+    /* the three rows of a facet are adjacent: base + kk * length (coalesced tables) */
+    const int64_t rb = pl.rowbase[(int64_t)(5 * p + 1 + f) * nc + c];
+    const int64_t rl = pl.rowlen[(int64_t)(5 * p + 1 + f) * nc + c];
 #pragma unroll
     for (int kk = 0; kk < 3; ++kk) {
       const int li = sb_lbdm(p, 3 * f + kk);
-      const int64_t r0 = pl.rowptr[dofs[li]];
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(patk + li * 32);
 #pragma unroll
       for (int k2 = 0; k2 < 3; ++k2) {
-        const uint8_t rk = patk[li * 32 + 3 * f + k2];
-        if (rk != 0xFF) vals[r0 + rk] = 0.0;
+        const int e = 3 * f + k2;
+        const uint32_t rk = (q[e >> 2] >> (8 * (e & 3))) & 0xFFu;
+        if (rk != 0xFFu) vals[rb + kk * rl + rk] = 0.0;
       }
     }
   }
@@ -178,10 +184,6 @@ k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
   if (c >= pl.n_cells) return;
   const int L = pl.L;
-  if (vals) {
-    if (k < pl.nb_dof) zero_shared_slots(pl, c, 1 + k, vals);
-    if (k == 0) zero_shared_slots(pl, c, 0, vals);
-  }
   const bool has_dofs = k < pl.nb_dof;
   const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
@@ -250,6 +252,11 @@ k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   for (int t = 0; t < SB_NRX; ++t) o[(int64_t)(SB_NMC + SB_NQ + t) * nc] = mRx[t];
 #pragma unroll
   for (int t = 0; t < SB_NR; ++t) o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc] = mR[t];
+  /* last, so that no load of the moment computation queues behind these stores */
+  if (vals) {
+    if (k < pl.nb_dof) zero_shared_slots(pl, c, 1 + k, vals);
+    if (k == 0) zero_shared_slots(pl, c, 0, vals);
+  }
 }
 
 template <int NB>
@@ -416,7 +423,7 @@ k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
      memory (a product mesh has 8 patterns -> 3.8 KB) */
   __align__(16) __shared__ uint8_t s_patk[SB_MAX_SMEM_PATTERNS][15][32];
   const int L = pl.L;
-  const bool stage = pl.n_patterns <= SB_MAX_SMEM_PATTERNS;
+  const bool stage = pl.stage_patk != 0;
   if (stage) {
     const int nw = (int)pl.n_patterns * 15 * 8;            /* 32-bit words */
     for (int w = threadIdx.x; w < nw; w += SB_TILE) {
@@ -524,8 +531,15 @@ struct RowsLauncher<NB, -1> {
 
 template <int NB>
 static void launch_rows(const PlanDev& d, const StateDev& sd, double* vals, double* b,
-                        unsigned nblk, cudaStream_t s) {
+                        unsigned nblk, cudaStream_t s, cudaEvent_t after_gen,
+                        cudaEvent_t after_fast) {
+#ifndef SB_EMUL_BUILD
+  if (after_gen) cudaEventRecord(after_gen, s);
+#endif
   RowsLauncher<NB, NB>::go(d, sd, vals, b, nblk, s);
+#ifndef SB_EMUL_BUILD
+  if (after_fast) cudaEventRecord(after_fast, s);
+#endif
   if (d.n_special > 0) {
     const unsigned nsb = (unsigned)((d.n_special + SB_TILE - 1) / SB_TILE);
     SB_LAUNCH(k_rows_special<NB>, nsb * (unsigned)d.P, SB_TILE, 0, s, d, sd, vals, b, (int)nsb);
@@ -701,7 +715,10 @@ extern "C" void sb_plan_destroy(sb_plan* pl) {
   if (!pl) return;
   for (void* p : pl->allocs) cudaFree(p);
 #ifndef SB_EMUL_BUILD
-  if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+  if (pl->ev0) {
+    cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(pl->evs[i]);
+  }
 #endif
   if (g_tables_owner == pl) g_tables_owner = nullptr;
   delete pl;
@@ -804,6 +821,8 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
     /* packed emission-order ranks for the fast row kernels */
     const int64_t np = pr->n_patterns;
     d.n_patterns = np;
+    /* SIMUDO_B200_NO_SMEM_PATTERNS: debugging knob, forces the global-memory rank path */
+    d.stage_patk = (np <= SB_MAX_SMEM_PATTERNS) && !getenv("SIMUDO_B200_NO_SMEM_PATTERNS");
     const int Pn = pr->P;
     std::vector<uint8_t> patk((size_t)np * L * 32, 0xFF);
     for (int64_t q = 0; q < np; ++q)
@@ -918,16 +937,20 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
     SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk, d_vals);
     ++nl;
   }
+  cudaEvent_t eg = nullptr, ef = nullptr;
+#ifndef SB_EMUL_BUILD
+  if (pl->profiling) { CUDA_TRY(cudaEventRecord(pl->evs[0], s)); eg = pl->evs[1]; ef = pl->evs[2]; }
+#endif
   switch (pl->d.nb_dof) {
-    case 0: launch_rows<0>(pl->d, sd, d_vals, d_b, nblk, s); break;
+    case 0: launch_rows<0>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); break;
     case 1: SB_LAUNCH(k_generation<1>, nblk, SB_TILE, 0, s, pl->d, sd);
-            launch_rows<1>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
+            launch_rows<1>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
     case 2: SB_LAUNCH(k_generation<2>, nblk, SB_TILE, 0, s, pl->d, sd);
-            launch_rows<2>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
+            launch_rows<2>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
     case 3: SB_LAUNCH(k_generation<3>, nblk, SB_TILE, 0, s, pl->d, sd);
-            launch_rows<3>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
+            launch_rows<3>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
     default: SB_LAUNCH(k_generation<4>, nblk, SB_TILE, 0, s, pl->d, sd);
-             launch_rows<4>(pl->d, sd, d_vals, d_b, nblk, s); ++nl; break;
+             launch_rows<4>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
   }
   nl += pl->d.P + (pl->d.n_special > 0 ? 1 : 0) - 1;
 #ifndef SB_EMUL_BUILD
@@ -946,6 +969,7 @@ extern "C" int sb_plan_set_profiling(sb_plan* pl, int on) {
   if (on && !pl->ev0) {
     CUDA_TRY(cudaEventCreate(&pl->ev0));
     CUDA_TRY(cudaEventCreate(&pl->ev1));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&pl->evs[i]));
   }
 #endif
   pl->profiling = on;
@@ -960,6 +984,22 @@ extern "C" int sb_plan_last_kernel_ms(sb_plan* pl, double* ms) {
   float f = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&f, pl->ev0, pl->ev1));
   *ms = f;
+#endif
+  return SB_OK;
+}
+
+extern "C" int sb_plan_last_stage_ms(sb_plan* pl, double* ms4) {
+  if (!pl || !ms4) return SB_ERR_ARG;
+  for (int i = 0; i < 4; ++i) ms4[i] = 0.0;
+#ifndef SB_EMUL_BUILD
+  if (!pl->profiling || !pl->ev1) { snprintf(g_err, sizeof g_err, "profiling is off"); return SB_ERR_ARG; }
+  CUDA_TRY(cudaEventSynchronize(pl->ev1));
+  cudaEvent_t e[5] = {pl->ev0, pl->evs[0], pl->evs[1], pl->evs[2], pl->ev1};
+  for (int i = 0; i < 4; ++i) {
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, e[i], e[i + 1]));
+    ms4[i] = f;
+  }
 #endif
   return SB_OK;
 }

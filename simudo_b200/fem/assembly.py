@@ -157,5 +157,12 @@ class AssemblyPlan(object):
         _lib.check(self.lib.sb_plan_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def last_stage_ms(self):
+        """{stage: ms} of the last pass: moments, generation, rows_fast, rows_special."""
+        ms = (C.c_double * 4)()
+        _lib.check(self.lib.sb_plan_last_stage_ms(self._h, ms))
+        return dict(zip(('k_moments', 'k_generation', 'k_rows_fast', 'k_rows_special'),
+                        [float(x) for x in ms]))
+
     def launch_count(self):
         return int(self.lib.sb_launch_count())

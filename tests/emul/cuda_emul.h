@@ -36,6 +36,7 @@ static thread_local dim3e threadIdx, blockIdx, blockDim, gridDim;
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };

@@ -221,3 +221,19 @@ def jacobian_consistent_with_residual_large(maker, nx, ny):
     err = (fd - an).abs().max().item() / an.abs().max().item()
     assert err < 1e-6, err
     return pa.n_cells
+
+
+def unstaged_rank_tables_match_staged():
+    """Meshes with more rank patterns than fit in shared memory take the
+    global-memory rank path of k_rows_fast; forced here with the library's
+    debugging knob and compared bit for bit."""
+    import os
+    pa = syn.ib_problem(nx=6, ny=3)
+    st = syn.synthetic_state(pa)
+    v0, b0 = run_plan(AssemblyPlan(pa), st)
+    os.environ['SIMUDO_B200_NO_SMEM_PATTERNS'] = '1'
+    try:
+        v1, b1 = run_plan(AssemblyPlan(pa), st)
+    finally:
+        del os.environ['SIMUDO_B200_NO_SMEM_PATTERNS']
+    assert torch.equal(v0, v1) and torch.equal(b0, b1)

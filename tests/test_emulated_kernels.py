@@ -30,6 +30,10 @@ def test_fill_dependent_ib_mobility_emulated(emulated_lib):
     hc.fill_dependent_ib_mobility()
 
 
+def test_unstaged_rank_tables_emulated(emulated_lib):
+    hc.unstaged_rank_tables_match_staged()
+
+
 def test_non_default_quadrature_emulated(emulated_lib):
     hc.non_default_quadrature_degrees()
 

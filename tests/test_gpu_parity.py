@@ -44,6 +44,10 @@ def test_fill_dependent_ib_mobility():
     hc.fill_dependent_ib_mobility()
 
 
+def test_unstaged_rank_tables():
+    hc.unstaged_rank_tables_match_staged()
+
+
 def test_non_default_quadrature():
     hc.non_default_quadrature_degrees()
 
