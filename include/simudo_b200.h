@@ -225,6 +225,43 @@ int  sb_band_set_refinement(sb_band_solver* s, int32_t steps);
 int  sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_t vstride,
                    const double* d_b, double* d_x, int32_t* h_info, void* stream);
 
+/* ---- a10: optical sub-problems -------------------------
+ * One scalar photon-flux field per (photon energy, direction) on CG2 over the PDD
+ * mesh.  Replaces, per field and per optical update (physics/steppers.py:120-136):
+ *   OpticalField.update_input  (physics/optical.py:260-274; dolfin.project of the
+ *       absorption coefficient onto CG2, fem/assign.py:12-47)   -> sb_optics_alpha_rhs
+ *       + a sb_band_solve with the constant CG2 mass matrix;
+ *   SystemAssembler on OpticalFieldMSORTE.get_weak_form()
+ *       (physics/optical1.py1:27-45, Dirichlet :57-61)          -> sb_optics_assemble
+ *       + a sb_band_solve;
+ *   OpticalField.update_output (physics/optical.py:248-258)     -> sb_optics_to_cells.
+ * CG2 dofs: vertex v -> v, facet f -> n_vertices + f; local order = 3 vertices, then
+ * the midpoint of the edge opposite vertex i (the layout of sb_state.d_phi_opt).    */
+typedef struct sb_optics sb_optics;
+typedef struct sb_optics_problem {
+  int64_t n_cells, n_dofs, nnz;
+  const int32_t* h_cell_dofs;   /* [n_cells][6]                                      */
+  const int32_t* h_pos;         /* [n_cells][36] CSR position of local entry (i, j)  */
+  const int64_t* h_rowptr;      /* [n_dofs + 1]                                      */
+  const int64_t* h_diag_pos;    /* [n_dofs] CSR position of the diagonal             */
+  const void* h_tables;         /* packed SbOpticsTables (simudo_b200/fem/cg2.py)    */
+  int64_t n_tables;             /* its size in bytes, checked                        */
+} sb_optics_problem;
+int  sb_optics_create(sb_plan* plan, const sb_optics_problem* pr, sb_optics** out);
+void sb_optics_destroy(sb_optics* o);   /* device buffers are released with the plan */
+int64_t sb_optics_tables_size(void);
+/* d_rhs[n_dofs] = int alpha_field N_i dx with alpha evaluated from the PDD state
+ * (electro_optical_process.py:415-418, 464-480) at the 12 points of the degree-6 rule */
+int sb_optics_alpha_rhs(sb_optics* o, const sb_state* st, int32_t field, double* d_rhs,
+                        void* stream);
+/* d_vals[nnz], d_rhs[n_dofs]: MSORTE matrix for direction (ox, oy) with CG2 absorption
+ * d_alpha[n_dofs]; rows of d_bc_dofs become Phi = d_bc_vals (inflow Dirichlet)          */
+int sb_optics_assemble(sb_optics* o, const double* d_alpha, double ox, double oy,
+                       int64_t n_bc, const int32_t* d_bc_dofs, const double* d_bc_vals,
+                       double* d_vals, double* d_rhs, void* stream);
+/* d_cells[n_cells][6] = d_nodal[cell_dofs]: one field's slice of sb_state.d_phi_opt    */
+int sb_optics_to_cells(sb_optics* o, const double* d_nodal, double* d_cells, void* stream);
+
 /* ---- measurement ------------------------------------------------------------------
  * CUDA-event timing (on the launching stream) of the dominant kernel of the last
  * sb_assemble call; sb_plan_last_kernel_ms synchronises on that event.            */

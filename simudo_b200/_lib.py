@@ -22,7 +22,9 @@ EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
             'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
-            'sb_band_solve', 'sb_band_set_refinement']
+            'sb_band_solve', 'sb_band_set_refinement', 'sb_optics_create',
+            'sb_optics_destroy', 'sb_optics_tables_size', 'sb_optics_alpha_rhs',
+            'sb_optics_assemble', 'sb_optics_to_cells']
 
 
 class SbProblem(C.Structure):
@@ -38,6 +40,13 @@ class SbProblem(C.Structure):
         ('n_natbc', C.c_int64), ('h_natbc_cell', C.c_void_p),
         ('h_natbc_row', C.c_void_p),
         ('h_tables', C.c_void_p), ('n_tables', C.c_int64)]
+
+
+class SbOpticsProblem(C.Structure):
+    _fields_ = [('n_cells', C.c_int64), ('n_dofs', C.c_int64), ('nnz', C.c_int64),
+                ('h_cell_dofs', C.c_void_p), ('h_pos', C.c_void_p),
+                ('h_rowptr', C.c_void_p), ('h_diag_pos', C.c_void_p),
+                ('h_tables', C.c_void_p), ('n_tables', C.c_int64)]
 
 
 class SbState(C.Structure):
@@ -86,6 +95,17 @@ def _declare(lib):
     lib.sb_band_solve.restype = C.c_int
     lib.sb_band_set_refinement.argtypes = [vp, i32]
     lib.sb_band_set_refinement.restype = C.c_int
+    lib.sb_optics_create.argtypes = [vp, C.POINTER(SbOpticsProblem), C.POINTER(vp)]
+    lib.sb_optics_create.restype = C.c_int
+    lib.sb_optics_destroy.argtypes = [vp]
+    lib.sb_optics_destroy.restype = None
+    lib.sb_optics_tables_size.restype = i64
+    lib.sb_optics_alpha_rhs.argtypes = [vp, C.POINTER(SbState), i32, vp, vp]
+    lib.sb_optics_alpha_rhs.restype = C.c_int
+    lib.sb_optics_assemble.argtypes = [vp, vp, dbl, dbl, i64, vp, vp, vp, vp, vp]
+    lib.sb_optics_assemble.restype = C.c_int
+    lib.sb_optics_to_cells.argtypes = [vp, vp, vp, vp]
+    lib.sb_optics_to_cells.restype = C.c_int
     return lib
 
 

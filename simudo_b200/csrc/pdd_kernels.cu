@@ -1059,3 +1059,5 @@ extern "C" int sb_surface_flux(sb_plan* pl, const double* d_u, int32_t p, int64_
   CUDA_TRY(cudaGetLastError());
   return SB_OK;
 }
+
+#include "optics.inl"

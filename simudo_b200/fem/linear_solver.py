@@ -40,18 +40,24 @@ def x_major_permutation(pa):
 class BandSolver(object):
     """Banded LU with partial pivoting + equilibration, one CTA per system."""
 
-    def __init__(self, pa, device, batch=1, max_band_bytes=8 << 30):
+    def __init__(self, pa, device, batch=1, max_band_bytes=8 << 30, csr=None):
+        """``pa``: ProblemArrays of the PDD system, or ``None`` with
+        ``csr=(n, rowptr, colidx, perm)`` for any other banded system (the CG2
+        optical matrices)."""
         self.lib = _lib.get()
         self.pa = pa
         self.device = torch.device(device)
-        self.n = pa.N
         self.batch = batch
-        rowptr = np.ascontiguousarray(pa.csr.rowptr)
-        colidx = np.ascontiguousarray(pa.csr.column_indices())
-        perm = np.ascontiguousarray(x_major_permutation(pa))
+        if csr is None:
+            csr = (pa.N, pa.csr.rowptr, pa.csr.column_indices(), x_major_permutation(pa))
+        n, rowptr, colidx, perm = csr
+        self.n = int(n)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        colidx = np.ascontiguousarray(colidx, dtype=np.int32)
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
         h = C.c_void_p()
         _lib.check(self.lib.sb_band_create(
-            pa.N, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p),
+            self.n, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p),
             perm.ctypes.data_as(C.c_void_p), batch, max_band_bytes, C.byref(h)))
         self._h = h
         kl, ku, n = C.c_int32(), C.c_int32(), C.c_int64()

@@ -40,6 +40,7 @@ def build_emulation_library():
     src2 = os.path.join(ROOT, 'simudo_b200', 'csrc', 'band_solver.cu')
     deps = [src, src2, os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_device.cuh'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_tables.h'),
+            os.path.join(ROOT, 'simudo_b200', 'csrc', 'optics.inl'),
             os.path.join(ROOT, 'include', 'simudo_b200.h'),
             os.path.join(EMUL_DIR, 'cuda_emul.h')]
     if (not os.path.exists(EMUL_SO)

@@ -237,3 +237,53 @@ def unstaged_rank_tables_match_staged():
     finally:
         del os.environ['SIMUDO_B200_NO_SMEM_PATTERNS']
     assert torch.equal(v0, v1) and torch.equal(b0, b1)
+
+
+def optics_parity(nx=9, ny=3):
+    """a10: alpha projection, MSORTE matrix / right-hand side and the solved photon
+    flux of every optical field against oracle/optics_oracle.py."""
+    import scipy.sparse as sps
+    from oracle import optics_oracle as oo
+    from simudo_b200.fem.optics_solver import OpticsPlan
+    pa = syn.ib_problem(nx=nx, ny=ny)
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    op = OpticsPlan(plan)
+    sp = op.space
+    u, bw = plan.tensor(st['u']), plan.tensor(st['base_w'])
+    mesh = pa.mesh
+    bf = mesh.boundary_facets()
+    nrm = mesh.boundary_outward_normals(bf)
+    for field, omega in ((0, (1.0, 0.0)), (1, (-1.0, 0.0)), (2, (0.6, 0.8))):
+        inflow = bf[nrm @ np.asarray(omega) < -1e-12]          # Omega . n < 0
+        bc_dofs = sp.facet_dofs(inflow)
+        bc_vals = 1e5 * (1.0 + 0.1 * np.arange(len(bc_dofs)) / len(bc_dofs))
+        # oracle
+        rhs0 = oo.alpha_rhs(pa, sp, st['u'], st['base_w'], field)
+        alpha0, phi0 = oo.solve_field(pa, sp, st['u'], st['base_w'], field, omega,
+                                      bc_dofs, bc_vals)
+        A0, b0 = oo.msorte_system(sp, alpha0, omega, bc_dofs, bc_vals)
+        # device
+        rhs = op.alpha_rhs(field, u, bw).cpu().numpy()
+        assert np.abs(rhs - rhs0).max() <= 1e-13 * np.abs(rhs0).max()
+        alpha = op.project_alpha(field, u, bw)
+        assert np.abs(alpha.cpu().numpy() - alpha0).max() <= 1e-11 * np.abs(alpha0).max()
+        assert alpha0.max() > 0
+        vals, b = op.assemble(plan.tensor(alpha0), omega, plan.tensor(bc_dofs, torch.int32),
+                              plan.tensor(bc_vals))
+        A = sps.csr_matrix((vals.cpu().numpy(), sp.colidx, sp.rowptr),
+                           shape=(sp.n_dofs, sp.n_dofs))
+        dA = abs(A - A0)
+        scale = abs(A0).max(axis=1).toarray().ravel()
+        assert (dA.max(axis=1).toarray().ravel() <= 1e-12 * scale).all()
+        assert np.array_equal(b.cpu().numpy(), b0)
+        phi, cells = op.solve_field(field, u, bw, omega, plan.tensor(bc_dofs, torch.int32),
+                                    plan.tensor(bc_vals))
+        phi = phi.cpu().numpy()
+        err = np.abs(phi - phi0).max() / np.abs(phi0).max()
+        assert err <= 1e-9, err
+        assert np.array_equal(cells.cpu().numpy(), phi[sp.cell_dofs])
+        # bit-reproducible (fixed-order segmented sums, no atomics)
+        vals2, _ = op.assemble(plan.tensor(alpha0), omega, plan.tensor(bc_dofs, torch.int32),
+                               plan.tensor(bc_vals))
+        assert torch.equal(vals2, vals)

@@ -78,3 +78,7 @@ def test_band_solver_with_refinement_emulated(emulated_lib):
     r = A @ x - b.numpy()
     rs = 1.0 / np.abs(A).max(axis=1).toarray().ravel()
     assert np.abs(rs * r).max() < 1e-12 * np.abs(rs * b.numpy()).max() + 1e-20
+
+
+def test_optics_parity_emulated(emulated_lib):
+    hc.optics_parity(nx=7, ny=3)

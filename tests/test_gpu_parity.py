@@ -88,3 +88,7 @@ def test_no_cpu_fallback():
     pa = syn.pn_problem(nx=4, ny=2)
     with pytest.raises(RuntimeError):
         AssemblyPlan(pa, device='cpu')
+
+
+def test_optics_parity():
+    hc.optics_parity(nx=33, ny=5)
