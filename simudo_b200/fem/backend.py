@@ -109,6 +109,27 @@ class CudaBackend(object):
         avg = cache['thm'] - torch.zeros_like(cache['thm']).index_add_(0, cache['inv'], phi_avg)
         self.plan.rebase_w(self.u, self.base_w, band, cache['cells'], avg)
 
+    # -- a10: optical sub-solves (physics/steppers.py:120-136) ------------------------
+    def optical_update(self, space, specs):
+        """``specs``: [(field index, direction, bc_dofs, bc_values)]; solves every
+        field for the current PDD state and writes its flux into ``phi_opt``."""
+        if getattr(self, '_optics', None) is None:
+            from .optics_solver import OpticsPlan
+            self._optics = OpticsPlan(self.plan, space)
+            self._optics_bc = {}
+        T = self.T
+        self.phi_nodal = getattr(self, 'phi_nodal', {})
+        for f, direction, bc_dofs, bc_vals in specs:
+            if f not in self._optics_bc:
+                self._optics_bc[f] = T(bc_dofs, torch.int32)
+            phi, _ = self._optics.solve_field(f, self.u, self.base_w, direction,
+                                              self._optics_bc[f], T(bc_vals),
+                                              out=self.phi_opt[f])
+            self.phi_nodal[f] = phi
+
+    def get_phi_opt(self):
+        return self.phi_opt.cpu().numpy()
+
     def surface_flux(self, p, cells, locals_):
         T = self.T
         out = self.plan.surface_flux(self.u, p, T(cells, torch.int32), T(locals_, torch.int8),

@@ -142,7 +142,8 @@ class PDDSystem(_SystemBase):
         self._u_host = np.zeros(self.pa.N)
         self.thmeq_phi = np.zeros((nc, 6))
         self._base_w0 = np.zeros((len(self.bands), nc))
-        self.phi_opt = np.zeros((len(fields), nc, 6)) if fields else None
+        self._phi_opt_host = np.zeros((len(fields), nc, 6)) if fields else None
+        self._phi_opt_stale = False      # True: the backend holds a newer flux
         self._backend = None
         self._dirty_host = False
 
@@ -367,6 +368,59 @@ class PDDSystem(_SystemBase):
             self._backend.set_state(self._u_host, self._base_w0 if self.full else None,
                                     self.thmeq_phi if self.full else None, self.phi_opt)
 
+    # -- a10 optics ------------------------------------------------------------------
+    @property
+    def phi_opt(self):
+        if self._phi_opt_stale:
+            self._phi_opt_host = np.array(self._backend.get_phi_opt(), copy=True)
+            self._phi_opt_stale = False
+        return self._phi_opt_host
+
+    def _optical_lowering(self):
+        """CG2 space + per field (direction, inflow dofs, inflow flux): the lowered
+        form of ``optical.spatial.add_BC('<field>/Phi', facets, flux)``
+        (``optical1.py1:57-61``)."""
+        if getattr(self, '_opt_low', None) is None:
+            from ..fem.cg2 import CG2Space
+            space = CG2Space(self.mesh)
+            osp = self.pdd.problem_data.optical.spatial
+            fields = []
+            for fld in self.fields:
+                dofs, vals = [], []
+                for bc, facets in osp.bc_facets(fld.key + '/Phi'):
+                    if len(facets) == 0:
+                        continue
+                    d = space.facet_dofs(facets)
+                    v = bc.value
+                    v = v.m_as('1/mesh_unit^2/s') if hasattr(v, 'm_as') else v
+                    dofs.append(d)
+                    vals.append(np.full(len(d), float(v)))
+                if dofs:
+                    d = np.concatenate(dofs)
+                    ud, first = np.unique(d, return_index=True)
+                    fields.append((tuple(float(x) for x in fld.direction[:2]),
+                                   ud.astype(np.int32), np.concatenate(vals)[first]))
+                else:
+                    fields.append((tuple(float(x) for x in fld.direction[:2]),
+                                   np.zeros(0, np.int32), np.zeros(0)))
+            self._opt_low = (space, fields)
+        return self._opt_low
+
+    def optical_update(self):
+        """``run_optical_subsolvers`` (``physics/steppers.py:120-136``): for every
+        field update_input -> solve -> update_output, on the backend's device state."""
+        if not self.fields:
+            return
+        space, fields = self._optical_lowering()
+        scale = float(self.pdd.problem_data.optical.Phi_scale.magnitude)
+        specs = [(f, d, dofs, vals * scale) for f, (d, dofs, vals) in enumerate(fields)]
+        self.backend.optical_update(space, specs)
+        self._phi_opt_stale = True       # the backend's copy is newer; pulled on demand
+
+    def photon_flux_host(self):
+        """[n_fields, Nc, 6] photon flux on the PDD mesh (``Phi_pddproj``)."""
+        return self.phi_opt
+
     def set_photon_flux(self, field_index, values):
         """P2 nodal photon flux [Nc, 6] of one optical field, 1/(mesh_unit^2 s)."""
         self.phi_opt[field_index] = values
@@ -402,9 +456,15 @@ class PDDSystem(_SystemBase):
 
     # -- save / restore for the adaptive stepper (adaptive_stepper.py:295-307) ---------
     def save(self):
-        return dict(u=self.u_host().copy(), base_w=np.array(self.base_w_host(), copy=True))
+        d = dict(u=self.u_host().copy(), base_w=np.array(self.base_w_host(), copy=True))
+        if self.fields:                  # optical/<field>/mixed_solution (optical.py:291-297)
+            d['phi_opt'] = np.array(self.phi_opt, copy=True)
+        return d
 
     def restore(self, saved):
+        if 'phi_opt' in saved:
+            self._phi_opt_host = saved['phi_opt'].copy()
+            self._phi_opt_stale = False
         self._u_host = saved['u'].copy()
         self._base_w0 = saved['base_w'].copy()
         if self._backend is not None:

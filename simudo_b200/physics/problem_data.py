@@ -30,6 +30,11 @@ class ProblemData(SetattrInitMixin):
             self._optical = Optical(problem_data=self)
         return self._optical
 
+    def optical_update(self, pdd=None):
+        """Solve every optical field for the current PDD state (the body of
+        ``run_optical_subsolvers``, ``physics/steppers.py:120-136``)."""
+        (pdd or self.pdd).system.optical_update()
+
     @property
     def goal_abbreviated(self):
         return {'local charge neutrality': 'ntrl', 'thermal equilibrium': 'thmq',

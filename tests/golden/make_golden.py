@@ -9,6 +9,9 @@
   of the hot path anywhere in the reference tree.
 * ``pn_diode_JV_oracle.json``: the same sweep computed with the oracle backend
   (C restatement + scipy LU), the fixture the GPU run is compared with.
+* ``ib_cell_JV_oracle.json``: illuminated four-layer intermediate-band cell
+  (example/fourlayer.py at the reduced size FOURLAYER_SMALL: light ramp +
+  bias sweep with self-consistent optics) through the oracle backend.
 """
 import json
 import os
@@ -34,6 +37,12 @@ def decode_svg(path='/root/reference/doc/source/_static/tutorial-pn-diode-JV.svg
     return out
 
 
+# reduced fourlayer (BASELINE config 2 shape: 4 layers, 3 bands, 3 optical fields, X = 100)
+FOURLAYER_SMALL = dict(p_thickness=0.2, n_thickness=0.2, IB_thickness=0.4, mesh_start=0.01,
+                       mesh_factor=1.5, mesh_max=0.05, V_exts=[0.0, 0.2, 0.4], X=100,
+                       CB_E=1.1, IB_E=0.65)
+
+
 def main():
     if os.path.exists('/root/reference'):
         jv = decode_svg()
@@ -45,6 +54,13 @@ def main():
     jv = pn_diode.run(backend_factory=OracleBackend)
     with open(os.path.join(HERE, 'pn_diode_JV_oracle.json'), 'w') as f:
         json.dump(dict(source='oracle backend, tests/golden/make_golden.py',
+                       units=['V', 'mA/cm^2'], jv=[(float(v), float(j)) for v, j in jv]),
+                  f, indent=1)
+    from simudo_b200.example import fourlayer
+    jv = fourlayer.run(P=FOURLAYER_SMALL, backend_factory=OracleBackend)
+    with open(os.path.join(HERE, 'ib_cell_JV_oracle.json'), 'w') as f:
+        json.dump(dict(source='oracle backend, tests/golden/make_golden.py, FOURLAYER_SMALL',
+                       params={k: v for k, v in FOURLAYER_SMALL.items()},
                        units=['V', 'mA/cm^2'], jv=[(float(v), float(j)) for v, j in jv]),
                   f, indent=1)
 

@@ -105,6 +105,18 @@ class OracleBackend(object):
         self.u, self.base_w = orc_mod.rebase_w(self.pa, self.u, self.base_w, band,
                                                ohmic['cells'], avg)
 
+    def optical_update(self, space, specs):
+        from oracle import optics_oracle as oo
+        self.phi_nodal = getattr(self, 'phi_nodal', {})
+        for f, direction, bc_dofs, bc_vals in specs:
+            _, phi = oo.solve_field(self.pa, space, self.u, self.base_w, f, direction,
+                                    bc_dofs, bc_vals)
+            self.phi_opt[f] = phi[space.cell_dofs]
+            self.phi_nodal[f] = phi
+
+    def get_phi_opt(self):
+        return self.phi_opt
+
     def surface_flux(self, p, cells, locals_):
         mesh = self.pa.mesh
         facets = mesh.cell_facets[np.asarray(cells), np.asarray(locals_).astype(np.int64)]

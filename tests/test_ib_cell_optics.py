@@ -1,0 +1,77 @@
+"""End-to-end a10: illuminated four-layer intermediate-band cell (BASELINE
+config 2 at reduced size) -- light ramp and bias sweep with self-consistent
+optics (steppers.py:120-150): every Newton iteration re-projects alpha(u_I),
+re-solves the three MSORTE fields and feeds Phi back into the generation term.
+
+CPU: host logic through the oracle backend + physical sanity of the result.
+GPU: the same run through the CUDA backend against the oracle fixture, 1e-6.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+from make_golden import FOURLAYER_SMALL            # noqa: E402
+
+
+def _golden():
+    with open(os.path.join(HERE, 'golden', 'ib_cell_JV_oracle.json')) as f:
+        return json.load(f)['jv']
+
+
+@pytest.fixture(scope='module')
+def oracle_run():
+    from oracle_backend import OracleBackend
+    from simudo_b200.example import fourlayer
+    return fourlayer.run(P=FOURLAYER_SMALL, backend_factory=OracleBackend, return_problem=True)
+
+
+def test_oracle_run_reproduces_fixture(oracle_run):
+    jv, _, _ = oracle_run
+    for (v, j), (v0, j0) in zip(jv, _golden()):
+        assert abs(v - v0) < 1e-12 and abs(j - j0) <= 1e-8 * abs(j0)
+
+
+def test_photocurrent_is_bounded_by_absorbed_flux(oracle_run):
+    """|J_sc| <= q * (photons absorbed), and most band-to-band absorbed photons are
+    collected at short circuit (thin, high-mobility device)."""
+    jv, problem, _ = oracle_run
+    sysm = problem.pdd.system
+    space, fields = sysm._optical_lowering()
+    be = sysm.backend
+    x = space.node_coordinates()[:, 0]
+    q_mA = 1.602176487e-19 * 1e3 * 1e8           # e * (1/um^2/s -> 1/cm^2/s) in mA/cm^2
+    absorbed = {}
+    for f, fld in enumerate(sysm.fields):
+        phi = be.phi_nodal[f]
+        left, right = phi[np.isclose(x, x.min())].mean(), phi[np.isclose(x, x.max())].mean()
+        assert right < left and phi.min() > -1e-9 * left          # attenuated, non-negative
+        assert abs(left / fields[f][2][0] - 1) < 1e-12            # inflow Dirichlet value
+        absorbed[fld.key] = (left - right) * q_mA
+    jsc = -jv[0][1]
+    total = sum(absorbed.values())
+    assert 0 < jsc < total
+    assert jsc > 0.5 * absorbed['forward_cv']
+    # forward bias reduces the collected current
+    assert -jv[-1][1] < jsc
+
+
+def test_dark_limit_has_no_photocurrent():
+    from oracle_backend import OracleBackend
+    from simudo_b200.example import fourlayer
+    P = dict(FOURLAYER_SMALL, X=0, V_exts=[0.0, 0.2])
+    jv = fourlayer.run(P=P, backend_factory=OracleBackend)
+    assert abs(jv[0][1]) < 1e-6 and jv[1][1] > 0
+
+
+@pytest.mark.gpu
+def test_ib_cell_on_gpu_matches_oracle_fixture():
+    from simudo_b200.example import fourlayer
+    jv = fourlayer.run(P=FOURLAYER_SMALL)
+    for (v, j), (v0, j0) in zip(jv, _golden()):
+        assert abs(v - v0) < 1e-9
+        assert abs(j - j0) <= 1e-6 * abs(j0), (v, j, j0)
