@@ -262,6 +262,20 @@ int sb_optics_assemble(sb_optics* o, const double* d_alpha, double ox, double oy
 /* d_cells[n_cells][6] = d_nodal[cell_dofs]: one field's slice of sb_state.d_phi_opt    */
 int sb_optics_to_cells(sb_optics* o, const double* d_nodal, double* d_cells, void* stream);
 
+/* ---- local-charge-neutrality stage ----------------------
+ * One Newton iteration of  <w, rho(phi) / eps> = 0  for the DG1 potential d_phi
+ * [n_cells][3] with every band at zero quasi-Fermi level: the initial-guess stage
+ * PoissonDriftDiffusion.easy_auto_pre_solve() runs for goal 'local charge neutrality'
+ * (physics/poisson_drift_diffusion1.py1:89-125; LocalChargeNeutralitySolver,
+ * physics/poisson_drift_diffusion.py:318-331 = NewtonSolverMaxDu,
+ * fem/newton_solver.py:533-541).  Residual, the 3 x 3 block Jacobian, its solve, the
+ * clipped/damped update and the metrics of sb_newton_update (same d_out layout) in one
+ * launch; d_du / d_b (optional, [n_cells][3]) receive the raw Newton step and residual. */
+int sb_lcn_iteration(const sb_model* model, int64_t n_cells, const double* d_cell_vertices,
+                     const int32_t* d_cell_tag, const double* d_tag_params, double* d_phi,
+                     const double* d_tol, double omega, double max_du, double rel_tol,
+                     double abs_tol, double* d_du, double* d_b, double* d_out, void* stream);
+
 /* ---- measurement ------------------------------------------------------------------
  * CUDA-event timing (on the launching stream) of the dominant kernel of the last
  * sb_assemble call; sb_plan_last_kernel_ms synchronises on that event.            */

@@ -24,7 +24,7 @@ EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
             'sb_band_solve', 'sb_band_set_refinement', 'sb_optics_create',
             'sb_optics_destroy', 'sb_optics_tables_size', 'sb_optics_alpha_rhs',
-            'sb_optics_assemble', 'sb_optics_to_cells']
+            'sb_optics_assemble', 'sb_optics_to_cells', 'sb_lcn_iteration']
 
 
 class SbProblem(C.Structure):
@@ -106,6 +106,9 @@ def _declare(lib):
     lib.sb_optics_assemble.restype = C.c_int
     lib.sb_optics_to_cells.argtypes = [vp, vp, vp, vp]
     lib.sb_optics_to_cells.restype = C.c_int
+    lib.sb_lcn_iteration.argtypes = [C.POINTER(SbModel), i64, vp, vp, vp, vp, vp, dbl, dbl, dbl,
+                                     dbl, vp, vp, vp, vp]
+    lib.sb_lcn_iteration.restype = C.c_int
     return lib
 
 

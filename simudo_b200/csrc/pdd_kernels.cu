@@ -1061,3 +1061,4 @@ extern "C" int sb_surface_flux(sb_plan* pl, const double* d_u, int32_t p, int64_
 }
 
 #include "optics.inl"
+#include "lcn.inl"

@@ -15,7 +15,7 @@ import torch
 from .assembly import AssemblyPlan
 from .linear_solver import BandSolver
 
-__all__ = ['CudaBackend']
+__all__ = ['CudaBackend', 'CudaLCNBackend']
 
 
 class CudaBackend(object):
@@ -135,3 +135,66 @@ class CudaBackend(object):
         out = self.plan.surface_flux(self.u, p, T(cells, torch.int32), T(locals_, torch.int8),
                                      T(np.ones(len(cells)))).cpu().numpy()
         return float(out[0]), float(out[1])
+
+
+class CudaLCNBackend(object):
+    """Device state + ``sb_lcn_iteration`` for the local-charge-neutrality stage
+    (``LCNSystem``).  No CPU fallback."""
+    name = 'cuda'
+
+    def __init__(self, system, device=None):
+        import ctypes as C
+        from .. import _lib
+        self._C, self._lib_mod = C, _lib
+        self.lib = _lib.get()
+        emul = _lib.is_emulated()
+        if device is None:
+            device = 'cpu' if emul else 'cuda:0'
+        self.device = torch.device(device)
+        if not emul and (self.device.type != 'cuda' or not torch.cuda.is_available()):
+            raise RuntimeError('simudo_b200 needs a CUDA device (no CPU fallback)')
+        self.system = system
+        self.model = system.model
+
+        def T(a, dtype=torch.float64):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+        self.T = T
+        self.cell_vertices = T(system.cell_vertices)
+        self.cell_tag = T(system.cell_tag, torch.int32)
+        self.tag_params = T(system.tag_params)
+        nc = system.cell_vertices.shape[0]
+        self.n_cells = nc
+        self.phi = torch.zeros((nc, 3), dtype=torch.float64, device=self.device)
+        self.du = torch.zeros_like(self.phi)
+        self.b = torch.zeros_like(self.phi)
+        self._out = torch.zeros(6, dtype=torch.float64, device=self.device)
+        self._tol = None
+
+    def set_phi(self, phi):
+        self.phi = self.T(phi).reshape(self.n_cells, 3).clone()
+
+    def get_phi(self):
+        return self.phi.cpu().numpy()
+
+    def get_du(self):
+        return self.du.cpu().numpy().ravel()
+
+    def get_b(self):
+        return self.b.cpu().numpy().ravel()
+
+    def iterate(self, tol, omega, max_du, rel_tol, abs_tol):
+        C = self._C
+        if self._tol is None:
+            self._tol = self.T(tol)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        stream = (C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                  if self.device.type == 'cuda' else None)
+        self._lib_mod.check(self.lib.sb_lcn_iteration(
+            C.byref(self.model), self.n_cells, p(self.cell_vertices), p(self.cell_tag),
+            p(self.tag_params), p(self.phi), p(self._tol), float(omega),
+            float(max_du) if max_du else 0.0, float(rel_tol), float(abs_tol),
+            p(self.du), p(self.b), p(self._out), stream))
+        out = self._out.cpu().numpy()
+        return dict(b_norm=float(out[0]), du_norm=float(out[1]),
+                    rel_du_norm=float(np.sqrt(out[2])) if out[5] > 0 else float('nan'),
+                    combined_du_norm=float(out[3]), has_nans=bool(out[4] > 0))

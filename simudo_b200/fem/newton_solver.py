@@ -178,41 +178,30 @@ class NewtonSolverLogDamping(NewtonSolver):
         raise NotImplementedError('log damping is not lowered to the device yet')
 
 
-class _HostBlockDiagonalMixin(object):
+class _BlockDiagonalMixin(object):
     """The local-charge-neutrality stage is a block-diagonal 3x3 problem per
-    cell and runs vectorised on the host (``LCNSystem``)."""
+    cell: assembly, solve, update and metrics are one launch (``LCNSystem.iterate``
+    -> ``sb_lcn_iteration``)."""
 
     def do_iteration(self):
         sysm = self.system
-        if not hasattr(sysm, 'residual_jacobian'):
+        if not hasattr(sysm, 'iterate'):
             return super().do_iteration()
         for hook in self.user_pre_iteration_hooks:
             hook(self)
-        F, J = sysm.residual_jacobian()
-        du = np.linalg.solve(J, F[:, :, None])[:, :, 0]
-        maxdu = self.get_max_du()
-        step = du if maxdu is None else np.clip(du, -maxdu, maxdu)
-        u = sysm.phi
-        rel_tol = self.parameters['relative_tolerance']
-        abs_tol = self.parameters['absolute_tolerance']
-        tol = self._tolerance_vector().reshape(u.shape)
+        m = sysm.iterate(self._tolerance_vector(), self.get_omega(), self.get_max_du(),
+                         self.parameters['relative_tolerance'],
+                         self.parameters['absolute_tolerance'])
         s = self.solution
-        with np.errstate(divide='ignore', invalid='ignore'):
-            s.combined_du_norm = float(np.max(np.abs(du) / (np.abs(u) * rel_tol + abs_tol * tol)))
-            r = np.abs(du / u)
-            ok = ~np.isnan(r)
-            s.rel_du_norm = float(np.linalg.norm(r[ok])) if ok.any() else float('nan')
-        s.b_norm = float(np.abs(F).max())
-        s.du_norm = float(np.abs(du).max())
-        s.has_nans = bool(np.isnan(u).any() or np.isnan(s.b_norm))
-        self._du_host, self._b_host = du.ravel(), F.ravel()
-        sysm.phi = u - self.get_omega() * step
+        s.b_norm, s.du_norm = m['b_norm'], m['du_norm']
+        s.rel_du_norm, s.combined_du_norm = m['rel_du_norm'], m['combined_du_norm']
+        s.has_nans = m['has_nans']
         self.logger.info('* iteration {:>3d}; {}'.format(self.iteration, s.str_error()))
         for hook in self.user_post_iteration_hooks:
             hook(self)
 
 
-class LocalChargeNeutralitySolver(_HostBlockDiagonalMixin, NewtonSolverMaxDu):
+class LocalChargeNeutralitySolver(_BlockDiagonalMixin, NewtonSolverMaxDu):
     """``poisson_drift_diffusion.py:318-331``."""
 
     def do_init_parameters(self):

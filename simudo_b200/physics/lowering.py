@@ -476,22 +476,48 @@ class LCNSystem(_SystemBase):
     """goal 'local charge neutrality': DG1 potential only, residual
     <w rho(phi)/eps> with UFL's estimated degree-4 (6-point) rule
     (``poisson_drift_diffusion1.py1:89-125``).  Cells decouple (block-diagonal
-    3x3 Jacobian), so this initial-guess stage runs vectorised on the host
-    (SURVEY 8f-2 lists moving the initialisation stages to the GPU as "next")."""
+    3x3 Jacobian); one Newton iteration is a single kernel launch
+    (``sb_lcn_iteration``, ``csrc/lcn.inl``) driven through the backend."""
 
     def __init__(self, pdd):
         super().__init__(pdd)
         tp = M.new_tag_params(len(self.cvs))
         self._band_rows(tp)
         self.tag_params = tp
+        self.model = M.make_model(self.band_model_list(), [], n_tags=len(self.cvs),
+                                  bands_have_dofs=False)
         nc = self.mesh.num_cells
-        self.phi = np.zeros((nc, 3))
-        from ..fem.reference_element import triangle_default_scheme, p1_eval
-        pts, w = triangle_default_scheme(4)
-        self.qw = w
-        self.ql = p1_eval(pts).T                    # [q, 3]
+        self._phi_host = np.zeros((nc, 3))
+        self.cell_vertices = np.ascontiguousarray(
+            self.mesh.coordinates[self.mesh.cells].reshape(nc, 6))
         self.N = 3 * nc
         self.full = False
+        self._backend = None
+
+    @property
+    def backend(self):
+        if self._backend is None:
+            factory = self.pdd.problem_data.backend_factory
+            if factory is None:
+                from ..fem.backend import CudaLCNBackend
+                cls = CudaLCNBackend
+            else:
+                cls = factory.lcn_backend
+            self._backend = cls(self)
+            self._backend.set_phi(self._phi_host)
+        return self._backend
+
+    @property
+    def phi(self):
+        if self._backend is not None:
+            return self._backend.get_phi()
+        return self._phi_host
+
+    @phi.setter
+    def phi(self, value):
+        self._phi_host = np.array(value, dtype=np.float64, copy=True).reshape(-1, 3)
+        if self._backend is not None:
+            self._backend.set_phi(self._phi_host)
 
     def phi_nodal(self):
         return self.phi
@@ -505,32 +531,9 @@ class LCNSystem(_SystemBase):
     def initialize_from(self, other):
         self.phi = np.array(other.phi_nodal(), copy=True)
 
-    def residual_jacobian(self):
-        tp = self.tag_params[self.cell_tag]          # [Nc, stride]
-        kT = tp[:, M.TP_KT][:, None]
-        phiq = self.phi @ self.ql.T                  # [Nc, q]
-        rho = np.repeat(tp[:, M.TP_RHO_STATIC][:, None], phiq.shape[1], axis=1)
-        drho = np.zeros_like(rho)
-        for b, band in enumerate(self.bands):
-            o = M.TP_BAND0 + 5 * b
-            N, E = tp[:, o + M.TPB_N][:, None], tp[:, o + M.TPB_E][:, None]
-            s = band.sign
-            if band.kind == M.BAND_NONDEGENERATE:
-                u = N * np.exp(s * E / kT) * np.exp(-s * phiq / kT)
-                du = -s / kT * u
-            else:
-                e = np.exp(s * (phiq - E) / kT)
-                f = 1.0 / (1.0 + e)
-                u = N * f
-                du = -s / kT * N * f * (e * f)
-            rho += s * u
-            drho += s * du
-        eps = tp[:, M.TP_EPS][:, None]
-        _, det = self.mesh.cell_jacobians()
-        wq = self.qw[None, :] * np.abs(det)[:, None]
-        F = np.einsum('cq,qi->ci', wq * rho / eps, self.ql)
-        J = np.einsum('cq,qi,qj->cij', wq * drho / eps, self.ql, self.ql)
-        return F, J
+    def iterate(self, tol, omega, max_du, rel_tol, abs_tol):
+        """One damped Newton iteration; returns the metric dict of ``newton_update``."""
+        return self.backend.iterate(tol, omega, max_du, rel_tol, abs_tol)
 
     def save(self):
         return dict(phi=self.phi.copy())

@@ -41,6 +41,7 @@ def build_emulation_library():
     deps = [src, src2, os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_device.cuh'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'pdd_tables.h'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'optics.inl'),
+            os.path.join(ROOT, 'simudo_b200', 'csrc', 'lcn.inl'),
             os.path.join(ROOT, 'include', 'simudo_b200.h'),
             os.path.join(EMUL_DIR, 'cuda_emul.h')]
     if (not os.path.exists(EMUL_SO)

@@ -287,3 +287,48 @@ def optics_parity(nx=9, ny=3):
         vals2, _ = op.assemble(plan.tensor(alpha0), omega, plan.tensor(bc_dofs, torch.int32),
                                plan.tensor(bc_vals))
         assert torch.equal(vals2, vals)
+
+
+def lcn_iteration_parity():
+    """(f-2) one local-charge-neutrality Newton iteration (sb_lcn_iteration) against the
+    numpy restatement, on the four-layer IB device's first stage."""
+    from oracle_backend import OracleBackend, OracleLCNBackend
+    from simudo_b200.fem.backend import CudaLCNBackend
+    from simudo_b200.example import fourlayer
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from make_golden import FOURLAYER_SMALL
+
+    class Stop(Exception):
+        pass
+
+    captured = {}
+
+    class Capture(OracleBackend):
+        pass
+
+    def lcn_factory(system):
+        captured['system'] = system
+        raise Stop()
+    Capture.lcn_backend = staticmethod(lcn_factory)
+    try:
+        fourlayer.run(P=FOURLAYER_SMALL, backend_factory=Capture)
+    except Stop:
+        pass
+    sysm = captured['system']
+    rng = np.random.RandomState(3)
+    phi0 = 0.3 + 0.2 * rng.rand(sysm.mesh.num_cells, 3)
+    ref, dev = OracleLCNBackend(sysm), CudaLCNBackend(sysm)
+    ref.set_phi(phi0)
+    dev.set_phi(phi0)
+    tol = sysm.tolerance_vector()
+    for it in range(3):
+        m0 = ref.iterate(tol, 0.2, 0.02, 1e-10, 0.1)
+        m1 = dev.iterate(tol, 0.2, 0.02, 1e-10, 0.1)
+        assert np.abs(dev.get_phi() - ref.get_phi()).max() < 1e-13
+        scale = np.abs(ref.get_b()).max()
+        assert np.abs(dev.get_b() - ref.get_b()).max() <= 1e-12 * scale
+        assert np.abs(dev.get_du() / ref.get_du() - 1).max() < 1e-9
+        for k in ('b_norm', 'du_norm', 'rel_du_norm', 'combined_du_norm'):
+            assert abs(m1[k] - m0[k]) <= 1e-9 * abs(m0[k]), (k, m0[k], m1[k])
+        assert m1['has_nans'] == m0['has_nans']

@@ -121,3 +121,75 @@ class OracleBackend(object):
         mesh = self.pa.mesh
         facets = mesh.cell_facets[np.asarray(cells), np.asarray(locals_).astype(np.int64)]
         return orc_mod.surface_flux(self.pa, self.u, p, facets)
+
+
+class OracleLCNBackend(object):
+    """Numpy restatement of the local-charge-neutrality Newton iteration
+    (``poisson_drift_diffusion1.py1:89-125``; solver ``poisson_drift_diffusion.py:
+    318-331``): vectorised over cells, generic 3x3 solves, metrics from
+    ``oracle.newton_metrics``.  Test infrastructure only."""
+    name = 'oracle'
+
+    def __init__(self, system):
+        from simudo_b200.fem import model as M
+        from simudo_b200.fem.reference_element import triangle_default_scheme, p1_eval
+        self.M = M
+        self.system = system
+        pts, w = triangle_default_scheme(4)
+        self.qw = w
+        self.ql = p1_eval(pts).T                    # [q, 3]
+        self.phi = None
+        self.du = self.b = None
+
+    def set_phi(self, phi):
+        self.phi = np.array(phi, dtype=np.float64).reshape(-1, 3)
+
+    def get_phi(self):
+        return self.phi
+
+    def get_du(self):
+        return self.du.ravel()
+
+    def get_b(self):
+        return self.b.ravel()
+
+    def residual_jacobian(self):
+        M, sysm = self.M, self.system
+        tp = sysm.tag_params[sysm.cell_tag]          # [Nc, stride]
+        kT = tp[:, M.TP_KT][:, None]
+        phiq = self.phi @ self.ql.T                  # [Nc, q]
+        rho = np.repeat(tp[:, M.TP_RHO_STATIC][:, None], phiq.shape[1], axis=1)
+        drho = np.zeros_like(rho)
+        for b, band in enumerate(sysm.bands):
+            o = M.TP_BAND0 + 5 * b
+            N, E = tp[:, o + M.TPB_N][:, None], tp[:, o + M.TPB_E][:, None]
+            s = band.sign
+            if band.kind == M.BAND_NONDEGENERATE:
+                u = N * np.exp(s * E / kT) * np.exp(-s * phiq / kT)
+                du = -s / kT * u
+            else:
+                e = np.exp(s * (phiq - E) / kT)
+                f = 1.0 / (1.0 + e)
+                u = N * f
+                du = -s / kT * N * f * (e * f)
+            rho += s * u
+            drho += s * du
+        eps = tp[:, M.TP_EPS][:, None]
+        _, det = sysm.mesh.cell_jacobians()
+        wq = self.qw[None, :] * np.abs(det)[:, None]
+        F = np.einsum('cq,qi->ci', wq * rho / eps, self.ql)
+        J = np.einsum('cq,qi,qj->cij', wq * drho / eps, self.ql, self.ql)
+        return F, J
+
+    def iterate(self, tol, omega, max_du, rel_tol, abs_tol):
+        F, J = self.residual_jacobian()
+        du = np.linalg.solve(J, F[:, :, None])[:, :, 0]
+        step = du if not max_du else np.clip(du, -max_du, max_du)
+        self.phi = self.phi - omega * step
+        self.du, self.b = du, F
+        m = orc_mod.newton_metrics(self.phi.ravel(), du.ravel(), F.ravel(),
+                                   np.asarray(tol).ravel(), rel_tol, abs_tol)
+        return {k: (bool(v) if k == 'has_nans' else float(v)) for k, v in m.items()}
+
+
+OracleBackend.lcn_backend = OracleLCNBackend

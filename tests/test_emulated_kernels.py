@@ -82,3 +82,7 @@ def test_band_solver_with_refinement_emulated(emulated_lib):
 
 def test_optics_parity_emulated(emulated_lib):
     hc.optics_parity(nx=7, ny=3)
+
+
+def test_lcn_iteration_parity_emulated(emulated_lib):
+    hc.lcn_iteration_parity()

@@ -92,3 +92,7 @@ def test_no_cpu_fallback():
 
 def test_optics_parity():
     hc.optics_parity(nx=33, ny=5)
+
+
+def test_lcn_iteration_parity():
+    hc.lcn_iteration_parity()
