@@ -755,6 +755,12 @@ SB_HD int sb_rank(const SbRanks& r, int e) { return (int)((r.w[e >> 2] >> (8 * (
 
 SB_HD void sb_store(double* vals, int64_t rowbase, int rk, double v, bool shared_slot) {
   if (!vals || rk == 0xFF) return;
+#if defined(SB_EXP_NOSTORE)          /* experiment: keep the math, drop the scatter */
+  if (v == 1.2345e-300) vals[0] = v;
+  return;
+#elif defined(SB_EXP_STOREONLY)      /* experiment: keep the scatter, drop the math */
+  v = 1.0;
+#endif
   double* dst = vals + rowbase + rk;
   if (shared_slot) SB_ATOMIC_ADD(dst, v); else *dst = v;
 }
@@ -902,6 +908,205 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
       }
     }
     if (io.b) io.b[io.d0[0] + i] = Fi;
+  }
+}
+
+
+/* =========================================================================
+ * Staged fast path.  Measured on B200 (profiles/README.md, "store-bound"): with
+ * one thread per cell every structural entry is its own 8-byte store -- a 32-byte
+ * sector transaction each -- and the row kernels spend 10.2 of 10.5 ms in that
+ * scatter; the arithmetic alone takes 2.9 ms.  Here a thread only *stages* the
+ * entries of one entity group (3 adjacent rows) in shared memory, in emission
+ * order; the warp then flushes cell after cell with lane = entry, so the stores of
+ * one instruction fall into the same one or two CSR rows and coalesce into full
+ * sectors (DG and interior rows are written as whole contiguous runs).
+ *
+ * Staging slot of lane:  [r3 * NK + k] value of emission slot k of row r3
+ *                        [3 * NK + r3] residual of row r3
+ * NK = 24 for the DG group (k: 0..11 BDM cols, 12 + 3 q + l DG col l of q),
+ * NK = 18 for the BDM groups (k: 0..11 BDM, 12..14 DG(PS), 15..17 DG(0)) --
+ * the same order as the packed rank table patk.
+ * ========================================================================= */
+#define SB_STAGE_STRIDE 77          /* doubles per lane: 3 * 24 + 3 used, odd stride */
+
+/* per-warp flush metadata, one entry per lane (cell) and group */
+struct SbWarpMeta {
+  int64_t rb[5][32];                /* vals offset of the group's first row   */
+  int32_t rl[5][32];                /* row length                             */
+  int32_t d0[5][32];                /* global dof of the group's first row    */
+  int32_t info[32];                 /* bit 0 active, bit 1 inside, bits 8.. pattern */
+};
+
+/* DG1 rows of sub-problem PS into the staging area (see sb_rows_scalar) */
+template <int PS, int NQ>
+SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCellGeom& g,
+                                bool inside, const double* fl, const double* sl, double coef,
+                                const double* mom1, const double* momJ, double* st) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double Fi = 0.0;
+    if (inside) {
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        const double dv = g.sdet * T.Dhat[m][i];
+        Fi += dv * fl[m];
+        st[i * 24 + m] = dv;
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) Fi += coef * T.G1[i][t] * mom1[t];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
+          st[i * 24 + 12 + 3 * q + l] = coef * v;
+        }
+    } else {
+      const double c1 = M.ext_w_coef * g.adet;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double v = c1 * T.M1[i][l];
+        Fi += v * sl[l];
+        st[i * 24 + 12 + 3 * PS + l] = v;
+      }
+    }
+    st[72 + i] = Fi;
+  }
+}
+
+/* the three BDM rows of entity group grp (facet 0, 1, 2, interior) into the staging
+ * area; MODE as in sb_rows_flux_fast                                             */
+template <int PS, int MODE>
+SB_HD void sb_stage_flux_group(const SbTables& T, const sb_model& M, const SbCellGeom& g,
+                               const double* W, const double (*V)[6][3], const double* fl,
+                               const double* sl, double jf, int grp, double* st) {
+  const double sc = (MODE == 2 ? M.ext_j_coef : 1.0) * g.iad;
+  const double divsign = (MODE == 0) ? -g.sdet : g.sdet;
+#pragma unroll 1
+  for (int r3 = 0; r3 < 3; ++r3) {
+    const int i = 3 * grp + r3;
+    double Ci[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ci[a][r] = T.bdmC[i][a][r];
+    double GY[2][6];
+#pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+      double y0, y1;
+      if (MODE == 1) {
+        y0 = 0.0; y1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          y0 += Ci[0][r] * W[sb_sym21(r, s2)];
+          y1 += Ci[1][r] * W[sb_sym21(r, s2)];
+        }
+      } else {                       /* W = identity: plain BDM mass matrix */
+        y0 = Ci[0][s2]; y1 = Ci[1][s2];
+      }
+      GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
+      GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
+    }
+    double* row = st + r3 * 18;
+    double Fi = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      double v = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2)
+        v = fma(GY[1][s2], T.bdmC[m][1][s2], fma(GY[0][s2], T.bdmC[m][0][s2], v));
+      Fi += v * fl[m];
+      row[m] = v;
+    }
+    if (MODE != 2) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const double dv = divsign * T.Dhat[i][l];
+        Fi += dv * sl[l];
+        if (MODE == 1) {
+          double d = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) d = fma(Ci[1][r], V[1][r][l], fma(Ci[0][r], V[0][r][l], d));
+          d *= g.iad;
+          row[12 + l] = dv + d;
+          row[15 + l] = d;
+        } else {
+          row[12 + l] = dv;
+        }
+      }
+    }
+    if (MODE == 1 && grp < 3) Fi -= jf * T.trI[r3];     /* base_w jump: facet dofs */
+    st[54 + r3] = Fi;
+  }
+}
+
+/* Warp-cooperative flush of one staged group: cell after cell, lane = entry.
+ * NK: slots per row; klo/khi: emitted slot range of a cell given its inside flag;
+ * facet >= 0: group of facet `facet` (its (facet, facet) entries and residual rows
+ * are shared with the neighbour -> atomic adds onto zeroed slots).              */
+template <int NK>
+SB_HD void sb_flush_group(const SbWarpMeta& meta, const double* __restrict__ stage0,
+                          const uint8_t* __restrict__ patk0, int patk_pattern_stride,
+                          int patk_row0, int grp5, int facet, int klo_in, int khi_in,
+                          int klo_out, int khi_out, double* __restrict__ vals,
+                          double* __restrict__ b, int lane) {
+  constexpr int NE = 3 * NK + 3;
+  constexpr int NIT = (NE + 31) / 32;
+  /* Everything that depends only on the lane is hoisted out of the cell loop: slot
+     e = lane + 32 it -> row r, emission slot k, rank-table offset, whether the slot is
+     emitted by inside / outside cells, whether it is a shared (atomic) slot.          */
+  int soff[NIT], rsel[NIT];
+  bool on_in[NIT], on_out[NIT], shared_slot[NIT], is_res[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int e = lane + 32 * it;
+    const bool ent = e < 3 * NK;
+    const int r = ent ? e / NK : (e < NE ? e - 3 * NK : 0);
+    const int k = ent ? e - r * NK : 0;
+    rsel[it] = r;
+    soff[it] = ent ? r * 32 + k : 0;
+    is_res[it] = !ent && e < NE;
+    on_in[it] = ent && vals != nullptr && k >= klo_in && k < khi_in;
+    on_out[it] = ent && vals != nullptr && k >= klo_out && k < khi_out;
+    shared_slot[it] = facet >= 0 && k < 9 && k / 3 == facet;
+  }
+  const bool res_on = b != nullptr;
+  const uint8_t* pk0 = patk0 + patk_row0 * 32;
+  /* independent cells: unrolled so that the shared-memory reads of several cells are
+     in flight together */
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const int32_t info = meta.info[i];
+    const bool act = (info & 1) != 0;
+    const bool inside = (info & 2) != 0;
+    const int64_t rl = meta.rl[grp5][i];
+    double* base = vals + meta.rb[grp5][i];
+    double* bbase = b + meta.d0[grp5][i];
+    const uint8_t* pk = pk0 + (info >> 8) * patk_pattern_stride;
+    const double* src = stage0 + i * SB_STAGE_STRIDE + lane;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const double v = src[32 * it];
+      if (!is_res[it]) {
+        const int rank = pk[soff[it]];
+        double* dst = base + (rsel[it] * rl + rank);
+        const bool on = act && (inside ? on_in[it] : on_out[it]);
+#ifdef SB_EXP_NOATOMIC
+        if (on) *dst = v;
+#else
+        if (on && shared_slot[it]) SB_ATOMIC_ADD(dst, v);
+        if (on && !shared_slot[it]) *dst = v;
+#endif
+      } else {
+        double* dst = bbase + rsel[it];
+        const bool on = act && res_on;
+        if (on && facet >= 0) SB_ATOMIC_ADD(dst, v);
+        if (on && facet < 0) *dst = v;
+      }
+    }
   }
 }
 

@@ -515,12 +515,181 @@ k_rows_fast(PlanDev pl, StateDev st, double* vals, double* b) {
   }
 }
 
+/* Staged variant of k_rows_fast (pdd_device.cuh, "Staged fast path"): threads stage
+ * one entity group at a time in shared memory, the warp flushes it with lane = entry.
+ * Needs the rank tables in shared memory (pl.stage_patk); no thread leaves before the
+ * last flush.                                                                     */
+template <int NB, int PS>
+__global__ void __launch_bounds__(SB_TILE, SB_MB_ROWS)
+k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
+  /* dynamic shared memory (95 KB > the 48 KB static limit): staging | meta | patk */
+#ifdef SB_EMUL_BUILD
+  unsigned char* s_dyn = emul::dyn_smem();
+#else
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+#endif
+  typedef double StageRow[32 * SB_STAGE_STRIDE];
+  typedef uint8_t PatkTab[15][32];
+  StageRow* s_stage = reinterpret_cast<StageRow*>(s_dyn);
+  SbWarpMeta* s_meta = reinterpret_cast<SbWarpMeta*>(s_dyn + sizeof(StageRow) * (SB_TILE / 32));
+  PatkTab* s_patk = reinterpret_cast<PatkTab*>(s_dyn + (sizeof(StageRow) + sizeof(SbWarpMeta))
+                                                * (SB_TILE / 32));
+  const int L = pl.L;
+  {
+    const int nw = (int)pl.n_patterns * 15 * 8;            /* 32-bit words */
+    for (int w = threadIdx.x; w < nw; w += SB_TILE) {
+      const int q = w / 120, rem = w % 120, r = rem / 8, e = rem % 8;
+      reinterpret_cast<uint32_t*>(&s_patk[q][r][0])[e] =
+          reinterpret_cast<const uint32_t*>(pl.patk + ((int64_t)q * L + 15 * PS + r) * 32)[e];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nc = pl.n_cells;
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  const bool active = (c < nc) && (pl.cell_special[c < nc ? c : 0] < 0);
+  const int64_t cc = active ? c : 0;                 /* inactive lanes read cell 0, emit nothing */
+  SbWarpMeta& meta = s_meta[warp];
+  double* stg = &s_stage[warp][lane * SB_STAGE_STRIDE];
+  const int32_t* dofs = pl.cell_dofs + cc * L;
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[cc] * SB_TAG_STRIDE;
+  constexpr int k = PS > 0 ? PS - 1 : 0;
+  const bool inside = (PS == 0) ? true : (tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0);
+#pragma unroll
+  for (int e = 0; e < 5; ++e) {
+    meta.rb[e][lane] = pl.rowbase[(int64_t)(5 * PS + e) * nc + cc];
+    meta.rl[e][lane] = pl.rowlen[(int64_t)(5 * PS + e) * nc + cc];
+    meta.d0[e][lane] = dofs[15 * PS + (e == 0 ? 0 : 3 * e)];
+  }
+  meta.info[lane] = (active ? 1 : 0) | (inside ? 2 : 0) | ((int32_t)pl.cell_pattern[cc] << 8);
+  const SbCellGeom g = sb_geom(pl.cell_vertices + cc * 6);
+  double fl[12], sl[3];
+#pragma unroll
+  for (int m = 0; m < 12; ++m) fl[m] = st.u[dofs[sb_lbdm(PS, m)]];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sl[i] = st.u[dofs[sb_ldg(PS, i)]];
+  double W[21];
+  double V[2][6][3];
+  double jumpf[3] = {0.0, 0.0, 0.0};
+  /* ---- group 0: DG rows ---------------------------------------------------- */
+  if (PS == 0) {
+    double mR[SB_NR] = {0.0, 0.0, 0.0};
+    double mX[1 + SB_MAX_BANDS][SB_NRX];
+#pragma unroll
+    for (int q = 0; q < 1 + SB_MAX_BANDS; ++q)
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < SB_MAX_BANDS; ++kk) {
+      if (kk >= pl.nb) break;
+      const double* o = momA_ptr(pl, kk, cc);
+#pragma unroll
+      for (int t = 0; t < SB_NRX; ++t) {
+        const double v = o[(int64_t)(SB_NMC + SB_NQ + t) * nc];
+        mX[0][t] += v;
+        if (kk < NB) mX[1 + kk][t] = v;
+      }
+#pragma unroll
+      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc];
+    }
+    mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
+    if (active)
+      sb_stage_scalar_rows<0, 1 + NB>(c_T, c_M, g, true, fl, sl, -g.adet, mR, &mX[0][0], stg);
+  } else {
+    double mG[SB_NG];
+    if (inside) {
+      const double* og = momG_ptr(pl, k, cc);
+#pragma unroll
+      for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = og[(int64_t)t * nc];
+    }
+    const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
+    if (active)
+      sb_stage_scalar_rows<PS, 1 + NB>(c_T, c_M, g, inside, fl, sl, coef, mG, mG + 3, stg);
+    if (inside) {
+      /* moments for the flux rows: loaded before the first flush */
+      double mC[SB_NMC], Q[SB_NQ];
+      const double* o = momA_ptr(pl, k, cc);
+#pragma unroll
+      for (int t = 0; t < SB_NMC; ++t) mC[t] = o[(int64_t)t * nc];
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NMC + t) * nc];
+      const double w0 = st.base_w[(int64_t)k * nc + cc];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        if ((pl.cell_jump_mask[cc * 3 + f] >> k) & 1) {
+          const int64_t cn = pl.cell_neighbors[cc * 3 + f];
+          const double ref_out = (f == 1) ? -1.0 : 1.0;
+          jumpf[f] = (st.base_w[(int64_t)k * nc + cn] - w0) * ref_out * g.sdet;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 21; ++e) {
+        double v = 0.0;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) v += c_T.G22u[e][t] * mC[t];
+        W[e] = v;
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < 10; ++t) v += c_T.G21[r][l][t] * Q[a * 10 + t];
+            V[a][r][l] = v;
+          }
+    }
+  }
+  const uint8_t* patk0 = &s_patk[0][0][0];
+  __syncwarp();
+  sb_flush_group<24>(meta, &s_stage[warp][0], patk0, 15 * 32, 0, 0, -1,
+                     0, 12 + 3 * (1 + NB), 12 + 3 * PS, 12 + 3 * PS + 3, vals, b, lane);
+  __syncwarp();
+  /* ---- groups 1..4: facet 0, 1, 2 and interior BDM rows ------------------------- */
+#pragma unroll 1
+  for (int grp = 0; grp < 4; ++grp) {
+#ifdef SB_EXP_NOFACET
+    if (grp < 3) continue;
+#endif
+#ifdef SB_EXP_STOREONLY
+    if (false) {
+#else
+    if (active) {
+#endif
+      if (PS == 0)
+        sb_stage_flux_group<PS, 0>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, stg);
+      else if (inside)
+        sb_stage_flux_group<PS, 1>(c_T, c_M, g, W, V, fl, sl, grp < 3 ? jumpf[grp < 3 ? grp : 0] : 0.0,
+                                   grp, stg);
+      else
+        sb_stage_flux_group<PS, 2>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, stg);
+    }
+    __syncwarp();
+    sb_flush_group<18>(meta, &s_stage[warp][0], patk0, 15 * 32, 3 + 3 * grp, 1 + grp,
+                       grp < 3 ? grp : -1, 0, PS == 0 ? 15 : 18, 0, 12, vals, b, lane);
+    __syncwarp();
+  }
+}
+
 /* launch k_rows_fast<NB, PS> for PS = 0 .. NB */
 template <int NB, int PS>
 struct RowsLauncher {
   static void go(const PlanDev& d, const StateDev& sd, double* vals, double* b, unsigned nblk,
                  cudaStream_t s) {
-    SB_LAUNCH((k_rows_fast<NB, PS>), nblk, SB_TILE, 0, s, d, sd, vals, b);
+    if (d.stage_patk) {
+      const size_t smem = (sizeof(double) * 32 * SB_STAGE_STRIDE + sizeof(SbWarpMeta))
+                          * (SB_TILE / 32) + (size_t)SB_MAX_SMEM_PATTERNS * 15 * 32;
+      static bool attr_set = false;        /* per instantiation */
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_rows_staged<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        attr_set = true;
+      }
+      SB_LAUNCH((k_rows_staged<NB, PS>), nblk, SB_TILE, smem, s, d, sd, vals, b);
+    } else
+      SB_LAUNCH((k_rows_fast<NB, PS>), nblk, SB_TILE, 0, s, d, sd, vals, b);
     RowsLauncher<NB, PS - 1>::go(d, sd, vals, b, nblk, s);
   }
 };
