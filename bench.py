@@ -35,7 +35,7 @@ BYTES_PER_CELL = {'ib': 10396, 'pn': 7424}
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one assembly pass,
 # per cell, from the committed `ncu --set full` capture (profiles/r1_split_kernels_summary.csv,
 # 320 396 IB cells)
-NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): 7.148e9 / 320396.0}
+NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): 7.780e9 / 320396.0}
 
 
 def parse_args():
@@ -317,7 +317,7 @@ def run_b200(args):
                           frac=achieved / peak,
                           traffic=(NCU_DRAM_BYTES_PER_CELL[(args.kind, args.pattern)] * pa.n_cells
                                    if (args.kind, args.pattern) in NCU_DRAM_BYTES_PER_CELL else None),
-                          kernel='assembly pass = k_moments + k_generation + k_rows_fast x P + '
+                          kernel='assembly pass = k_moments + k_generation + k_rows_staged x P + '
                                  'k_rows_special (CUDA events around the pass inside sb_assemble)',
                           kernel_ms=k_ms, stage_ms=stage_ms,
                           algorithmic_bytes=alg_bytes, peak_source=peak_kind),
