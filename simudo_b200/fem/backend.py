@@ -149,7 +149,9 @@ class CudaLCNBackend(object):
         self.lib = _lib.get()
         emul = _lib.is_emulated()
         if device is None:
-            device = 'cpu' if emul else 'cuda:0'
+            # the process' current CUDA device (one process per GPU sets it once)
+            device = 'cpu' if emul else 'cuda:%d' % (
+                torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.device = torch.device(device)
         if not emul and (self.device.type != 'cuda' or not torch.cuda.is_available()):
             raise RuntimeError('simudo_b200 needs a CUDA device (no CPU fallback)')
