@@ -1056,10 +1056,11 @@ SB_HD void sb_flush_group(const SbWarpMeta& meta, const double* __restrict__ sta
   constexpr int NE = 3 * NK + 3;
   constexpr int NIT = (NE + 31) / 32;
   /* Everything that depends only on the lane is hoisted out of the cell loop: slot
-     e = lane + 32 it -> row r, emission slot k, rank-table offset, whether the slot is
-     emitted by inside / outside cells, whether it is a shared (atomic) slot.          */
+     e = lane + 32 it -> row r, emission slot k, rank-table offset, and (as bit `it` of
+     a mask) whether inside / outside cells emit it, whether it is a shared (atomic)
+     slot, whether it is a residual slot.                                             */
   int soff[NIT], rsel[NIT];
-  bool on_in[NIT], on_out[NIT], shared_slot[NIT], is_res[NIT];
+  uint32_t inbits = 0, outbits = 0, shbits = 0, resbits = 0;
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int e = lane + 32 * it;
@@ -1068,21 +1069,20 @@ SB_HD void sb_flush_group(const SbWarpMeta& meta, const double* __restrict__ sta
     const int k = ent ? e - r * NK : 0;
     rsel[it] = r;
     soff[it] = ent ? r * 32 + k : 0;
-    is_res[it] = !ent && e < NE;
-    on_in[it] = ent && vals != nullptr && k >= klo_in && k < khi_in;
-    on_out[it] = ent && vals != nullptr && k >= klo_out && k < khi_out;
-    shared_slot[it] = facet >= 0 && k < 9 && k / 3 == facet;
+    if (ent && vals != nullptr && k >= klo_in && k < khi_in) inbits |= 1u << it;
+    if (ent && vals != nullptr && k >= klo_out && k < khi_out) outbits |= 1u << it;
+    if (facet >= 0 && k < 9 && k / 3 == facet) shbits |= 1u << it;
+    if (!ent && e < NE && b != nullptr) resbits |= 1u << it;
   }
-  const bool res_on = b != nullptr;
   const uint8_t* pk0 = patk0 + patk_row0 * 32;
   /* independent cells: unrolled so that the shared-memory reads of several cells are
      in flight together */
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < 32; ++i) {
     const int32_t info = meta.info[i];
-    const bool act = (info & 1) != 0;
-    const bool inside = (info & 2) != 0;
-    const int64_t rl = meta.rl[grp5][i];
+    const uint32_t onb = (info & 1) ? ((info & 2) ? inbits : outbits) : 0u;
+    const uint32_t resb = (info & 1) ? resbits : 0u;
+    const int rl = meta.rl[grp5][i];
     double* base = vals + meta.rb[grp5][i];
     double* bbase = b + meta.d0[grp5][i];
     const uint8_t* pk = pk0 + (info >> 8) * patk_pattern_stride;
@@ -1090,21 +1090,19 @@ SB_HD void sb_flush_group(const SbWarpMeta& meta, const double* __restrict__ sta
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const double v = src[32 * it];
-      if (!is_res[it]) {
-        const int rank = pk[soff[it]];
-        double* dst = base + (rsel[it] * rl + rank);
-        const bool on = act && (inside ? on_in[it] : on_out[it]);
+      const int off = rsel[it] * rl + (int)pk[soff[it]];      /* < 3 * 255 + 255 */
+      double* dst = base + off;
+      const bool on = (onb >> it) & 1u;
 #ifdef SB_EXP_NOATOMIC
-        if (on) *dst = v;
+      if (on) *dst = v;
 #else
-        if (on && shared_slot[it]) SB_ATOMIC_ADD(dst, v);
-        if (on && !shared_slot[it]) *dst = v;
+      const bool sh = (shbits >> it) & 1u;
+      if (on && sh) SB_ATOMIC_ADD(dst, v);
+      if (on && !sh) *dst = v;
 #endif
-      } else {
-        double* dst = bbase + rsel[it];
-        const bool on = act && res_on;
-        if (on && facet >= 0) SB_ATOMIC_ADD(dst, v);
-        if (on && facet < 0) *dst = v;
+      if ((resb >> it) & 1u) {
+        double* rdst = bbase + rsel[it];
+        if (facet >= 0) SB_ATOMIC_ADD(rdst, v); else *rdst = v;
       }
     }
   }
