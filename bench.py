@@ -140,6 +140,12 @@ def cpu_baseline(kind, cells, steps=2, threads=None):
                        % (kind, n, n, pa.n_cells, pa.N, steps, dt)), dt, pa
 
 
+def workload_name(kind, nx, ny):
+    """Same string on both arms (the driver matches them)."""
+    return ('2D %s cell, synthetic product mesh nx=%d ny=%d per GPU (BASELINE configs[3])'
+            % (kind, nx, ny))
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path.  Real FEniCS cannot be
     installed here, so this is the oracle port on all host cores."""
@@ -167,8 +173,10 @@ def run_reference(args):
                 steps=steps, warmup=args.warmup, ms_per_step=dt * 1e3,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic',
-                config=dict(workload='2D %s cell, synthetic product mesh' % args.kind,
-                            cells=pa.n_cells, dofs=pa.N),
+                config=dict(workload=workload_name(args.kind, args.nx, args.ny),
+                            sample_cells=pa.n_cells, sample_dofs=pa.N,
+                            note='each step = one assembly pass over a bounded sample of the '
+                                 'workload (same mesh family, state and physics)'),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=int(threads), kind='port',
                                   sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -303,8 +311,8 @@ def run_b200(args):
             warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True,
             scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
             config=dict(
-                workload='2D %s cell, synthetic %dx%d-point product mesh per GPU '
-                         '(BASELINE configs[3])' % (args.kind, len(np.unique(pa.mesh.coordinates[:, 0])), args.ny),
+                workload=workload_name(args.kind, args.nx, args.ny),
+                x_points=int(len(np.unique(pa.mesh.coordinates[:, 0]))),
                 cells_per_gpu=pa.n_cells, dofs_per_gpu=pa.N, nnz_per_gpu=pa.csr.nnz,
                 sub_problems=pa.P, local_dofs=pa.L, optical_fields=pa.model.n_fields,
                 pattern=('structural non-zeros of the dolfin cell blocks' if pa.pattern == 'structural'
