@@ -928,7 +928,8 @@ SB_HD void sb_rows_scalar_fast(const SbTables& T, const sb_model& M, const SbFas
  * NK = 18 for the BDM groups (k: 0..11 BDM, 12..14 DG(PS), 15..17 DG(0)) --
  * the same order as the packed rank table patk.
  * ========================================================================= */
-#define SB_STAGE_STRIDE 77          /* doubles per lane: 3 * 24 + 3 used, odd stride */
+#define SB_STAGE_STRIDE 78          /* doubles per lane: 1 + 3 * 24 + 3 used; 78 * 8 B keeps every
+                                       lane's base 16-byte aligned for the bulk copies */
 
 /* per-warp flush metadata, one entry per lane (cell) and group */
 struct SbWarpMeta {
@@ -938,11 +939,48 @@ struct SbWarpMeta {
   int32_t info[32];                 /* bit 0 active, bit 1 inside, bits 8.. pattern */
 };
 
+/* Rows owned by one cell (its DG rows, its interior BDM rows) are a contiguous run
+ * of 3 * rl values that this thread alone writes.  They are staged in *rank* order
+ * (final memory order) at stg[phase + ...], phase = parity of the run's first index,
+ * so that shared and global addresses have the same 16-byte phase, and leave the SM
+ * as one asynchronous bulk copy (cp.async.bulk shared -> global, the 1-D TMA path);
+ * an odd start or an odd length contributes one scalar store at that end.                          */
+SB_HD void sb_bulk_store_owned(double* gdst, const double* stg, int phase, int n) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const double* s0 = stg + phase;
+  const int head = phase;                         /* one scalar up to the 16-byte boundary */
+  const int nb = (n - head) & ~1;                 /* bulk part: whole 16-byte units        */
+  if (head) gdst[0] = s0[0];
+  if (head + nb < n) gdst[n - 1] = s0[n - 1];
+  const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s0 + head);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst + head), "r"(saddr), "r"(nb * 8) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+  for (int e = 0; e < n; ++e) gdst[e] = stg[phase + e];
+#endif
+}
+/* the staging area may be rewritten once the bulk engine has read it */
+SB_HD void sb_bulk_wait_read() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+
 /* DG1 rows of sub-problem PS into the staging area (see sb_rows_scalar) */
+/* pk != nullptr: rank-ordered staging for the bulk copy (pk = the cell's rank rows of
+ * this group, rl = row length, st already offset by the phase); the residual then goes
+ * straight to bdst (global, may be null) */
 template <int PS, int NQ>
 SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCellGeom& g,
                                 bool inside, const double* fl, const double* sl, double coef,
-                                const double* mom1, const double* momJ, double* st) {
+                                const double* mom1, const double* momJ, double* st,
+                                const uint8_t* pk = nullptr, int rl = 24, double* bdst = nullptr) {
+#define SB_DG_SLOT(i, k) (pk ? (i) * rl + (int)pk[(i) * 32 + (k)] : (i) * 24 + (k))
+  if (pk && !inside) {               /* not emitted entries of owned rows stay zero */
+    for (int e = 0; e < 3 * rl; ++e) st[e] = 0.0;
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     double Fi = 0.0;
@@ -951,7 +989,7 @@ SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCe
       for (int m = 0; m < 12; ++m) {
         const double dv = g.sdet * T.Dhat[m][i];
         Fi += dv * fl[m];
-        st[i * 24 + m] = dv;
+        st[SB_DG_SLOT(i, m)] = dv;
       }
 #pragma unroll
       for (int t = 0; t < 3; ++t) Fi += coef * T.G1[i][t] * mom1[t];
@@ -962,7 +1000,7 @@ SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCe
           double v = 0.0;
 #pragma unroll
           for (int t = 0; t < 6; ++t) v += T.G11[i][l][t] * momJ[6 * q + t];
-          st[i * 24 + 12 + 3 * q + l] = coef * v;
+          st[SB_DG_SLOT(i, 12 + 3 * q + l)] = coef * v;
         }
     } else {
       const double c1 = M.ext_w_coef * g.adet;
@@ -970,11 +1008,12 @@ SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCe
       for (int l = 0; l < 3; ++l) {
         const double v = c1 * T.M1[i][l];
         Fi += v * sl[l];
-        st[i * 24 + 12 + 3 * PS + l] = v;
+        st[SB_DG_SLOT(i, 12 + 3 * PS + l)] = v;
       }
     }
-    st[72 + i] = Fi;
+    if (pk) { if (bdst) bdst[i] = Fi; } else st[72 + i] = Fi;
   }
+#undef SB_DG_SLOT
 }
 
 /* the three BDM rows of entity group grp (facet 0, 1, 2, interior) into the staging
@@ -982,9 +1021,13 @@ SB_HD void sb_stage_scalar_rows(const SbTables& T, const sb_model& M, const SbCe
 template <int PS, int MODE>
 SB_HD void sb_stage_flux_group(const SbTables& T, const sb_model& M, const SbCellGeom& g,
                                const double* W, const double (*V)[6][3], const double* fl,
-                               const double* sl, double jf, int grp, double* st) {
+                               const double* sl, double jf, int grp, double* st,
+                               const uint8_t* pk = nullptr, int rl = 18, double* bdst = nullptr) {
   const double sc = (MODE == 2 ? M.ext_j_coef : 1.0) * g.iad;
   const double divsign = (MODE == 0) ? -g.sdet : g.sdet;
+  if (pk && MODE == 2) {             /* not emitted entries of owned rows stay zero */
+    for (int e = 0; e < 3 * rl; ++e) st[e] = 0.0;
+  }
 #pragma unroll 1
   for (int r3 = 0; r3 < 3; ++r3) {
     const int i = 3 * grp + r3;
@@ -1010,7 +1053,9 @@ SB_HD void sb_stage_flux_group(const SbTables& T, const sb_model& M, const SbCel
       GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
       GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
     }
-    double* row = st + r3 * 18;
+    double* row = st + (pk ? r3 * rl : r3 * 18);
+    const uint8_t* prow = pk ? pk + r3 * 32 : nullptr;
+#define SB_BDM_SLOT(k) (prow ? (int)prow[(k)] : (k))
     double Fi = 0.0;
 #pragma unroll
     for (int m = 0; m < 12; ++m) {
@@ -1019,7 +1064,7 @@ SB_HD void sb_stage_flux_group(const SbTables& T, const sb_model& M, const SbCel
       for (int s2 = 0; s2 < 6; ++s2)
         v = fma(GY[1][s2], T.bdmC[m][1][s2], fma(GY[0][s2], T.bdmC[m][0][s2], v));
       Fi += v * fl[m];
-      row[m] = v;
+      row[SB_BDM_SLOT(m)] = v;
     }
     if (MODE != 2) {
 #pragma unroll
@@ -1031,15 +1076,16 @@ SB_HD void sb_stage_flux_group(const SbTables& T, const sb_model& M, const SbCel
 #pragma unroll
           for (int r = 0; r < 6; ++r) d = fma(Ci[1][r], V[1][r][l], fma(Ci[0][r], V[0][r][l], d));
           d *= g.iad;
-          row[12 + l] = dv + d;
-          row[15 + l] = d;
+          row[SB_BDM_SLOT(12 + l)] = dv + d;
+          row[SB_BDM_SLOT(15 + l)] = d;
         } else {
-          row[12 + l] = dv;
+          row[SB_BDM_SLOT(12 + l)] = dv;
         }
       }
     }
     if (MODE == 1 && grp < 3) Fi -= jf * T.trI[r3];     /* base_w jump: facet dofs */
-    st[54 + r3] = Fi;
+    if (pk) { if (bdst) bdst[r3] = Fi; } else st[54 + r3] = Fi;
+#undef SB_BDM_SLOT
   }
 }
 

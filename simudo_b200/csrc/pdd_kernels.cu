@@ -58,6 +58,7 @@ struct PlanDev {
   const int32_t* cell_pattern;   /* [n_cells]                                */
   int64_t n_patterns;
   int stage_patk;                /* rank tables fit the shared-memory staging area */
+  int owned_bulk;                /* DG / interior rows have the structural lengths: bulk copy */
   const uint8_t* patk;           /* [n_patterns][L][32] packed emission-order ranks */
   const int32_t* sp_cells;       /* [n_special] cells with Dirichlet / natural-BC rows */
   const int64_t* rowbase;        /* [5P][n_cells] vals offset of the first row of each
@@ -562,6 +563,11 @@ k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
     meta.d0[e][lane] = dofs[15 * PS + (e == 0 ? 0 : 3 * e)];
   }
   meta.info[lane] = (active ? 1 : 0) | (inside ? 2 : 0) | ((int32_t)pl.cell_pattern[cc] << 8);
+  /* owned rows: bulk copy needs the structural row lengths and a Jacobian to write */
+  const bool bulk = pl.owned_bulk && vals != nullptr;
+  const int64_t rb0 = meta.rb[0][lane], rb4 = meta.rb[4][lane];
+  const int ph0 = (int)(rb0 & 1), ph4 = (int)(rb4 & 1);
+  const uint8_t* pk_own = &s_patk[pl.cell_pattern[cc]][0][0];      /* rows 0..2 DG, 12..14 interior */
   const SbCellGeom g = sb_geom(pl.cell_vertices + cc * 6);
   double fl[12], sl[3];
 #pragma unroll
@@ -593,8 +599,14 @@ k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
       for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc];
     }
     mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
-    if (active)
-      sb_stage_scalar_rows<0, 1 + NB>(c_T, c_M, g, true, fl, sl, -g.adet, mR, &mX[0][0], stg);
+    if (active) {
+      if (bulk)
+        sb_stage_scalar_rows<0, 1 + NB>(c_T, c_M, g, true, fl, sl, -g.adet, mR, &mX[0][0],
+                                        stg + ph0, pk_own, 12 + 3 * (1 + NB),
+                                        b ? b + dofs[0] : nullptr);
+      else
+        sb_stage_scalar_rows<0, 1 + NB>(c_T, c_M, g, true, fl, sl, -g.adet, mR, &mX[0][0], stg);
+    }
   } else {
     double mG[SB_NG];
     if (inside) {
@@ -603,8 +615,14 @@ k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
       for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = og[(int64_t)t * nc];
     }
     const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
-    if (active)
-      sb_stage_scalar_rows<PS, 1 + NB>(c_T, c_M, g, inside, fl, sl, coef, mG, mG + 3, stg);
+    if (active) {
+      if (bulk)
+        sb_stage_scalar_rows<PS, 1 + NB>(c_T, c_M, g, inside, fl, sl, coef, mG, mG + 3,
+                                         stg + ph0, pk_own, 12 + 3 * (1 + NB),
+                                         b ? b + dofs[15 * PS] : nullptr);
+      else
+        sb_stage_scalar_rows<PS, 1 + NB>(c_T, c_M, g, inside, fl, sl, coef, mG, mG + 3, stg);
+    }
     if (inside) {
       /* moments for the flux rows: loaded before the first flush */
       double mC[SB_NMC], Q[SB_NQ];
@@ -643,33 +661,49 @@ k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
     }
   }
   const uint8_t* patk0 = &s_patk[0][0][0];
-  __syncwarp();
-  sb_flush_group<24>(meta, &s_stage[warp][0], patk0, 15 * 32, 0, 0, -1,
-                     0, 12 + 3 * (1 + NB), 12 + 3 * PS, 12 + 3 * PS + 3, vals, b, lane);
-  __syncwarp();
+  if (bulk) {
+    if (active) sb_bulk_store_owned(vals + rb0, stg, ph0, 3 * (12 + 3 * (1 + NB)));
+    sb_bulk_wait_read();
+  } else {
+    __syncwarp();
+    sb_flush_group<24>(meta, &s_stage[warp][0], patk0, 15 * 32, 0, 0, -1,
+                       0, 12 + 3 * (1 + NB), 12 + 3 * PS, 12 + 3 * PS + 3, vals, b, lane);
+    __syncwarp();
+  }
   /* ---- groups 1..4: facet 0, 1, 2 and interior BDM rows ------------------------- */
 #pragma unroll 1
   for (int grp = 0; grp < 4; ++grp) {
 #ifdef SB_EXP_NOFACET
     if (grp < 3) continue;
 #endif
+    /* the interior rows (grp 3) are owned: rank-ordered staging + bulk copy */
+    const bool own = bulk && grp == 3;
+    double* sdst = own ? stg + ph4 : stg;
+    const uint8_t* pkg = own ? pk_own + 12 * 32 : nullptr;
+    double* bdst = (own && b) ? b + dofs[15 * PS + 12] : nullptr;
+    constexpr int rl4 = PS == 0 ? 15 : 18;
 #ifdef SB_EXP_STOREONLY
     if (false) {
 #else
     if (active) {
 #endif
       if (PS == 0)
-        sb_stage_flux_group<PS, 0>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, stg);
+        sb_stage_flux_group<PS, 0>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, sdst, pkg, rl4, bdst);
       else if (inside)
         sb_stage_flux_group<PS, 1>(c_T, c_M, g, W, V, fl, sl, grp < 3 ? jumpf[grp < 3 ? grp : 0] : 0.0,
-                                   grp, stg);
+                                   grp, sdst, pkg, rl4, bdst);
       else
-        sb_stage_flux_group<PS, 2>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, stg);
+        sb_stage_flux_group<PS, 2>(c_T, c_M, g, W, V, fl, sl, 0.0, grp, sdst, pkg, rl4, bdst);
     }
-    __syncwarp();
-    sb_flush_group<18>(meta, &s_stage[warp][0], patk0, 15 * 32, 3 + 3 * grp, 1 + grp,
-                       grp < 3 ? grp : -1, 0, PS == 0 ? 15 : 18, 0, 12, vals, b, lane);
-    __syncwarp();
+    if (own) {
+      if (active) sb_bulk_store_owned(vals + rb4, stg, ph4, 3 * rl4);
+      sb_bulk_wait_read();
+    } else {
+      __syncwarp();
+      sb_flush_group<18>(meta, &s_stage[warp][0], patk0, 15 * 32, 3 + 3 * grp, 1 + grp,
+                         grp < 3 ? grp : -1, 0, PS == 0 ? 15 : 18, 0, 12, vals, b, lane);
+      __syncwarp();
+    }
   }
 }
 
@@ -1035,6 +1069,13 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
       }
       UP(rowbase, rbase.data(), rbase.size());
       UP(rowlen, rlen.data(), rlen.size());
+      /* owned rows (DG, interior BDM) of the structural layout: fixed lengths, even */
+      bool bulk = true;
+      for (int p = 0; p < Pn && bulk; ++p)
+        for (int64_t c = 0; c < nc; ++c)
+          if (rlen[(size_t)(5 * p) * nc + c] != 12 + 3 * Pn ||
+              rlen[(size_t)(5 * p + 4) * nc + c] != (p == 0 ? 15 : 18)) { bulk = false; break; }
+      d.owned_bulk = bulk && !getenv("SIMUDO_B200_NO_BULK_STORE");
     }
     std::vector<int32_t> spc;
     for (int64_t c = 0; c < nc; ++c) if (special[c] >= 0) spc.push_back((int32_t)c);

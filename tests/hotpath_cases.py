@@ -332,3 +332,20 @@ def lcn_iteration_parity():
         for k in ('b_norm', 'du_norm', 'rel_du_norm', 'combined_du_norm'):
             assert abs(m1[k] - m0[k]) <= 1e-9 * abs(m0[k]), (k, m0[k], m1[k])
         assert m1['has_nans'] == m0['has_nans']
+
+
+def bulk_store_matches_entry_flush():
+    """Owned rows leave the SM through cp.async.bulk (1-D TMA) copies of rank-ordered
+    staging; the library's debugging knob forces the lane = entry flush instead.  Both
+    must give the same bits (pn: odd run lengths, ib: even)."""
+    import os
+    for maker, nx, ny in ((syn.ib_problem, 9, 4), (syn.pn_problem, 8, 3)):
+        pa = maker(nx=nx, ny=ny)
+        st = syn.synthetic_state(pa)
+        v0, b0 = run_plan(AssemblyPlan(pa), st)
+        os.environ['SIMUDO_B200_NO_BULK_STORE'] = '1'
+        try:
+            v1, b1 = run_plan(AssemblyPlan(pa), st)
+        finally:
+            del os.environ['SIMUDO_B200_NO_BULK_STORE']
+        assert torch.equal(v0, v1) and torch.equal(b0, b1)

@@ -86,3 +86,7 @@ def test_optics_parity_emulated(emulated_lib):
 
 def test_lcn_iteration_parity_emulated(emulated_lib):
     hc.lcn_iteration_parity()
+
+
+def test_bulk_store_matches_entry_flush_emulated(emulated_lib):
+    hc.bulk_store_matches_entry_flush()

@@ -96,3 +96,7 @@ def test_optics_parity():
 
 def test_lcn_iteration_parity():
     hc.lcn_iteration_parity()
+
+
+def test_bulk_store_matches_entry_flush():
+    hc.bulk_store_matches_entry_flush()
