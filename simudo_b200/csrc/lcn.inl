@@ -98,9 +98,9 @@ __global__ void k_lcn_iteration(int64_t nc, const double* cell_vertices, const i
     }
   }
 #ifdef SB_EMUL_BUILD
-  if (c < nc) {
-    out[0] = fmax(out[0], bmax); out[1] = fmax(out[1], dmax); out[2] += rsum;
-    out[3] = fmax(out[3], cmax); out[4] = fmax(out[4], nanf); out[5] += cnt;
+  if (c < nc) {                      /* emulated threads run concurrently: atomics */
+    atomic_max_pos(out + 0, bmax); atomic_max_pos(out + 1, dmax); atomicAdd(out + 2, rsum);
+    atomic_max_pos(out + 3, cmax); atomic_max_pos(out + 4, nanf); atomicAdd(out + 5, cnt);
   }
 #else
   /* warp reduce, then one atomic per warp */

@@ -169,6 +169,37 @@ SB_HD void sb_exp_pair(double x, double& ep, double& em) {
   em = (E - ro) * sb_pow2i(-k);
 }
 
+/* expm1(x) with the same reduction: expm1(x) = 2^k expm1(r) + (2^k - 1), where
+ * expm1(r) = r O(r^2) + r^2 E1(r^2) has no cancellation (E = 1 + z E1); for k = 0 this
+ * is the series itself, so the value near thermal equilibrium (x -> 0) keeps full
+ * relative accuracy; branch-free.  x is clamped to [-700, 700].                   */
+SB_HD double sb_expm1(double x) {
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 1.4426950408889634074, magic);
+#ifdef __CUDA_ARCH__
+  const int k = __double2loint(t);
+#else
+  uint64_t tb;
+  memcpy(&tb, &t, sizeof tb);
+  const int k = (int)(uint32_t)(tb & 0xFFFFFFFFu);
+#endif
+  const double kf = t - magic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double z = r * r;
+  double E1 = 1.0 / 479001600.0, O = 1.0 / 6227020800.0;
+  E1 = fma(E1, z, 1.0 / 3628800.0);  O = fma(O, z, 1.0 / 39916800.0);
+  E1 = fma(E1, z, 1.0 / 40320.0);    O = fma(O, z, 1.0 / 362880.0);
+  E1 = fma(E1, z, 1.0 / 720.0);      O = fma(O, z, 1.0 / 5040.0);
+  E1 = fma(E1, z, 1.0 / 24.0);       O = fma(O, z, 1.0 / 120.0);
+  E1 = fma(E1, z, 0.5);              O = fma(O, z, 1.0 / 6.0);
+  O = fma(O, z, 1.0);
+  const double em_r = fma(r, O, z * E1);
+  const double s = sb_pow2i(k);
+  return fma(s, em_r, s - 1.0);
+}
+
 /* Pointwise band quantities at chi = e phi + w (band statistics
  * poisson_drift_diffusion1.py1:170-245):
  *   su = s u / eps, dsu = d(su)/dchi, c = dd_scale / (mu u), dc = dc/dchi   */
@@ -311,6 +342,10 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBand
  * ------------------------------------------------------------------------- */
 struct SbBandsAtPoint {
   double u[SB_MAX_BANDS], du[SB_MAX_BANDS], w[SB_MAX_BANDS], u0[SB_MAX_BANDS];
+  /* expm1(s_R (w_R - w_I) / kT) for every band R against the trap band `trap`
+     (-1: none): shared by the Shockley-Read and the radiative IB process of a pair */
+  double em[SB_MAX_BANDS];
+  int trap;
 };
 
 SB_HD int sb_gen_sign(const sb_model& M, int p, int k) {
@@ -332,7 +367,7 @@ SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff,
   const double F = same ? (N_I - B.u[IB]) : B.u[IB];
   const double dF = same ? -B.du[IB] : B.du[IB];
   const double x = sR * (B.w[RB] - B.w[IB]) * beta;
-  const double em = expm1(x), ex = em + 1.0;
+  const double em = (B.trap == IB) ? B.em[RB] : sb_expm1(x), ex = em + 1.0;
   g += coeff * em * B.u[RB] * F;
   dphi += coeff * em * (B.du[RB] * F + B.u[RB] * dF);
   dw[RB] += coeff * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
@@ -372,7 +407,7 @@ SB_HD void sb_process_point(const sb_model& M, const double* tp, int p,
       g = S;
       if (M.proc_radiative[p]) {
         const double x = beta * (B.w[dst] - B.w[src]);
-        const double em = expm1(x), ex = em + 1.0;
+        const double em = sb_expm1(x), ex = em + 1.0;
         g -= pp[SB_TPP_P0] * em;
         dw[dst] -= pp[SB_TPP_P0] * beta * ex;
         dw[src] += pp[SB_TPP_P0] * beta * ex;
@@ -412,7 +447,14 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
     for (int t = 0; t < 9 + 6 * NB; ++t) mG[k][t] = 0.0;
   SbBandK K[NB > 0 ? NB : 1];
   bool need_u0 = false;
-  for (int p = 0; p < M.n_procs; ++p) need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
+  int trap = -1;
+  for (int p = 0; p < M.n_procs; ++p) {
+    need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
+    if (trap < 0 && (M.proc_kind[p] == SB_PROC_SR_TRAP ||
+                     (M.proc_kind[p] == SB_PROC_RAD_IB && M.proc_radiative[p])))
+      trap = M.proc_trap[p];
+  }
+  const double beta_pt = 1.0 / tp[SB_TP_KT];
 #pragma unroll
   for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
 #pragma unroll 1
@@ -433,6 +475,13 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
       sb_band_u(K[l], phi + B.w[l], B.u[l], B.du[l]);
       B.u0[l] = 0.0;
       if (need_u0) { double d_; sb_band_u(K[l], phi_te, B.u0[l], d_); }
+    }
+    B.trap = trap;
+    if (trap >= 0) {
+#pragma unroll
+      for (int l = 0; l < NB; ++l)
+        B.em[l] = (l == trap) ? 0.0
+                              : sb_expm1((double)M.band_sign[l] * (B.w[l] - B.w[trap]) * beta_pt);
     }
     double phi_clip[SB_MAX_FIELDS];
     for (int f = 0; f < M.n_fields; ++f) {
