@@ -19,6 +19,13 @@ everything here is evaluated point by point in physical space: physical
 gradients ``J^-T grad N``, alpha and grad alpha at the quadrature points,
 outward unit normals from the facet geometry.
 
+Shared with the product are only elementary tables: the P2 Lagrange basis and its
+gradients and the published quadrature point sets
+(``simudo_b200.fem.reference_element`` / ``cg2.p2_gradients``), themselves pinned in
+tests/test_optics.py (exactness of the degree-6 rule, finite-difference check of the
+gradients).  Mass / MSORTE matrices and right-hand sides are assembled here from
+scratch.
+
 Parity status: unpinned against dolfin (FEniCS is not installable here); pinned
 against the analytic Beer-Lambert solution exp(-alpha x), which the second-order
 form reproduces to discretisation error (tests/test_optics.py).
