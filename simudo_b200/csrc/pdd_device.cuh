@@ -142,31 +142,72 @@ SB_HD double sb_pow2i(int k) {
   return d;
 #endif
 }
-SB_HD void sb_exp_pair(double x, double& ep, double& em) {
+/* Coefficients of the exp kernels.  On the device they sit in the constant bank so
+ * that every DFMA of the chains takes its coefficient as a c[bank][offset] operand;
+ * as inline literals each 64-bit coefficient cost two extra move instructions per
+ * use (the kernels run at the register limit, ptxas rematerialises them), which
+ * tripled the instruction count of the chains.                                   */
+#define SB_EXPC_VALUES { \
+  1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10, \
+  1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, \
+  1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0 }
+#if defined(__CUDACC__) && !defined(SB_EMUL_BUILD)
+static __constant__ double c_sb_expc[14] = SB_EXPC_VALUES;
+#endif
+static const double h_sb_expc[14] = SB_EXPC_VALUES;
+#ifdef __CUDA_ARCH__
+#define SB_EXPC(i) c_sb_expc[i]
+#else
+#define SB_EXPC(i) h_sb_expc[i]
+#endif
+
+/* range reduction shared by the exp kernels: x (clamped to +-700) = k ln2 + r */
+SB_HD double sb_exp_reduce(double x, int& k) {
   x = fmin(fmax(x, -700.0), 700.0);
   const double magic = 6755399441055744.0;            /* 1.5 * 2^52 */
-  const double t = fma(x, 1.4426950408889634074, magic);
+  const double t = fma(x, SB_EXPC(0), magic);
 #ifdef __CUDA_ARCH__
-  const int k = __double2loint(t);
+  k = __double2loint(t);
 #else
   uint64_t tb;
   memcpy(&tb, &t, sizeof tb);
-  const int k = (int)(uint32_t)(tb & 0xFFFFFFFFu);
+  k = (int)(uint32_t)(tb & 0xFFFFFFFFu);
 #endif
   const double kf = t - magic;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
+  double r = fma(kf, SB_EXPC(1), x);
+  r = fma(kf, SB_EXPC(2), r);
+  return r;
+}
+
+SB_HD void sb_exp_pair(double x, double& ep, double& em) {
+  int k;
+  const double r = sb_exp_reduce(x, k);
   const double z = r * r;
-  double E = 1.0 / 479001600.0, O = 1.0 / 6227020800.0;
-  E = fma(E, z, 1.0 / 3628800.0);  O = fma(O, z, 1.0 / 39916800.0);
-  E = fma(E, z, 1.0 / 40320.0);    O = fma(O, z, 1.0 / 362880.0);
-  E = fma(E, z, 1.0 / 720.0);      O = fma(O, z, 1.0 / 5040.0);
-  E = fma(E, z, 1.0 / 24.0);       O = fma(O, z, 1.0 / 120.0);
-  E = fma(E, z, 0.5);              O = fma(O, z, 1.0 / 6.0);
-  E = fma(E, z, 1.0);              O = fma(O, z, 1.0);
+  double E = SB_EXPC(3), O = SB_EXPC(8);
+  E = fma(E, z, SB_EXPC(4));  O = fma(O, z, SB_EXPC(9));
+  E = fma(E, z, SB_EXPC(5));  O = fma(O, z, SB_EXPC(10));
+  E = fma(E, z, SB_EXPC(6));  O = fma(O, z, SB_EXPC(11));
+  E = fma(E, z, SB_EXPC(7));  O = fma(O, z, SB_EXPC(12));
+  E = fma(E, z, 0.5);         O = fma(O, z, SB_EXPC(13));
+  E = fma(E, z, 1.0);         O = fma(O, z, 1.0);
   const double ro = r * O;
   ep = (E + ro) * sb_pow2i(k);
   em = (E - ro) * sb_pow2i(-k);
+}
+
+/* exp(x) alone, same chains */
+SB_HD double sb_exp(double x) {
+  int k;
+  const double r = sb_exp_reduce(x, k);
+  const double z = r * r;
+  double E = SB_EXPC(3), O = SB_EXPC(8);
+  E = fma(E, z, SB_EXPC(4));  O = fma(O, z, SB_EXPC(9));
+  E = fma(E, z, SB_EXPC(5));  O = fma(O, z, SB_EXPC(10));
+  E = fma(E, z, SB_EXPC(6));  O = fma(O, z, SB_EXPC(11));
+  E = fma(E, z, SB_EXPC(7));  O = fma(O, z, SB_EXPC(12));
+  E = fma(E, z, 0.5);         O = fma(O, z, SB_EXPC(13));
+  E = fma(E, z, 1.0);         O = fma(O, z, 1.0);
+  return fma(r, O, E) * sb_pow2i(k);
 }
 
 /* expm1(x) with the same reduction: expm1(x) = 2^k expm1(r) + (2^k - 1), where
@@ -174,51 +215,61 @@ SB_HD void sb_exp_pair(double x, double& ep, double& em) {
  * is the series itself, so the value near thermal equilibrium (x -> 0) keeps full
  * relative accuracy; branch-free.  x is clamped to [-700, 700].                   */
 SB_HD double sb_expm1(double x) {
-  x = fmin(fmax(x, -700.0), 700.0);
-  const double magic = 6755399441055744.0;
-  const double t = fma(x, 1.4426950408889634074, magic);
-#ifdef __CUDA_ARCH__
-  const int k = __double2loint(t);
-#else
-  uint64_t tb;
-  memcpy(&tb, &t, sizeof tb);
-  const int k = (int)(uint32_t)(tb & 0xFFFFFFFFu);
-#endif
-  const double kf = t - magic;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
+  int k;
+  const double r = sb_exp_reduce(x, k);
   const double z = r * r;
-  double E1 = 1.0 / 479001600.0, O = 1.0 / 6227020800.0;
-  E1 = fma(E1, z, 1.0 / 3628800.0);  O = fma(O, z, 1.0 / 39916800.0);
-  E1 = fma(E1, z, 1.0 / 40320.0);    O = fma(O, z, 1.0 / 362880.0);
-  E1 = fma(E1, z, 1.0 / 720.0);      O = fma(O, z, 1.0 / 5040.0);
-  E1 = fma(E1, z, 1.0 / 24.0);       O = fma(O, z, 1.0 / 120.0);
-  E1 = fma(E1, z, 0.5);              O = fma(O, z, 1.0 / 6.0);
+  double E1 = SB_EXPC(3), O = SB_EXPC(8);
+  E1 = fma(E1, z, SB_EXPC(4));  O = fma(O, z, SB_EXPC(9));
+  E1 = fma(E1, z, SB_EXPC(5));  O = fma(O, z, SB_EXPC(10));
+  E1 = fma(E1, z, SB_EXPC(6));  O = fma(O, z, SB_EXPC(11));
+  E1 = fma(E1, z, SB_EXPC(7));  O = fma(O, z, SB_EXPC(12));
+  E1 = fma(E1, z, 0.5);         O = fma(O, z, SB_EXPC(13));
   O = fma(O, z, 1.0);
   const double em_r = fma(r, O, z * E1);
   const double s = sb_pow2i(k);
   return fma(s, em_r, s - 1.0);
 }
 
+/* 1 / d for d in [1, 1e305] (d = 1 + exp(x), x clamped): hardware approximation plus two
+ * Newton steps, within 1 ulp, and no special-case branch -- the IEEE division's slow path
+ * would end the basic block and with it the interleaving of neighbouring points.     */
+SB_HD double sb_rcp_pos(double d) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / d;
+#endif
+}
+
 /* Pointwise band quantities at chi = e phi + w (band statistics
  * poisson_drift_diffusion1.py1:170-245):
  *   su = s u / eps, dsu = d(su)/dchi, c = dd_scale / (mu u), dc = dc/dchi   */
-SB_HD void sb_band_point(const SbBandK& K, double chi,
-                         double& su, double& dsu, double& c, double& dc) {
+/* kind / const_mob passed separately: callers that hold K in shared memory pass the
+ * warp-uniform model values so that the branch stays uniform and the unrolled point
+ * loops remain straight-line code (independent exp chains interleave) */
+SB_HD void sb_band_point_kind(const SbBandK& K, int kind, int const_mob, double chi,
+                              double& su, double& dsu, double& c, double& dc) {
   double e, einv;
   sb_exp_pair(K.sbeta * (chi - K.E), e, einv);
-  if (K.kind == SB_BAND_NONDEGENERATE) {
+  if (kind == SB_BAND_NONDEGENERATE) {
     const double ue = K.N_eps * einv;         /* u / eps */
     su = K.s * ue;
     dsu = -K.beta * ue;
     c = K.cinv * e;
     dc = K.sbeta * c;
   } else {
-    const double f = 1.0 / (1.0 + e);
+    const double f = 1.0 / (1.0 + e);         /* IEEE division: in the moment kernel its slow-path
+                                                 branch also bounds the interleaving, measured
+                                                 faster (fewer spills) than sb_rcp_pos here */
     const double omf = e * f;                 /* 1 - f */
     su = K.s * K.N_eps * f;
     dsu = -K.beta * K.N_eps * f * omf;
-    if (K.const_mob) {
+    if (const_mob) {
       c = K.cinv * (1.0 + e);
       dc = K.cinv * K.sbeta * e;
     } else {
@@ -227,18 +278,23 @@ SB_HD void sb_band_point(const SbBandK& K, double chi,
     }
   }
 }
+SB_HD void sb_band_point(const SbBandK& K, double chi,
+                         double& su, double& dsu, double& c, double& dc) {
+  sb_band_point_kind(K, K.kind, K.const_mob, chi, su, dsu, c, dc);
+}
 
 /* carrier density and its chi-derivative only (generation term) */
+/* branch-free for both kinds (selects): the bands of a point form one basic block */
+SB_HD void sb_band_u_kind(const SbBandK& K, int kind, double chi, double& u, double& du) {
+  double e, einv;
+  sb_exp_pair(K.sbeta * (chi - K.E), e, einv);
+  const double f = sb_rcp_pos(1.0 + e);
+  const bool nd = (kind == SB_BAND_NONDEGENERATE);
+  u = K.N * (nd ? einv : f);
+  du = -K.sbeta * u * (nd ? 1.0 : e * f);
+}
 SB_HD void sb_band_u(const SbBandK& K, double chi, double& u, double& du) {
-  if (K.kind == SB_BAND_NONDEGENERATE) {
-    u = K.N * exp(-K.sbeta * (chi - K.E));
-    du = -K.sbeta * u;
-  } else {
-    const double e = exp(K.sbeta * (chi - K.E));
-    const double f = 1.0 / (1.0 + e);
-    u = K.N * f;
-    du = -K.sbeta * u * (e * f);
-  }
+  sb_band_u_kind(K, K.kind, chi, u, du);
 }
 
 /* ------------------------------------------------------------------------- *
@@ -251,11 +307,20 @@ SB_HD void sb_band_u(const SbBandK& K, double chi, double& u, double& du) {
  * MM > 0: compile-time number of points per axis (inner loop unrolled, the
  * independent exp chains of neighbouring points interleave); MM = 0: R.m.
  * ------------------------------------------------------------------------- */
-template <int MM>
-SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBandK& K,
+template <int MM, int MODE = 0>
+SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho_, bool do_dd_, const SbBandK& K,
                           double chi0, double chix, double chiy, const double (*gc)[6],
                           double* mC, double* Q, double* mR, double* mRx) {
   const int m = MM > 0 ? MM : R.m;
+  /* MODE 1 / 2: rho and dd both on, kind fixed (non-degenerate / intermediate with constant
+     mobility): the unrolled loop over the 11 points of a row is straight-line code, so the
+     independent exp chains of neighbouring points interleave (measured 3.19 -> 2.77 ms per
+     1M cells; with the run-time branches every point was its own basic block and the warp
+     ran one dependent chain at a time).  MODE 0: everything at run time. */
+  const bool do_rho = MODE ? true : do_rho_;
+  const bool do_dd = MODE ? true : do_dd_;
+  const int kind = MODE == 1 ? SB_BAND_NONDEGENERATE : (MODE == 2 ? SB_BAND_INTERMEDIATE : K.kind);
+  const int cmob = MODE == 2 ? 1 : K.const_mob;       /* MODE 2: constant-mobility IB */
   if (do_dd) {
 #pragma unroll
     for (int t = 0; t < SB_NMC; ++t) mC[t] = 0.0;
@@ -291,7 +356,7 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBand
     for (int i = 0; i < m; ++i) {
       const double chi = chij + chis * R.a[i];
       double su, dsu, c, dc;
-      sb_band_point(K, chi, su, dsu, c, dc);
+      sb_band_point_kind(K, kind, cmob, chi, su, dsu, c, dc);
       const double* wg = R.wag[i];
       if (do_dd) {
         const double* g3 = R.g3[i];
@@ -339,12 +404,33 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho, bool do_dd, const SbBand
 
 /* ------------------------------------------------------------------------- *
  * phase B: generation terms of all bands at the points of the g-rule.
+ *
+ * The process list is data (sb_model in the constant bank), so band indices are
+ * only known at run time.  Everything per point nevertheless stays in registers:
+ * arrays are indexed with compile-time indices only, a run-time band index goes
+ * through sb_pick / sb_bump (select chains over the NB <= 4 candidates; the index
+ * is warp-uniform).  Dynamically indexed thread-local arrays put the first
+ * version of this kernel at 5.6 GB of local-memory traffic per 320 k cells.
  * ------------------------------------------------------------------------- */
+template <int NB>
+SB_HD double sb_pick(const double* a, int i) {
+  double v = a[0];
+#pragma unroll
+  for (int l = 1; l < NB; ++l) v = (i == l) ? a[l] : v;
+  return v;
+}
+template <int NB>
+SB_HD void sb_bump(double* a, int i, double v) {
+#pragma unroll
+  for (int l = 0; l < NB; ++l) a[l] = (i == l) ? a[l] + v : a[l];
+}
+
+template <int NB>
 struct SbBandsAtPoint {
-  double u[SB_MAX_BANDS], du[SB_MAX_BANDS], w[SB_MAX_BANDS], u0[SB_MAX_BANDS];
+  double u[NB > 0 ? NB : 1], du[NB > 0 ? NB : 1], w[NB > 0 ? NB : 1], u0[NB > 0 ? NB : 1];
   /* expm1(s_R (w_R - w_I) / kT) for every band R against the trap band `trap`
      (-1: none): shared by the Shockley-Read and the radiative IB process of a pair */
-  double em[SB_MAX_BANDS];
+  double em[NB > 0 ? NB : 1];
   int trap;
 };
 
@@ -356,79 +442,274 @@ SB_HD int sb_gen_sign(const sb_model& M, int p, int k) {
 
 /* Shockley-Read kernel G = expm1(x) u_R F c and its partials
  * (electro_optical_process.py:294-312), hand-derived.                     */
-SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff,
-                      const SbBandsAtPoint& B, double& g, double& dphi, double* dw) {
+template <int NB>
+SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff, double beta,
+                      const SbBandsAtPoint<NB>& B, double& g, double& dphi, double* dw) {
   const int IB = M.proc_trap[p];
   const int RB = (M.proc_dst[p] == IB) ? M.proc_src[p] : M.proc_dst[p];
-  const double beta = 1.0 / tp[SB_TP_KT];
   const double sR = (double)M.band_sign[RB];
   const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
   const bool same = (M.band_sign[IB] == M.band_sign[RB]);
-  const double F = same ? (N_I - B.u[IB]) : B.u[IB];
-  const double dF = same ? -B.du[IB] : B.du[IB];
-  const double x = sR * (B.w[RB] - B.w[IB]) * beta;
-  const double em = (B.trap == IB) ? B.em[RB] : sb_expm1(x), ex = em + 1.0;
-  g += coeff * em * B.u[RB] * F;
-  dphi += coeff * em * (B.du[RB] * F + B.u[RB] * dF);
-  dw[RB] += coeff * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
-  dw[IB] += coeff * B.u[RB] * (-ex * sR * beta * F + em * dF);
+  const double uI = sb_pick<NB>(B.u, IB), duI = sb_pick<NB>(B.du, IB);
+  const double uR = sb_pick<NB>(B.u, RB), duR = sb_pick<NB>(B.du, RB);
+  const double F = same ? (N_I - uI) : uI;
+  const double dF = same ? -duI : duI;
+  double em;
+  if (B.trap == IB) {
+    em = sb_pick<NB>(B.em, RB);
+  } else {
+    em = sb_expm1(sR * (sb_pick<NB>(B.w, RB) - sb_pick<NB>(B.w, IB)) * beta);
+  }
+  const double ex = em + 1.0;
+  g += coeff * em * uR * F;
+  dphi += coeff * em * (duR * F + uR * dF);
+  sb_bump<NB>(dw, RB, coeff * F * (ex * sR * beta * uR + em * duR));
+  sb_bump<NB>(dw, IB, coeff * uR * (-ex * sR * beta * F + em * dF));
 }
 
 /* One process at one point: G_p (positive = the destination band gains
  * carriers) and its partials w.r.t. phi and every w_l.  Band k then receives
  * sign(p, k) * G_p (TwoBandEOPMixin, electro_optical_process.py:193-205).    */
-SB_HD void sb_process_point(const sb_model& M, const double* tp, int p,
-                            const SbBandsAtPoint& B, const double* phi_clip,
+template <int NB>
+SB_HD void sb_process_point(const sb_model& M, const double* tp, int p, double beta,
+                            const SbBandsAtPoint<NB>& B, const double* phi_clip,
                             double& g, double& dphi, double* dw) {
   g = 0.0; dphi = 0.0;
 #pragma unroll
-  for (int l = 0; l < SB_MAX_BANDS; ++l) dw[l] = 0.0;
-  const double beta = 1.0 / tp[SB_TP_KT];
+  for (int l = 0; l < NB; ++l) dw[l] = 0.0;
   const double* pp = tp + SB_TP_PROC0 + 8 * p;
   const int dst = M.proc_dst[p], src = M.proc_src[p];
-  switch (M.proc_kind[p]) {
-    case SB_PROC_SRH: {
-      const double D = (B.u[dst] + pp[SB_TPP_P2]) * pp[SB_TPP_P1]
-                     + (B.u[src] + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
-      const double r = (B.u[src] * B.u[dst] - B.u0[src] * B.u0[dst]) / D;
-      const double dr_dst = (B.u[src] - r * pp[SB_TPP_P1]) / D * B.du[dst];
-      const double dr_src = (B.u[dst] - r * pp[SB_TPP_P0]) / D * B.du[src];
-      g = -r;
-      dw[dst] = -dr_dst;
-      dw[src] -= dr_src;
-      dphi = -(dr_dst + dr_src);
-    } break;
-    case SB_PROC_SR_TRAP:
-      sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, g, dphi, dw);
-      break;
-    case SB_PROC_RAD_BB: {
-      double S = 0.0;
-      for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-      g = S;
-      if (M.proc_radiative[p]) {
-        const double x = beta * (B.w[dst] - B.w[src]);
-        const double em = sb_expm1(x), ex = em + 1.0;
-        g -= pp[SB_TPP_P0] * em;
-        dw[dst] -= pp[SB_TPP_P0] * beta * ex;
-        dw[src] += pp[SB_TPP_P0] * beta * ex;
-      }
-    } break;
-    case SB_PROC_RAD_IB: {
-      const int IB = M.proc_trap[p];
-      const int RB = (dst == IB) ? src : dst;
-      const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
-      const bool same = (M.band_sign[IB] == M.band_sign[RB]);
-      const double Fa = same ? B.u[IB] : (N_I - B.u[IB]);
-      const double dFa = same ? B.du[IB] : -B.du[IB];
-      double S = 0.0;
-      for (int f = 0; f < M.n_fields; ++f) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-      g = S * Fa;
-      dw[IB] = S * dFa;
-      dphi = S * dFa;
-      if (M.proc_radiative[p])
-        sb_sr_trap(M, tp, p, pp[SB_TPP_P0], B, g, dphi, dw);
-    } break;
-    default: break;
+  const int kind = M.proc_kind[p];
+  if (kind == SB_PROC_SRH) {
+    const double ud = sb_pick<NB>(B.u, dst), us = sb_pick<NB>(B.u, src);
+    const double D = (ud + pp[SB_TPP_P2]) * pp[SB_TPP_P1] + (us + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
+    const double r = (us * ud - sb_pick<NB>(B.u0, src) * sb_pick<NB>(B.u0, dst)) / D;
+    const double dr_dst = (us - r * pp[SB_TPP_P1]) / D * sb_pick<NB>(B.du, dst);
+    const double dr_src = (ud - r * pp[SB_TPP_P0]) / D * sb_pick<NB>(B.du, src);
+    g = -r;
+    sb_bump<NB>(dw, dst, -dr_dst);
+    sb_bump<NB>(dw, src, -dr_src);
+    dphi = -(dr_dst + dr_src);
+  } else if (kind == SB_PROC_SR_TRAP) {
+    sb_sr_trap<NB>(M, tp, p, pp[SB_TPP_P0], beta, B, g, dphi, dw);
+  } else if (kind == SB_PROC_RAD_BB) {
+    double S = 0.0;
+#pragma unroll
+    for (int f = 0; f < SB_MAX_FIELDS; ++f)
+      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+    g = S;
+    if (M.proc_radiative[p]) {
+      const double x = beta * (sb_pick<NB>(B.w, dst) - sb_pick<NB>(B.w, src));
+      const double em = sb_expm1(x), ex = em + 1.0;
+      g -= pp[SB_TPP_P0] * em;
+      sb_bump<NB>(dw, dst, -pp[SB_TPP_P0] * beta * ex);
+      sb_bump<NB>(dw, src, pp[SB_TPP_P0] * beta * ex);
+    }
+  } else if (kind == SB_PROC_RAD_IB) {
+    const int IB = M.proc_trap[p];
+    const int RB = (dst == IB) ? src : dst;
+    const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
+    const bool same = (M.band_sign[IB] == M.band_sign[RB]);
+    const double uI = sb_pick<NB>(B.u, IB), duI = sb_pick<NB>(B.du, IB);
+    const double Fa = same ? uI : (N_I - uI);
+    const double dFa = same ? duI : -duI;
+    double S = 0.0;
+#pragma unroll
+    for (int f = 0; f < SB_MAX_FIELDS; ++f)
+      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+    g = S * Fa;
+    sb_bump<NB>(dw, IB, S * dFa);
+    dphi = S * dFa;
+    if (M.proc_radiative[p])
+      sb_sr_trap<NB>(M, tp, p, pp[SB_TPP_P0], beta, B, g, dphi, dw);
+  }
+}
+
+/* ---- processes with compile-time band indices -------------------------------------- *
+ * The process list is data, but a process only ever touches its (dst, src) pair, and there
+ * are at most NB (NB - 1) <= 12 ordered pairs.  sb_process_accumulate dispatches once per
+ * process on the pair (warp-uniform compare chain) into a body where every band index is a
+ * template constant: no select chains, and only the 2 x 2 non-zero partials dg/dw are
+ * accumulated instead of NB x NB.  Same arithmetic and order as sb_process_point followed by
+ * the signed accumulation (adding the structurally zero partials changed nothing).      */
+template <int NB, int IB, int RB>
+SB_HD void sb_sr_trap_ct(const sb_model& M, const double* tp, double coeff, double beta,
+                         const SbBandsAtPoint<NB>& B, double& g, double& dphi,
+                         double& dwR, double& dwI) {
+  const double sR = (double)M.band_sign[RB];
+  const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
+  const bool same = (M.band_sign[IB] == M.band_sign[RB]);
+  const double F = same ? (N_I - B.u[IB]) : B.u[IB];
+  const double dF = same ? -B.du[IB] : B.du[IB];
+  const double em = (B.trap == IB) ? B.em[RB] : sb_expm1(sR * (B.w[RB] - B.w[IB]) * beta);
+  const double ex = em + 1.0;
+  g += coeff * em * B.u[RB] * F;
+  dphi += coeff * em * (B.du[RB] * F + B.u[RB] * dF);
+  dwR += coeff * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
+  dwI += coeff * B.u[RB] * (-ex * sR * beta * F + em * dF);
+}
+
+template <int NB, int DST, int SRC>
+SB_HD void sb_process_pair(const sb_model& M, const double* tp, int p, double beta,
+                           const SbBandsAtPoint<NB>& B, const double* phi_clip,
+                           double* gk, double* dphik, double* dwk) {
+  double g = 0.0, dphi = 0.0, dwd = 0.0, dws = 0.0;     /* dG/dw_dst, dG/dw_src */
+  const double* pp = tp + SB_TP_PROC0 + 8 * p;
+  const int kind = M.proc_kind[p];
+  if (kind == SB_PROC_SRH) {
+    const double D = (B.u[DST] + pp[SB_TPP_P2]) * pp[SB_TPP_P1]
+                   + (B.u[SRC] + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
+    const double r = (B.u[SRC] * B.u[DST] - B.u0[SRC] * B.u0[DST]) / D;
+    const double dr_dst = (B.u[SRC] - r * pp[SB_TPP_P1]) / D * B.du[DST];
+    const double dr_src = (B.u[DST] - r * pp[SB_TPP_P0]) / D * B.du[SRC];
+    g = -r;
+    dwd += -dr_dst;
+    dws += -dr_src;
+    dphi = -(dr_dst + dr_src);
+  } else if (kind == SB_PROC_SR_TRAP) {
+    if (M.proc_trap[p] == DST) sb_sr_trap_ct<NB, DST, SRC>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dws, dwd);
+    else                       sb_sr_trap_ct<NB, SRC, DST>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dwd, dws);
+  } else if (kind == SB_PROC_RAD_BB) {
+    double S = 0.0;
+#pragma unroll
+    for (int f = 0; f < SB_MAX_FIELDS; ++f)
+      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+    g = S;
+    if (M.proc_radiative[p]) {
+      const double x = beta * (B.w[DST] - B.w[SRC]);
+      const double em = sb_expm1(x), ex = em + 1.0;
+      g -= pp[SB_TPP_P0] * em;
+      dwd += -pp[SB_TPP_P0] * beta * ex;
+      dws += pp[SB_TPP_P0] * beta * ex;
+    }
+  } else if (kind == SB_PROC_RAD_IB) {
+    const bool ib_dst = (M.proc_trap[p] == DST);
+    const double N_I = tp[SB_TP_BAND0 + 5 * (ib_dst ? DST : SRC) + SB_TPB_N];
+    const bool same = (M.band_sign[DST] == M.band_sign[SRC]);
+    const double uI = ib_dst ? B.u[DST] : B.u[SRC], duI = ib_dst ? B.du[DST] : B.du[SRC];
+    const double Fa = same ? uI : (N_I - uI);
+    const double dFa = same ? duI : -duI;
+    double S = 0.0;
+#pragma unroll
+    for (int f = 0; f < SB_MAX_FIELDS; ++f)
+      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
+    g = S * Fa;
+    if (ib_dst) dwd += S * dFa; else dws += S * dFa;
+    dphi = S * dFa;
+    if (M.proc_radiative[p]) {
+      if (ib_dst) sb_sr_trap_ct<NB, DST, SRC>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dws, dwd);
+      else        sb_sr_trap_ct<NB, SRC, DST>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dwd, dws);
+    }
+  }
+  /* band dst gains G, band src gains -(s_dst s_src) G (TwoBandEOPMixin) */
+  const double ss = -(double)(M.band_sign[DST] * M.band_sign[SRC]);
+  gk[DST] += g;          gk[SRC] += ss * g;
+  dphik[DST] += dphi;    dphik[SRC] += ss * dphi;
+  dwk[DST * NB + DST] += dwd;       dwk[DST * NB + SRC] += dws;
+  dwk[SRC * NB + DST] += ss * dwd;  dwk[SRC * NB + SRC] += ss * dws;
+}
+
+template <int NB, int PAIR>
+struct SbPairDispatch {
+  static SB_HD void go(int pair, const sb_model& M, const double* tp, int p, double beta,
+                       const SbBandsAtPoint<NB>& B, const double* phi_clip,
+                       double* gk, double* dphik, double* dwk) {
+    if (pair == PAIR) {
+      if constexpr (PAIR / NB != PAIR % NB)
+        sb_process_pair<NB, PAIR / NB, PAIR % NB>(M, tp, p, beta, B, phi_clip, gk, dphik, dwk);
+    } else {
+      SbPairDispatch<NB, PAIR - 1>::go(pair, M, tp, p, beta, B, phi_clip, gk, dphik, dwk);
+    }
+  }
+};
+template <int NB>
+struct SbPairDispatch<NB, -1> {
+  static SB_HD void go(int, const sb_model&, const double*, int, double,
+                       const SbBandsAtPoint<NB>&, const double*, double*, double*, double*) {}
+};
+
+/* which processes need what, hoisted out of the point loop */
+SB_HD void sb_phaseB_scan(const sb_model& M, bool& need_u0, int& trap) {
+  need_u0 = false;
+  trap = -1;
+  for (int p = 0; p < M.n_procs; ++p) {
+    need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
+    if (trap < 0 && (M.proc_kind[p] == SB_PROC_SR_TRAP ||
+                     (M.proc_kind[p] == SB_PROC_RAD_IB && M.proc_radiative[p])))
+      trap = M.proc_trap[p];
+  }
+}
+
+/* Point n of the g-rule: totals per band gk[k] = g_k, dphik[k] = dg_k/dphi,
+ * dwk[k * NB + l] = dg_k/dw_l.  dgv[3 p + i]: P1 nodal values of (phi | delta_w_l);
+ * w0[l]: base_w of the cell; K[l]: band constants.                                */
+template <int NB>
+SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* tp, int n,
+                           const double* dgv, const double* w0, const SbBandK* K,
+                           bool need_u0, int trap, double beta_pt,
+                           const double* thmeq6, const double* phi_opt, int64_t field_stride,
+                           double* gk, double* dphik, double* dwk) {
+  const double X = T.gX[n], Y = T.gY[n];
+  const double l0 = 1.0 - X - Y;
+  const double phi = dgv[0] * l0 + dgv[1] * X + dgv[2] * Y;
+  const double* n2 = T.gp2[n];
+  SbBandsAtPoint<NB> B;
+#pragma unroll
+  for (int l = 0; l < NB; ++l) {
+    B.w[l] = w0[l] + dgv[3 + 3 * l] * l0 + dgv[4 + 3 * l] * X + dgv[5 + 3 * l] * Y;
+    sb_band_u_kind(K[l], M.band_kind[l], phi + B.w[l], B.u[l], B.du[l]);
+    B.u0[l] = 0.0;
+  }
+  if (need_u0) {
+    double phi_te = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) phi_te += (thmeq6 ? thmeq6[a] : 0.0) * n2[a];
+#pragma unroll
+    for (int l = 0; l < NB; ++l) { double d_; sb_band_u_kind(K[l], M.band_kind[l], phi_te, B.u0[l], d_); }
+  }
+  B.trap = trap;
+  if (trap >= 0) {
+    const double wt = sb_pick<NB>(B.w, trap);
+#pragma unroll
+    for (int l = 0; l < NB; ++l)
+      B.em[l] = sb_expm1((double)M.band_sign[l] * (B.w[l] - wt) * beta_pt);   /* l == trap: expm1(0) = 0 */
+  } else {
+#pragma unroll
+    for (int l = 0; l < NB; ++l) B.em[l] = 0.0;
+  }
+  double phi_clip[SB_MAX_FIELDS];
+#pragma unroll
+  for (int f = 0; f < SB_MAX_FIELDS; ++f) {
+    double v = 0.0;
+    if (f < M.n_fields) {
+      const double* pf = phi_opt + (int64_t)f * field_stride;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) v += pf[a] * n2[a];
+    }
+    phi_clip[f] = v < 0.0 ? 0.0 : v;      /* optical.py:201-203 */
+  }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    gk[k] = 0.0; dphik[k] = 0.0;
+#pragma unroll
+    for (int l = 0; l < NB; ++l) dwk[k * NB + l] = 0.0;
+  }
+#pragma unroll 1
+  for (int p = 0; p < M.n_procs; ++p) {
+#ifndef SB_GEN_PAIR
+    double g, dphi, dw[NB > 0 ? NB : 1];
+    sb_process_point<NB>(M, tp, p, beta_pt, B, phi_clip, g, dphi, dw);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const double sg = (double)sb_gen_sign(M, p, k);
+      gk[k] += sg * g; dphik[k] += sg * dphi;
+#pragma unroll
+      for (int l = 0; l < NB; ++l) dwk[k * NB + l] += sg * dw[l];
+    }
+#else
+    SbPairDispatch<NB, NB * NB - 1>::go(M.proc_dst[p] * NB + M.proc_src[p], M, tp, p, beta_pt, B,
+                                        phi_clip, gk, dphik, dwk);
+#endif
   }
 }
 
@@ -446,73 +727,17 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
 #pragma unroll
     for (int t = 0; t < 9 + 6 * NB; ++t) mG[k][t] = 0.0;
   SbBandK K[NB > 0 ? NB : 1];
-  bool need_u0 = false;
-  int trap = -1;
-  for (int p = 0; p < M.n_procs; ++p) {
-    need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
-    if (trap < 0 && (M.proc_kind[p] == SB_PROC_SR_TRAP ||
-                     (M.proc_kind[p] == SB_PROC_RAD_IB && M.proc_radiative[p])))
-      trap = M.proc_trap[p];
-  }
+  bool need_u0;
+  int trap;
+  sb_phaseB_scan(M, need_u0, trap);
   const double beta_pt = 1.0 / tp[SB_TP_KT];
 #pragma unroll
   for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
 #pragma unroll 1
   for (int n = 0; n < T.ng; ++n) {
-    const double X = T.gX[n], Y = T.gY[n];
-    const double l0 = 1.0 - X - Y;
-    const double phi = dgv[0][0] * l0 + dgv[0][1] * X + dgv[0][2] * Y;
-    const double* n2 = T.gp2[n];
-    double phi_te = 0.0;
-    if (need_u0 && thmeq6) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) phi_te += thmeq6[a] * n2[a];
-    }
-    SbBandsAtPoint B;
-#pragma unroll
-    for (int l = 0; l < NB; ++l) {
-      B.w[l] = w0[l] + dgv[1 + l][0] * l0 + dgv[1 + l][1] * X + dgv[1 + l][2] * Y;
-      sb_band_u(K[l], phi + B.w[l], B.u[l], B.du[l]);
-      B.u0[l] = 0.0;
-      if (need_u0) { double d_; sb_band_u(K[l], phi_te, B.u0[l], d_); }
-    }
-    B.trap = trap;
-    if (trap >= 0) {
-#pragma unroll
-      for (int l = 0; l < NB; ++l)
-        B.em[l] = (l == trap) ? 0.0
-                              : sb_expm1((double)M.band_sign[l] * (B.w[l] - B.w[trap]) * beta_pt);
-    }
-    double phi_clip[SB_MAX_FIELDS];
-    for (int f = 0; f < M.n_fields; ++f) {
-      const double* pf = phi_opt + (int64_t)f * field_stride;
-      double v = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) v += pf[a] * n2[a];
-      phi_clip[f] = v < 0.0 ? 0.0 : v;      /* optical.py:201-203 */
-    }
-    /* pointwise totals per band */
-    double gk[NB > 0 ? NB : 1], dphik[NB > 0 ? NB : 1], dwk[NB > 0 ? NB : 1][SB_MAX_BANDS];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      gk[k] = 0.0; dphik[k] = 0.0;
-#pragma unroll
-      for (int l = 0; l < SB_MAX_BANDS; ++l) dwk[k][l] = 0.0;
-    }
-#pragma unroll 1
-    for (int p = 0; p < M.n_procs; ++p) {
-      double g, dphi, dw[SB_MAX_BANDS];
-      sb_process_point(M, tp, p, B, phi_clip, g, dphi, dw);
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        const int sgi = sb_gen_sign(M, p, k);
-        if (!sgi) continue;
-        const double sg = (double)sgi;
-        gk[k] += sg * g; dphik[k] += sg * dphi;
-#pragma unroll
-        for (int l = 0; l < NB; ++l) dwk[k][l] += sg * dw[l];
-      }
-    }
+    double gk[NB > 0 ? NB : 1], dphik[NB > 0 ? NB : 1], dwk[NB > 0 ? NB * NB : 1];
+    sb_phaseB_point<NB>(T, M, tp, n, &dgv[0][0], w0, K, need_u0, trap, beta_pt, thmeq6, phi_opt,
+                        field_stride, gk, dphik, dwk);
     const double* wp = T.gwpsi[n];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -524,7 +749,7 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
 #pragma unroll
       for (int l = 0; l < NB; ++l)
 #pragma unroll
-        for (int t = 0; t < 6; ++t) mG[k][9 + 6 * l + t] += wp[t] * dwk[k][l];
+        for (int t = 0; t < 6; ++t) mG[k][9 + 6 * l + t] += wp[t] * dwk[k * NB + l];
     }
   }
 }

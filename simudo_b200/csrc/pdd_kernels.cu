@@ -234,7 +234,12 @@ k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   const bool rho = (K.N != 0.0);
   const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
   if (same_rule && c_M.quad_m_super == 11) {
-    if (rho || dd) sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    /* common cases as straight-line instances (see sb_phaseA_band) */
+    if (rho && dd && K.kind == SB_BAND_NONDEGENERATE)
+      sb_phaseA_band<11, 1>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    else if (rho && dd && K.const_mob)
+      sb_phaseA_band<11, 2>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    else if (rho || dd) sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
   } else if (same_rule) {
     if (rho || dd) sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
   } else {
