@@ -525,109 +525,6 @@ SB_HD void sb_process_point(const sb_model& M, const double* tp, int p, double b
   }
 }
 
-/* ---- processes with compile-time band indices -------------------------------------- *
- * The process list is data, but a process only ever touches its (dst, src) pair, and there
- * are at most NB (NB - 1) <= 12 ordered pairs.  sb_process_accumulate dispatches once per
- * process on the pair (warp-uniform compare chain) into a body where every band index is a
- * template constant: no select chains, and only the 2 x 2 non-zero partials dg/dw are
- * accumulated instead of NB x NB.  Same arithmetic and order as sb_process_point followed by
- * the signed accumulation (adding the structurally zero partials changed nothing).      */
-template <int NB, int IB, int RB>
-SB_HD void sb_sr_trap_ct(const sb_model& M, const double* tp, double coeff, double beta,
-                         const SbBandsAtPoint<NB>& B, double& g, double& dphi,
-                         double& dwR, double& dwI) {
-  const double sR = (double)M.band_sign[RB];
-  const double N_I = tp[SB_TP_BAND0 + 5 * IB + SB_TPB_N];
-  const bool same = (M.band_sign[IB] == M.band_sign[RB]);
-  const double F = same ? (N_I - B.u[IB]) : B.u[IB];
-  const double dF = same ? -B.du[IB] : B.du[IB];
-  const double em = (B.trap == IB) ? B.em[RB] : sb_expm1(sR * (B.w[RB] - B.w[IB]) * beta);
-  const double ex = em + 1.0;
-  g += coeff * em * B.u[RB] * F;
-  dphi += coeff * em * (B.du[RB] * F + B.u[RB] * dF);
-  dwR += coeff * F * (ex * sR * beta * B.u[RB] + em * B.du[RB]);
-  dwI += coeff * B.u[RB] * (-ex * sR * beta * F + em * dF);
-}
-
-template <int NB, int DST, int SRC>
-SB_HD void sb_process_pair(const sb_model& M, const double* tp, int p, double beta,
-                           const SbBandsAtPoint<NB>& B, const double* phi_clip,
-                           double* gk, double* dphik, double* dwk) {
-  double g = 0.0, dphi = 0.0, dwd = 0.0, dws = 0.0;     /* dG/dw_dst, dG/dw_src */
-  const double* pp = tp + SB_TP_PROC0 + 8 * p;
-  const int kind = M.proc_kind[p];
-  if (kind == SB_PROC_SRH) {
-    const double D = (B.u[DST] + pp[SB_TPP_P2]) * pp[SB_TPP_P1]
-                   + (B.u[SRC] + pp[SB_TPP_P3]) * pp[SB_TPP_P0];
-    const double r = (B.u[SRC] * B.u[DST] - B.u0[SRC] * B.u0[DST]) / D;
-    const double dr_dst = (B.u[SRC] - r * pp[SB_TPP_P1]) / D * B.du[DST];
-    const double dr_src = (B.u[DST] - r * pp[SB_TPP_P0]) / D * B.du[SRC];
-    g = -r;
-    dwd += -dr_dst;
-    dws += -dr_src;
-    dphi = -(dr_dst + dr_src);
-  } else if (kind == SB_PROC_SR_TRAP) {
-    if (M.proc_trap[p] == DST) sb_sr_trap_ct<NB, DST, SRC>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dws, dwd);
-    else                       sb_sr_trap_ct<NB, SRC, DST>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dwd, dws);
-  } else if (kind == SB_PROC_RAD_BB) {
-    double S = 0.0;
-#pragma unroll
-    for (int f = 0; f < SB_MAX_FIELDS; ++f)
-      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-    g = S;
-    if (M.proc_radiative[p]) {
-      const double x = beta * (B.w[DST] - B.w[SRC]);
-      const double em = sb_expm1(x), ex = em + 1.0;
-      g -= pp[SB_TPP_P0] * em;
-      dwd += -pp[SB_TPP_P0] * beta * ex;
-      dws += pp[SB_TPP_P0] * beta * ex;
-    }
-  } else if (kind == SB_PROC_RAD_IB) {
-    const bool ib_dst = (M.proc_trap[p] == DST);
-    const double N_I = tp[SB_TP_BAND0 + 5 * (ib_dst ? DST : SRC) + SB_TPB_N];
-    const bool same = (M.band_sign[DST] == M.band_sign[SRC]);
-    const double uI = ib_dst ? B.u[DST] : B.u[SRC], duI = ib_dst ? B.du[DST] : B.du[SRC];
-    const double Fa = same ? uI : (N_I - uI);
-    const double dFa = same ? duI : -duI;
-    double S = 0.0;
-#pragma unroll
-    for (int f = 0; f < SB_MAX_FIELDS; ++f)
-      if (f < M.n_fields) S += phi_clip[f] * pp[SB_TPP_FIELD0 + f];
-    g = S * Fa;
-    if (ib_dst) dwd += S * dFa; else dws += S * dFa;
-    dphi = S * dFa;
-    if (M.proc_radiative[p]) {
-      if (ib_dst) sb_sr_trap_ct<NB, DST, SRC>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dws, dwd);
-      else        sb_sr_trap_ct<NB, SRC, DST>(M, tp, pp[SB_TPP_P0], beta, B, g, dphi, dwd, dws);
-    }
-  }
-  /* band dst gains G, band src gains -(s_dst s_src) G (TwoBandEOPMixin) */
-  const double ss = -(double)(M.band_sign[DST] * M.band_sign[SRC]);
-  gk[DST] += g;          gk[SRC] += ss * g;
-  dphik[DST] += dphi;    dphik[SRC] += ss * dphi;
-  dwk[DST * NB + DST] += dwd;       dwk[DST * NB + SRC] += dws;
-  dwk[SRC * NB + DST] += ss * dwd;  dwk[SRC * NB + SRC] += ss * dws;
-}
-
-template <int NB, int PAIR>
-struct SbPairDispatch {
-  static SB_HD void go(int pair, const sb_model& M, const double* tp, int p, double beta,
-                       const SbBandsAtPoint<NB>& B, const double* phi_clip,
-                       double* gk, double* dphik, double* dwk) {
-    if (pair == PAIR) {
-      if constexpr (PAIR / NB != PAIR % NB)
-        sb_process_pair<NB, PAIR / NB, PAIR % NB>(M, tp, p, beta, B, phi_clip, gk, dphik, dwk);
-    } else {
-      SbPairDispatch<NB, PAIR - 1>::go(pair, M, tp, p, beta, B, phi_clip, gk, dphik, dwk);
-    }
-  }
-};
-template <int NB>
-struct SbPairDispatch<NB, -1> {
-  static SB_HD void go(int, const sb_model&, const double*, int, double,
-                       const SbBandsAtPoint<NB>&, const double*, double*, double*, double*) {}
-};
-
 /* which processes need what, hoisted out of the point loop */
 SB_HD void sb_phaseB_scan(const sb_model& M, bool& need_u0, int& trap) {
   need_u0 = false;
@@ -696,7 +593,6 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
   }
 #pragma unroll 1
   for (int p = 0; p < M.n_procs; ++p) {
-#ifndef SB_GEN_PAIR
     double g, dphi, dw[NB > 0 ? NB : 1];
     sb_process_point<NB>(M, tp, p, beta_pt, B, phi_clip, g, dphi, dw);
 #pragma unroll
@@ -706,10 +602,6 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
 #pragma unroll
       for (int l = 0; l < NB; ++l) dwk[k * NB + l] += sg * dw[l];
     }
-#else
-    SbPairDispatch<NB, NB * NB - 1>::go(M.proc_dst[p] * NB + M.proc_src[p], M, tp, p, beta_pt, B,
-                                        phi_clip, gk, dphik, dwk);
-#endif
   }
 }
 
@@ -733,7 +625,11 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   const double beta_pt = 1.0 / tp[SB_TP_KT];
 #pragma unroll
   for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
-#pragma unroll 1
+#ifndef SB_GEN_UNROLL
+#define SB_GEN_UNROLL 1
+#endif
+  constexpr int gen_unroll = SB_GEN_UNROLL;
+#pragma unroll gen_unroll
   for (int n = 0; n < T.ng; ++n) {
     double gk[NB > 0 ? NB : 1], dphik[NB > 0 ? NB : 1], dwk[NB > 0 ? NB * NB : 1];
     sb_phaseB_point<NB>(T, M, tp, n, &dgv[0][0], w0, K, need_u0, trap, beta_pt, thmeq6, phi_opt,
