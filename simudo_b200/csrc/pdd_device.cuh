@@ -307,10 +307,15 @@ SB_HD void sb_band_u(const SbBandK& K, double chi, double& u, double& du) {
  * MM > 0: compile-time number of points per axis (inner loop unrolled, the
  * independent exp chains of neighbouring points interleave); MM = 0: R.m.
  * ------------------------------------------------------------------------- */
+#ifndef SB_TILE
+#define SB_TILE 128
+#endif
 template <int MM, int MODE = 0>
 SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho_, bool do_dd_, const SbBandK& K,
                           double chi0, double chix, double chiy, const double (*gc)[6],
-                          double* mC, double* Q, double* mR, double* mRx) {
+                          double* mC, double* Q, double* mR, double* mRx,
+                          double* qs = nullptr /* Q accumulators in shared memory: Q[t] at
+                                                  qs[t * SB_TILE] (then Q is not touched) */) {
   const int m = MM > 0 ? MM : R.m;
   /* MODE 1 / 2: rho and dd both on, kind fixed (non-degenerate / intermediate with constant
      mobility): the unrolled loop over the 11 points of a row is straight-line code, so the
@@ -325,7 +330,7 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho_, bool do_dd_, const SbBa
 #pragma unroll
     for (int t = 0; t < SB_NMC; ++t) mC[t] = 0.0;
 #pragma unroll
-    for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
+    for (int t = 0; t < SB_NQ; ++t) { if (qs) qs[t * SB_TILE] = 0.0; else Q[t] = 0.0; }
   }
   if (do_rho) {
 #pragma unroll
@@ -387,8 +392,13 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho_, bool do_dd_, const SbBa
       for (int n = 0; n <= 3; ++n)
 #pragma unroll
         for (int p = 0; p <= n; ++p, ++t) {
-          Q[t] += wh[t] * Sq[0][p];
-          Q[10 + t] += wh[t] * Sq[1][p];
+          if (qs) {
+            qs[t * SB_TILE] += wh[t] * Sq[0][p];
+            qs[(10 + t) * SB_TILE] += wh[t] * Sq[1][p];
+          } else {
+            Q[t] += wh[t] * Sq[0][p];
+            Q[10 + t] += wh[t] * Sq[1][p];
+          }
         }
     }
     if (do_rho) {
@@ -597,7 +607,13 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
     sb_process_point<NB>(M, tp, p, beta_pt, B, phi_clip, g, dphi, dw);
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
+#ifdef SB_GEN_SKIP0
+      const int sgi = sb_gen_sign(M, p, k);
+      if (!sgi) continue;                       /* warp-uniform */
+      const double sg = (double)sgi;
+#else
       const double sg = (double)sb_gen_sign(M, p, k);
+#endif
       gk[k] += sg * g; dphik[k] += sg * dphi;
 #pragma unroll
       for (int l = 0; l < NB; ++l) dwk[k * NB + l] += sg * dw[l];

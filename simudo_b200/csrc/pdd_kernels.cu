@@ -235,10 +235,21 @@ k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
   if (same_rule && c_M.quad_m_super == 11) {
     /* common cases as straight-line instances (see sb_phaseA_band) */
-    if (rho && dd && K.kind == SB_BAND_NONDEGENERATE)
-      sb_phaseA_band<11, 1>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
-    else if (rho && dd && K.const_mob)
-      sb_phaseA_band<11, 2>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+#ifdef SB_MOM_Q_SMEM
+    __shared__ double s_q[SB_NQ][SB_TILE];
+    double* qs = &s_q[0][threadIdx.x];
+#define SB_Q_READBACK for (int t = 0; t < SB_NQ; ++t) Q[t] = qs[t * SB_TILE]
+#else
+    double* qs = nullptr;
+#define SB_Q_READBACK
+#endif
+    if (rho && dd && K.kind == SB_BAND_NONDEGENERATE) {
+      sb_phaseA_band<11, 1>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
+      SB_Q_READBACK;
+    } else if (rho && dd && K.const_mob) {
+      sb_phaseA_band<11, 2>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
+      SB_Q_READBACK;
+    }
     else if (rho || dd) sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
   } else if (same_rule) {
     if (rho || dd) sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
