@@ -607,13 +607,9 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
     sb_process_point<NB>(M, tp, p, beta_pt, B, phi_clip, g, dphi, dw);
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
-#ifdef SB_GEN_SKIP0
       const int sgi = sb_gen_sign(M, p, k);
       if (!sgi) continue;                       /* warp-uniform */
       const double sg = (double)sgi;
-#else
-      const double sg = (double)sb_gen_sign(M, p, k);
-#endif
       gk[k] += sg * g; dphik[k] += sg * dphi;
 #pragma unroll
       for (int l = 0; l < NB; ++l) dwk[k * NB + l] += sg * dw[l];
@@ -634,6 +630,7 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   for (int k = 0; k < NB; ++k)
 #pragma unroll
     for (int t = 0; t < 9 + 6 * NB; ++t) mG[k][t] = 0.0;
+
   SbBandK K[NB > 0 ? NB : 1];
   bool need_u0;
   int trap;

@@ -235,20 +235,27 @@ k_moments(PlanDev pl, StateDev st, int nblk, double* vals) {
   const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
   if (same_rule && c_M.quad_m_super == 11) {
     /* common cases as straight-line instances (see sb_phaseA_band) */
-#ifdef SB_MOM_Q_SMEM
+#ifndef SB_MOM_Q_REGS
+    /* the 20 Q accumulators are touched once per rule row: in shared memory they free 40
+       registers for the interleaved exp chains of the row (fewer spills, 2.65 -> 2.50 ms) */
     __shared__ double s_q[SB_NQ][SB_TILE];
     double* qs = &s_q[0][threadIdx.x];
-#define SB_Q_READBACK for (int t = 0; t < SB_NQ; ++t) Q[t] = qs[t * SB_TILE]
 #else
     double* qs = nullptr;
-#define SB_Q_READBACK
 #endif
+    bool fastm = false;
     if (rho && dd && K.kind == SB_BAND_NONDEGENERATE) {
       sb_phaseA_band<11, 1>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
-      SB_Q_READBACK;
+      fastm = true;
     } else if (rho && dd && K.const_mob) {
       sb_phaseA_band<11, 2>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
-      SB_Q_READBACK;
+      fastm = true;
+    }
+    if (fastm) {
+      if (qs) {
+#pragma unroll
+        for (int t = 0; t < SB_NQ; ++t) Q[t] = qs[t * SB_TILE];
+      }
     }
     else if (rho || dd) sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
   } else if (same_rule) {
