@@ -34,8 +34,8 @@ UNIT = 'DOF/s'
 BYTES_PER_CELL = {'ib': 10396, 'pn': 7424}
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one assembly pass,
 # per cell, from the committed `ncu --set full` capture (profiles/r1_s2_kernels_summary.csv,
-# 320 396 IB cells: 3.667 GB read + 4.121 GB written over the 7 launches of one pass)
-NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): 7.788e9 / 320396.0}
+# 320 396 IB cells: 3.662 GB read + 3.970 GB written over the 7 launches of one pass)
+NCU_DRAM_BYTES_PER_CELL = {('ib', 'structural'): 7.632e9 / 320396.0}
 
 
 def parse_args():
