@@ -47,8 +47,11 @@ def parse_args():
     ap.add_argument('--nx', type=int, default=708, help='x points of the product mesh')
     ap.add_argument('--ny', type=int, default=708, help='y points per rank strip')
     ap.add_argument('--kind', default='ib', choices=['ib', 'pn'])
-    ap.add_argument('--pattern', default='structural', choices=['structural', 'dolfin'],
-                    help='CSR layout: structural non-zeros only (native) or dolfin dense cell blocks')
+    ap.add_argument('--pattern', default='native', choices=['native', 'structural', 'dolfin'],
+                    help="CSR layout: 'native' = structural non-zeros, columns in kernel emission "
+                         "order (closed-form kernels); 'structural' = same entries, ascending "
+                         "columns; 'dolfin' = dense cell blocks")
+    ap.add_argument('--no-e2e', action='store_true', help='kernel experiments: skip the host-buffer arm')
     ap.add_argument('--cpu-cells', type=int, default=40000,
                     help='cells of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -294,6 +297,12 @@ def run_b200(args):
     stage_ms = plan.last_stage_ms()
     k_ms = float(np.mean(kernel_ms))
     # end-to-end through the public API with host buffers
+    if args.no_e2e:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps(dict(ms_per_step=total_ms / args.steps, kernel_ms=k_ms, stage_ms=stage_ms,
+                                  native=plan.is_native(), cells=pa.n_cells, launches=int(launches))))
+        return
     pipe = make_pipe()
     for _ in range(3):
         step_e2e()
@@ -345,8 +354,10 @@ def run_b200(args):
                 x_points=int(len(np.unique(pa.mesh.coordinates[:, 0]))),
                 cells_per_gpu=pa.n_cells, dofs_per_gpu=pa.N, nnz_per_gpu=pa.csr.nnz,
                 sub_problems=pa.P, local_dofs=pa.L, optical_fields=pa.model.n_fields,
-                pattern=('structural non-zeros of the dolfin cell blocks' if pa.pattern == 'structural'
-                         else 'dolfin dense cell blocks'), numbering=pa.numbering,
+                pattern={'structural': 'structural non-zeros of the dolfin cell blocks, ascending columns',
+                         'native': 'structural non-zeros of the dolfin cell blocks, columns in emission order',
+                         'dolfin': 'dolfin dense cell blocks'}[pa.pattern],
+                numbering=pa.numbering, native_kernels=plan.is_native(),
                 parallelism=('y-strips x%d, NCCL ghost exchange %d B/rank/step' % (world, halo.bytes_per_exchange)) if world > 1 else 'single GPU',
                 l2='inputs (%.0f MB) and outputs (%.1f GB) far exceed the 126 MB L2'
                    % (h2d / 1e6, (alg_bytes) / 1e9),

@@ -171,6 +171,11 @@ int sb_assemble(sb_plan* plan, const sb_state* state,
                 double* d_vals, double* d_b, void* stream);
 int sb_plan_zero_values(sb_plan* plan, double* d_vals, void* stream);
 int64_t sb_plan_nnz(const sb_plan* plan);
+/* 1 when the plan runs the closed-form kernels (csrc/native.inl): dof numbering 'b200' and
+ * CSR pattern 'native' of simudo_b200/fem/dofmap.py (structural non-zeros of the dolfin
+ * pattern, columns of a row in emission order), Dirichlet dofs on boundary facets only.
+ * Any other numbering / pattern handed to sb_plan_create runs the generic kernels.      */
+int sb_plan_is_native(const sb_plan* plan);
 /* materialise the CSR column indices (int32) on the device: for export/solvers */
 int sb_plan_column_indices(sb_plan* plan, int32_t* d_colidx, void* stream);
 

@@ -83,6 +83,14 @@ class Oracle(object):
         self.n_threads = n_threads
         self._keep = []
         self.colidx = pa.csr.column_indices()
+        # the C restatement inserts by binary search in ascending columns (like PETSc's
+        # MatSetValues); layouts with another column order inside a row ('native') are
+        # assembled in sorted order and permuted back into the caller's layout
+        rp = pa.csr.rowptr
+        rows = np.repeat(np.arange(pa.N, dtype=np.int64), np.diff(rp))
+        self._perm = np.lexsort((self.colidx, rows))
+        self._sorted = bool((self._perm == np.arange(len(self._perm))).all())
+        self._colidx_sorted = np.ascontiguousarray(self.colidx[self._perm])
         self._rules = {}
         m = pa.model
         self.rule_default = self._make_rule(*fl.default_triangle_scheme(4))
@@ -115,7 +123,7 @@ class Oracle(object):
             cell_vertices=pa.cell_vertices, cell_tag=pa.cell_tag,
             cell_dofs=pa.cell_dofs, cell_neighbors=pa.cell_neighbors,
             cell_jump_mask=pa.cell_jump_mask, tag_params=pa.tag_params,
-            rowptr=pa.csr.rowptr, colidx=self.colidx, bc_dofs=pa.bc_dofs,
+            rowptr=pa.csr.rowptr, colidx=self._colidx_sorted, bc_dofs=pa.bc_dofs,
             natbc_cell=pa.natbc_cell, natbc_row=pa.natbc_row,
             facet_w=self.facet_w, facet_trace=self.facet_trace)
         nb, nc, nf = pa.model.n_bands, pa.n_cells, pa.model.n_fields
@@ -156,6 +164,10 @@ class Oracle(object):
                                        C.c_int((1 if want_A else 0) | (2 if want_b else 0)))
         if rc != 0:
             raise RuntimeError('oracle assembly failed')
+        if want_A and not self._sorted:
+            out = np.empty_like(vals)
+            out[self._perm] = vals
+            vals = out
         return vals, b
 
     def cell_tensors(self, cells, u, base_w=None, thmeq_phi=None, phi_opt=None):

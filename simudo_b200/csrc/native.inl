@@ -1,0 +1,794 @@
+/*
+ * native.inl -- the closed-form ("native") fast path of sb_assemble (included by
+ * pdd_kernels.cu).
+ *
+ * Same arithmetic as the generic kernels (NewtonSolution.A / .b,
+ * simudo/fem/newton_solver.py:61-77; forms poisson_drift_diffusion1.py1:42-47,264-303),
+ * for problems whose dof numbering and CSR layout are the library's own:
+ *
+ *   numbering 'b200'  cell c owns dofs 6P c + 6p + (0..2 DG1 | 3..5 interior BDM2); facet
+ *                     f owns dofs 6P Nc + 3P f + 3p + k            (fem/dofmap.py)
+ *   pattern 'native'  structural non-zeros only, the columns of a row in the emission
+ *                     order of these kernels (fem/dofmap.py: _native_ranks_of_row):
+ *                       DG1 row        [BDM(p) 0..11 | DG(q) q = 0..P-1]
+ *                       interior row   [BDM(p) 0..11 | DG(p) | DG(0) if p > 0]
+ *                       facet row      [3 dofs of the facet | run of cell A | run of cell B]
+ *
+ * so that (1) no dof map, row-pointer or rank table is read at all -- every address is a
+ * closed form of the cell index and three facet ids; (2) everything a cell contributes to
+ * a row is one contiguous run: the rows a cell owns (6P rows, one contiguous block of
+ * vals) leave the SM as cp.async.bulk copies (1-D TMA), its runs in the facet rows are
+ * flushed by the warp with lane = entry, no rank lookup; (3) the (facet dof, facet dof)
+ * 3 x 3 blocks two cells share are written once, by the facet's first cell, as its own
+ * block plus the neighbour's block -- k_moments_nat leaves every cell's blocks in the
+ * moment scratch -- so no slot is zeroed and no atomic touches the Jacobian.
+ *
+ * sb_plan_create verifies the closed forms entry by entry (detect_native) and falls back
+ * to the generic kernels otherwise ('ufc' numbering, dolfin / sorted patterns, Dirichlet
+ * dofs on interior facets).
+ */
+
+/* moment scratch of the native path, [quantity][cell]:
+ *   band k:   (k * SB_NAT_NA + q):  W 21 | Q 20 | Rx 6 | R 3 | S 18
+ *   then      generation moments   (nb * SB_NAT_NA + k * SB_NG + t)
+ *   then      S of the Poisson sub-problem, 18                                  */
+#define SB_NAT_NA 68
+#define SB_NAT_W 0
+#define SB_NAT_Q 21
+#define SB_NAT_RX 41
+#define SB_NAT_R 47
+#define SB_NAT_S 50
+
+__device__ __forceinline__ double* natA_ptr(const PlanDev& pl, int k, int64_t c) {
+  return pl.scratch + (int64_t)k * SB_NAT_NA * pl.n_cells + c;
+}
+__device__ __forceinline__ double* natG_ptr(const PlanDev& pl, int k, int64_t c) {
+  return pl.scratch + ((int64_t)pl.nb * SB_NAT_NA + (int64_t)k * SB_NG) * pl.n_cells + c;
+}
+__device__ __forceinline__ double* natS0_ptr(const PlanDev& pl, int64_t c) {
+  return pl.scratch + (int64_t)pl.nb * (SB_NAT_NA + SB_NG) * pl.n_cells + c;
+}
+
+/* (facet dof, facet dof) blocks of the cell's flux mass matrix <xi_i . xi_m c> / |detJ|:
+ * S[6 f + sym3(k, k')] for i = 3f + k, m = 3f + k'.  W = the 21 packed values of
+ * int c pi_r pi_s, or nullptr for c = 1 (plain BDM mass through Mhat).               */
+__device__ __forceinline__ void sb_facet_blocks(const SbTables& T, const SbCellGeom& g,
+                                                const double* W, double coef, double* S) {
+  const double sc = coef * g.iad;
+  if (!W) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int k2 = k; k2 < 3; ++k2) {
+          const double* mh = T.Mhat[3 * f + k][3 * f + k2];
+          S[6 * f + sb_sym3(k, k2)] = sc * (g.G11 * mh[0] + g.G12 * mh[1] + g.G22 * mh[2]);
+        }
+    return;
+  }
+#pragma unroll 1
+  for (int f = 0; f < 3; ++f) {
+    double Sf[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = 3 * f + k;
+      double GY[2][6];
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2) {
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          y0 += T.bdmC[i][0][r] * W[sb_sym21(r, s2)];
+          y1 += T.bdmC[i][1][r] * W[sb_sym21(r, s2)];
+        }
+        GY[0][s2] = (g.G11 * y0 + g.G12 * y1) * sc;
+        GY[1][s2] = (g.G12 * y0 + g.G22 * y1) * sc;
+      }
+#pragma unroll
+      for (int k2 = k; k2 < 3; ++k2) {
+        const int m = 3 * f + k2;
+        double v = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < 6; ++s2)
+          v = fma(GY[1][s2], T.bdmC[m][1][s2], fma(GY[0][s2], T.bdmC[m][0][s2], v));
+        Sf[sb_sym3(k, k2)] = v;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 6; ++t) S[6 * f + t] = Sf[t];
+  }
+}
+
+/* ---- phase A, native: thread = (cell, band) -------------------------------------------- */
+__global__ void __launch_bounds__(SB_TILE, SB_MB_MOM)
+k_moments_nat(PlanDev pl, StateDev st, int nblk) {
+  const int k = blockIdx.x / nblk;
+  const int64_t c = (int64_t)(blockIdx.x % nblk) * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  const int P = pl.P;
+  const int64_t nc = pl.n_cells;
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const SbBandK K = sb_band_consts(c_M, tp, k);
+  const bool dd = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+  const double* uc = st.u + (int64_t)6 * P * c;
+  double phi[3], dw[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { phi[i] = uc[i]; dw[i] = uc[6 * (1 + k) + i]; }
+  const double w0 = st.base_w[(int64_t)k * nc + c];
+  double gc[2][6];
+  if (dd) {
+    double jc[2][6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) jc[a][r] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      const double fm = (m < 9)
+          ? st.u[pl.nat_dofF0 + (int64_t)3 * P * pl.nat_fid[c * 3 + m / 3] + 3 * (1 + k) + m % 3]
+          : uc[6 * (1 + k) + 3 + (m - 9)];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) jc[a][r] += fm * c_T.bdmC[m][a][r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      gc[0][r] = g.G11 * jc[0][r] + g.G12 * jc[1][r];
+      gc[1][r] = g.G12 * jc[0][r] + g.G22 * jc[1][r];
+    }
+  }
+  const double chi0 = phi[0] + dw[0] + w0;
+  const double chix = (phi[1] - phi[0]) + (dw[1] - dw[0]);
+  const double chiy = (phi[2] - phi[0]) + (dw[2] - dw[0]);
+  double mC[SB_NMC], Q[SB_NQ], mRx[SB_NRX], mR[SB_NR] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int t = 0; t < SB_NMC; ++t) mC[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
+#pragma unroll
+  for (int t = 0; t < SB_NRX; ++t) mRx[t] = 0.0;
+  const bool rho = (K.N != 0.0);
+  const bool same_rule = (c_M.quad_m_rho == c_M.quad_m_super);
+  if (same_rule && c_M.quad_m_super == 11) {
+    __shared__ double s_q[SB_NQ][SB_TILE];
+    double* qs = &s_q[0][threadIdx.x];
+    bool fastm = false;
+    if (rho && dd && K.kind == SB_BAND_NONDEGENERATE) {
+      sb_phaseA_band<11, 1>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
+      fastm = true;
+    } else if (rho && dd && K.const_mob) {
+      sb_phaseA_band<11, 2>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx, qs);
+      fastm = true;
+    }
+    if (fastm) {
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = qs[t * SB_TILE];
+    } else if (rho || dd) {
+      sb_phaseA_band<11>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    }
+  } else if (same_rule) {
+    if (rho || dd) sb_phaseA_band<0>(c_T.sup, rho, dd, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+  } else {
+    if (rho) sb_phaseA_band<0>(c_T.rho, true, false, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+    if (dd) sb_phaseA_band<0>(c_T.sup, false, true, K, chi0, chix, chiy, gc, mC, Q, mR, mRx);
+  }
+  double* o = natA_ptr(pl, k, c);
+#pragma unroll
+  for (int t = 0; t < SB_NRX; ++t) o[(int64_t)(SB_NAT_RX + t) * nc] = mRx[t];
+#pragma unroll
+  for (int t = 0; t < SB_NR; ++t) o[(int64_t)(SB_NAT_R + t) * nc] = mR[t];
+  double S[18];
+  if (dd) {
+#pragma unroll
+    for (int t = 0; t < SB_NQ; ++t) o[(int64_t)(SB_NAT_Q + t) * nc] = Q[t];
+    double W[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < 15; ++t) v += c_T.G22u[e][t] * mC[t];
+      W[e] = v;
+      o[(int64_t)(SB_NAT_W + e) * nc] = v;
+    }
+    sb_facet_blocks(c_T, g, W, 1.0, S);
+  } else {
+    sb_facet_blocks(c_T, g, nullptr, c_M.ext_j_coef, S);
+  }
+#pragma unroll
+  for (int t = 0; t < 18; ++t) o[(int64_t)(SB_NAT_S + t) * nc] = S[t];
+  if (k == 0) {                                   /* Poisson <psi_i . psi_m> blocks */
+    sb_facet_blocks(c_T, g, nullptr, 1.0, S);
+    double* o0 = natS0_ptr(pl, c);
+#pragma unroll
+    for (int t = 0; t < 18; ++t) o0[(int64_t)t * nc] = S[t];
+  }
+}
+
+/* ---- phase B, native: thread = cell ---------------------------------------------------- */
+template <int NB>
+__global__ void __launch_bounds__(SB_TILE, SB_MB_GEN)
+k_generation_nat(PlanDev pl, StateDev st) {
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  if (c >= pl.n_cells) return;
+  constexpr int P = NB + 1;
+  const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
+  const double* uc = st.u + (int64_t)6 * P * c;
+  double dgv[1 + SB_MAX_BANDS][3];
+  double w0[SB_MAX_BANDS];
+  bool inside_k[SB_MAX_BANDS];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dgv[0][i] = uc[i];
+  bool any_inside = false;
+#pragma unroll
+  for (int k = 0; k < SB_MAX_BANDS; ++k) {
+    w0[k] = 0.0; inside_k[k] = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dgv[1 + k][i] = 0.0;
+    if (k < NB) {
+      w0[k] = st.base_w[(int64_t)k * pl.n_cells + c];
+      inside_k[k] = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
+      any_inside = any_inside || inside_k[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = uc[6 * (1 + k) + i];
+    }
+  }
+  if (!any_inside) return;                        /* nobody reads this cell's g moments */
+  double mG[NB > 0 ? NB : 1][SB_NG];
+  sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k, st.thmeq ? st.thmeq + c * 6 : nullptr,
+                    st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG, true);
+  const int64_t nc = pl.n_cells;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (!inside_k[k]) continue;
+    double* o = natG_ptr(pl, k, c);
+#pragma unroll
+    for (int t = 0; t < 9 + 6 * NB; ++t) o[(int64_t)t * nc] = mG[k][t];
+  }
+}
+
+/* ---- phase C, native --------------------------------------------------------------------
+ * thread = cell (arithmetic), warp = 32 cells (stores).  Per sub-problem PS a cell emits
+ *   group 0: its 3 DG rows, group 4: its 3 interior BDM rows -- one contiguous block of
+ *            vals each, staged in final order with the 16-byte phase of the global address
+ *            and copied out by cp.async.bulk;
+ *   group 1..3: its run in the 3 rows of facet 0..2 (3 + RB entries when it is the facet's
+ *            first cell, RB otherwise), staged [row][entry] and flushed by the warp with
+ *            lane = entry: one store instruction covers up to two row runs.           */
+#define SB_NAT_FROW 18                              /* staging slots per facet row */
+#define SB_NAT_STR(P) ((((3 * (12 + 3 * (P))) > 3 * SB_NAT_FROW ? (3 * (12 + 3 * (P))) : 3 * SB_NAT_FROW) + 2) | 1)
+
+struct SbNatMeta {
+  int64_t gb[3][32];        /* vals index of the cell's run in row k = 0 of facet f      */
+  int32_t rn[3][32];        /* row length | entries per run << 16 (0: nothing to store)  */
+};
+
+/* One BDM row I (compile-time: every table operand is a constant-bank immediate) of
+ * sub-problem PS in native order.  MODE 0 Poisson, 1 band inside its subdomain, 2 outside.
+ *   run  -> where the row's non-(facet, facet) entries start in the staging area
+ *   W    packed int c pi_r pi_s (MODE 1);  Q the 20 moments of c' g^a (MODE 1)
+ *   jc   Dubiner coefficients of the cell's flux, jc[b][s] = sum_m fl_m C_m[b][s]: the
+ *        flux part of the residual is sum GY_i[b][s] jc[b][s] (no second pass over fl)
+ * returns the residual of the row (jump term not included).                             */
+template <int PS, int MODE, int I>
+__device__ __forceinline__ double sb_nat_row(const SbTables& T, double g11, double g12, double g22,
+                                             double iad, double divsign, const double* W,
+                                             const double* Q, const double (*jc)[6],
+                                             const double* fl, const double* sl, double* run) {
+  constexpr int GRP = I < 9 ? I / 3 : 3;
+  constexpr int dg0 = GRP < 3 ? 9 : 12;
+  double Fi = 0.0;
+  if (MODE == 1) {
+    double GY0[6], GY1[6];
+#pragma unroll
+    for (int s2 = 0; s2 < 6; ++s2) {
+      double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        y0 = fma(T.bdmC[I][0][r], W[sb_sym21(r, s2)], y0);
+        y1 = fma(T.bdmC[I][1][r], W[sb_sym21(r, s2)], y1);
+      }
+      GY0[s2] = g11 * y0 + g12 * y1;
+      GY1[s2] = g12 * y0 + g22 * y1;
+      Fi = fma(GY1[s2], jc[1][s2], fma(GY0[s2], jc[0][s2], Fi));
+    }
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      if (GRP < 3 && m / 3 == GRP) continue;
+      double v = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < 6; ++s2)
+        v = fma(GY1[s2], T.bdmC[m][1][s2], fma(GY0[s2], T.bdmC[m][0][s2], v));
+      run[GRP < 3 ? (m < 3 * GRP ? m : m - 3) : m] = v;
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const double dv = divsign * T.Dhat[I][l];
+      Fi = fma(dv, sl[l], Fi);
+      double d = 0.0;
+#pragma unroll
+      for (int t = 0; t < 20; ++t) d = fma(T.D3[I][l][t], Q[t], d);
+      d *= iad;
+      run[dg0 + l] = dv + d;
+      run[dg0 + 3 + l] = d;
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 12; ++m) {
+      const double v = g11 * T.Mhat[I][m][0] + g12 * T.Mhat[I][m][1] + g22 * T.Mhat[I][m][2];
+      Fi = fma(v, fl[m], Fi);
+      if (GRP < 3 && m / 3 == GRP) continue;
+      run[GRP < 3 ? (m < 3 * GRP ? m : m - 3) : m] = v;
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      if (MODE == 0) {
+        const double dv = divsign * T.Dhat[I][l];
+        Fi = fma(dv, sl[l], Fi);
+        run[dg0 + l] = dv;
+      } else {                                   /* structural entries that vanish outside */
+        run[dg0 + l] = 0.0;
+        run[dg0 + 3 + l] = 0.0;
+      }
+    }
+  }
+  return Fi;
+}
+
+/* compiler-only fence between the unrolled rows: without it ptxas interleaves the rows of a
+ * group for ILP and spills their operands */
+#if defined(__CUDA_ARCH__)
+#define SB_ROW_FENCE() asm volatile("" ::: "memory")
+#else
+#define SB_ROW_FENCE() ((void)0)
+#endif
+
+/* the three BDM rows of group GRP (0..2: facet GRP, 3: interior) into st[k * rowstr + ..];
+ * lead: 3 when the staged run starts with the 3 (facet, facet) entries (this cell is the
+ * facet's first cell), else 0; S: their values (own + neighbour block, packed symmetric).
+ * g11, g12, g22: J^T J scaled by coef / |detJ|; divsign: sign of the divergence block (0:
+ * none, band outside its subdomain); iad: 1 / |detJ|.                                     */
+template <int PS, int MODE, int GRP>
+__device__ __forceinline__ void sb_nat_flux_group(
+    const SbTables& T, double g11, double g12, double g22, double iad, double divsign,
+    const double* W, const double* Q, const double (*jc)[6], const double* fl, const double* sl,
+    double jf, int lead, const double* S, double* st, int rowstr, double* Fout) {
+  if (GRP < 3 && lead) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int k2 = 0; k2 < 3; ++k2) st[k * rowstr + k2] = S[sb_sym3(k, k2)];
+  }
+  Fout[0] = sb_nat_row<PS, MODE, 3 * GRP + 0>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
+                                              st + lead);
+  SB_ROW_FENCE();
+  Fout[1] = sb_nat_row<PS, MODE, 3 * GRP + 1>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
+                                              st + rowstr + lead);
+  SB_ROW_FENCE();
+  Fout[2] = sb_nat_row<PS, MODE, 3 * GRP + 2>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
+                                              st + 2 * rowstr + lead);
+  if (MODE == 1 && GRP < 3) {                     /* base_w jump: facet dofs */
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Fout[k] -= jf * T.trI[k];
+  }
+}
+
+/* warp flush of one staged facet group: cell after cell, lane = (row, entry) */
+__device__ __forceinline__ void sb_nat_flush_facet(const SbNatMeta& meta, int f, const double* wst,
+                                                   int str, double* __restrict__ vals, int lane) {
+  const int k0 = lane / SB_NAT_FROW, e0 = lane - k0 * SB_NAT_FROW;           /* slot lane      */
+  const int s1 = lane + 32;
+  const int k1 = s1 / SB_NAT_FROW, e1 = s1 - k1 * SB_NAT_FROW;               /* slot lane + 32 */
+  const bool has1 = s1 < 3 * SB_NAT_FROW;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const int32_t rn = meta.rn[f][i];
+    const int n = rn >> 16, rl = rn & 0xFFFF;
+    if (n == 0) continue;                                   /* warp-uniform */
+    double* base = vals + meta.gb[f][i];
+    const double* src = wst + i * str;
+    if (e0 < n) base[k0 * rl + e0] = src[lane];
+    if (has1 && e1 < n) base[k1 * rl + e1] = src[s1];
+  }
+}
+
+/* the 12 BDM rows of one cell and sub-problem: three facet groups (staged, flushed by the
+ * warp) and the interior group (bulk copy); see k_rows_nat                                */
+template <int NB, int PS, int MODE>
+__device__ __forceinline__ void sb_nat_flux_part(
+    const PlanDev& pl, const StateDev& st, double* __restrict__ vals, double* __restrict__ b,
+    const SbNatMeta& meta, double* wst, double* stg, double* stg16, int lane, int64_t cc,
+    bool active, bool bulk, int32_t finfo, const int32_t* fid, const SbCellGeom& g,
+    const double* fl, const double* sl, bool inside, int64_t g0, int64_t dof0) {
+  constexpr int P = NB + 1;
+  constexpr int RDG = 12 + 3 * P;
+  constexpr int RI = PS == 0 ? 15 : 18;
+  constexpr int STR = SB_NAT_STR(P);
+  constexpr int kb = PS > 0 ? PS - 1 : 0;
+  const int64_t nc = pl.n_cells;
+  double W[21], Q[SB_NQ], jc[2][6];
+  double jumpf[3] = {0.0, 0.0, 0.0};
+  double sc = g.iad, divsign = (MODE == 0) ? -g.sdet : g.sdet;
+  const double* sa_base = (PS == 0) ? natS0_ptr(pl, cc) : natA_ptr(pl, kb, cc) + (int64_t)SB_NAT_S * nc;
+  if (MODE == 1) {
+    if (inside) {
+      const double* o = natA_ptr(pl, kb, cc);
+#pragma unroll
+      for (int e = 0; e < 21; ++e) W[e] = o[(int64_t)(SB_NAT_W + e) * nc];
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NAT_Q + t) * nc];
+      const double w0 = st.base_w[(int64_t)kb * nc + cc];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        if ((finfo >> (12 + 4 * f + kb)) & 1) {
+          const int64_t cn = pl.cell_neighbors[cc * 3 + f];
+          const double ref_out = (f == 1) ? -1.0 : 1.0;
+          jumpf[f] = (st.base_w[(int64_t)kb * nc + cn] - w0) * ref_out * g.sdet;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int s2 = r; s2 < 6; ++s2) W[sb_sym21(r, s2)] = (r == s2) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
+      sc = c_M.ext_j_coef * g.iad;
+      divsign = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double v = 0.0;
+#pragma unroll
+        for (int m = 0; m < 12; ++m) v = fma(fl[m], c_T.bdmC[m][a][r], v);
+        jc[a][r] = v;
+      }
+  } else if (MODE == 2) {
+    sc = c_M.ext_j_coef * g.iad;
+  }
+  const double g11 = g.G11 * sc, g12 = g.G12 * sc, g22 = g.G22 * sc;
+
+#define SB_NAT_FACET_GROUP(GRP)                                                              \
+  {                                                                                          \
+    const int bits = (finfo >> (4 * GRP)) & 3;                                               \
+    const int lead = (bits & 2) ? 0 : 3;                                                     \
+    double S[6];                                                                             \
+    if (lead) {                                                                              \
+      _Pragma("unroll") for (int t = 0; t < 6; ++t) S[t] = sa_base[(int64_t)(6 * GRP + t) * nc]; \
+      if (bits == 0) {                            /* interior facet, this cell is first */  \
+        const int64_t cn = pl.cell_neighbors[cc * 3 + GRP];                                  \
+        const int f2 = (finfo >> (4 * GRP + 2)) & 3;                                         \
+        const double* sn = sa_base + (cn - cc);                                              \
+        _Pragma("unroll") for (int t = 0; t < 6; ++t) S[t] += sn[(int64_t)(6 * f2 + t) * nc]; \
+      }                                                                                      \
+    }                                                                                        \
+    double Fr[3];                                                                            \
+    sb_bulk_wait_read();                          /* previous bulk copy has left the slot */ \
+    if (active) {                                                                            \
+      sb_nat_flux_group<PS, MODE, GRP>(c_T, g11, g12, g22, g.iad, divsign, W, Q, jc, fl, sl, \
+                                       jumpf[GRP], lead, S, stg, SB_NAT_FROW, Fr);           \
+      if (b) {                                                                               \
+        double* bd = b + pl.nat_dofF0 + (int64_t)3 * P * fid[GRP] + 3 * PS;                  \
+        _Pragma("unroll") for (int k = 0; k < 3; ++k) SB_ATOMIC_ADD(bd + k, Fr[k]);          \
+      }                                                                                      \
+    }                                                                                        \
+    __syncwarp();                                                                            \
+    if (vals) sb_nat_flush_facet(meta, GRP, wst, STR, vals, lane);                           \
+    __syncwarp();                                                                            \
+  }
+  SB_NAT_FACET_GROUP(0)
+  SB_NAT_FACET_GROUP(1)
+  SB_NAT_FACET_GROUP(2)
+#undef SB_NAT_FACET_GROUP
+
+  /* interior BDM rows: owned, bulk copy */
+  {
+    const int64_t g1 = g0 + 3 * RDG;
+    const int ph = (int)(g1 & 1);
+    double* sd = stg16 + ph;
+    double Fr[3];
+    if (active) {
+      sb_nat_flux_group<PS, MODE, 3>(c_T, g11, g12, g22, g.iad, divsign, W, Q, jc, fl, sl, 0.0, 0,
+                                     nullptr, sd, RI, Fr);
+      if (b) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) b[dof0 + 3 + k] = Fr[k];
+      }
+    }
+    if (bulk) sb_bulk_store_owned(vals + g1, stg16, ph, 3 * RI);
+  }
+}
+
+template <int NB, int PS>
+__global__ void __launch_bounds__(SB_TILE, SB_MB_ROWS)
+k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restrict__ b) {
+#ifdef SB_EMUL_BUILD
+  unsigned char* s_dyn = emul::dyn_smem();
+#else
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+#endif
+  constexpr int P = NB + 1;
+  constexpr int RDG = 12 + 3 * P;                 /* DG row length                      */
+  constexpr int RI = PS == 0 ? 15 : 18;           /* interior BDM row length            */
+  constexpr int RB = PS == 0 ? 12 : 15;           /* a cell's run in a facet row        */
+  constexpr int STR = SB_NAT_STR(P);              /* staging doubles per lane (odd)     */
+  constexpr int CB = 3 * RDG * P + 45 + 54 * (P - 1);   /* owned values per cell        */
+  constexpr int OFF_DG = PS == 0 ? 0 : (3 * RDG + 45) + (PS - 1) * (3 * RDG + 54);
+  constexpr int kb = PS > 0 ? PS - 1 : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wst = reinterpret_cast<double*>(s_dyn) + (size_t)warp * 32 * STR;
+  SbNatMeta& meta = reinterpret_cast<SbNatMeta*>(s_dyn + sizeof(double) * 32 * STR * (SB_TILE / 32))[warp];
+  double* stg = wst + lane * STR;                 /* this lane's slot                   */
+  double* stg16 = stg + (lane & 1);               /* 16-byte aligned (STR is odd)       */
+  const int64_t nc = pl.n_cells;
+  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  const int64_t cc = c < nc ? c : nc - 1;
+  const bool active = (c < nc) && (pl.cell_special[cc] < 0);
+  const int32_t finfo = pl.nat_finfo[cc];
+  const bool inside = (PS == 0) ? true : (((finfo >> (24 + kb)) & 1) != 0);
+  int32_t fid[3];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) fid[f] = pl.nat_fid[cc * 3 + f];
+  const SbCellGeom g = sb_geom(pl.cell_vertices + cc * 6);
+  const double* uc = st.u + (int64_t)6 * P * cc + 6 * PS;
+  double fl[12], sl[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { sl[i] = uc[i]; fl[9 + i] = uc[3 + i]; }
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * P * fid[f] + 3 * PS;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fl[3 * f + k] = uf[k];
+  }
+  /* flush metadata of the three facet groups */
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    const int bits = (finfo >> (4 * f)) & 3;
+    const bool bnd = bits & 1, second = bits & 2;
+    const int rl = bnd ? (PS == 0 ? 15 : 18) : (PS == 0 ? 27 : 33);
+    const int rowoff = PS == 0 ? 0 : (bnd ? 45 + 3 * (PS - 1) * 18 : 81 + 3 * (PS - 1) * 33);
+    meta.gb[f][lane] = pl.nat_fbase[fid[f]] + rowoff + (second ? 3 + RB : 0);
+    const int n = (active && vals != nullptr) ? (second ? RB : RB + 3) : 0;
+    meta.rn[f][lane] = rl | (n << 16);
+  }
+  const int64_t g0 = cc * CB + OFF_DG;            /* vals index of the DG block          */
+  const int64_t dof0 = (int64_t)6 * P * cc + 6 * PS;
+  const bool bulk = active && vals != nullptr;
+
+  /* ---- group 0: DG rows ----------------------------------------------------------- */
+  {
+    const int ph = (int)(g0 & 1);
+    double* sd = stg16 + ph;
+    double F[3] = {0.0, 0.0, 0.0};
+    if (PS == 0 || inside) {
+      double mom[9 + 6 * (NB > 0 ? NB : 1)];     /* [0..2] P1 source | [3 + 6q ..] d/d(q) */
+      double coef;
+      if (PS == 0) {
+#pragma unroll
+        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NB; ++kk) {
+          const double* o = natA_ptr(pl, kk, cc);
+#pragma unroll
+          for (int t = 0; t < SB_NRX; ++t) {
+            const double v = o[(int64_t)(SB_NAT_RX + t) * nc];
+            mom[3 + t] += v;
+            mom[3 + 6 * (1 + kk) + t] = v;
+          }
+#pragma unroll
+          for (int t = 0; t < SB_NR; ++t) mom[t] += o[(int64_t)(SB_NAT_R + t) * nc];
+        }
+        const double* tp = pl.tag_params + (int64_t)pl.cell_tag[cc] * SB_TAG_STRIDE;
+        mom[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
+        coef = -g.adet;
+      } else {
+        const double* og = natG_ptr(pl, kb, cc);
+#pragma unroll
+        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = og[(int64_t)t * nc];
+        coef = -(double)c_M.band_sign[kb] * c_M.e_charge * g.adet;
+      }
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double Fi = 0.0;
+#pragma unroll
+          for (int m = 0; m < 12; ++m) {
+            const double dv = g.sdet * c_T.Dhat[m][i];
+            Fi += dv * fl[m];
+            sd[i * RDG + m] = dv;
+          }
+#pragma unroll
+          for (int t = 0; t < 3; ++t) Fi += coef * c_T.G1[i][t] * mom[t];
+#pragma unroll
+          for (int q = 0; q < 1 + NB; ++q)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+              double v = 0.0;
+#pragma unroll
+              for (int t = 0; t < 6; ++t) v += c_T.G11[i][l][t] * mom[3 + 6 * q + t];
+              sd[i * RDG + 12 + 3 * q + l] = coef * v;
+            }
+          F[i] = Fi;
+        }
+      }
+    } else if (active) {                          /* band outside its subdomain (:285-286) */
+      const double c1 = c_M.ext_w_coef * g.adet;
+#pragma unroll
+      for (int e = 0; e < 3 * RDG; ++e) sd[e] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const double v = c1 * c_T.M1[i][l];
+          F[i] += v * sl[l];
+          sd[i * RDG + 12 + 3 * PS + l] = v;
+        }
+    }
+    if (active && b) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) b[dof0 + i] = F[i];
+    }
+    if (bulk) sb_bulk_store_owned(vals + g0, stg16, ph, 3 * RDG);
+  }
+
+  /* ---- flux rows ------------------------------------------------------------------- *
+   * PS = 0: plain BDM mass (MODE 0).  PS > 0: one moment-driven code path (MODE 1) for the
+   * whole warp -- a lane outside the band's subdomain runs it with W = identity, Q = 0, no
+   * divergence block and the penalty coefficient, which is exactly the out-of-subdomain
+   * form (:288-289) -- except when no lane of the warp is inside: then the cheap MODE 2.
+   * (A per-lane branch between the two would keep both operand sets live: spills.)       */
+  if (PS == 0) {
+    sb_nat_flux_part<NB, PS, 0>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                finfo, fid, g, fl, sl, true, g0, dof0);
+  } else {
+    const bool any_in = __any_sync(0xffffffffu, inside && active);
+    if (any_in)
+      sb_nat_flux_part<NB, PS, 1>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                  finfo, fid, g, fl, sl, inside, g0, dof0);
+    else
+      sb_nat_flux_part<NB, PS, 2>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                  finfo, fid, g, fl, sl, false, g0, dof0);
+  }
+  sb_bulk_wait_read();                            /* the slot may be reused once it was read */
+}
+
+/* launch k_rows_nat<NB, PS> for PS = NB .. 0 */
+template <int NB, int PS>
+struct NatRowsLauncher {
+  static void go(const PlanDev& d, const StateDev& sd, double* vals, double* b, unsigned nblk,
+                 cudaStream_t s) {
+    const size_t smem = (sizeof(double) * 32 * SB_NAT_STR(NB + 1) + sizeof(SbNatMeta)) * (SB_TILE / 32);
+    cudaFuncSetAttribute(k_rows_nat<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SB_LAUNCH((k_rows_nat<NB, PS>), nblk, SB_TILE, smem, s, d, sd, vals, b);
+    NatRowsLauncher<NB, PS - 1>::go(d, sd, vals, b, nblk, s);
+  }
+};
+template <int NB>
+struct NatRowsLauncher<NB, -1> {
+  static void go(const PlanDev&, const StateDev&, double*, double*, unsigned, cudaStream_t) {}
+};
+
+/* ---- host: does the problem have the closed-form layout? ------------------------------- *
+ * On success fills fid [nc][3], finfo [nc], fbase [nf] and returns true.                   */
+static bool detect_native(const sb_model* model, const sb_problem* pr, std::vector<int32_t>& fid,
+                          std::vector<int32_t>& finfo, std::vector<int64_t>& fbase, int64_t* dofF0) {
+  const int P = pr->P, L = 15 * P;
+  const int64_t nc = pr->n_cells, N = pr->n_dofs;
+  if (!model->bands_have_dofs || P < 2 || getenv("SIMUDO_B200_NO_NATIVE")) return false;
+  const int64_t F0 = (int64_t)6 * P * nc;
+  if (N <= F0 || (N - F0) % (3 * P) != 0) return false;
+  const int64_t nf = (N - F0) / (3 * P);
+  const int RDG = 12 + 3 * P;
+  const int64_t CB = (int64_t)3 * RDG * P + 45 + 54 * (P - 1);
+  const int32_t* cd = pr->h_cell_dofs;
+  const int64_t* rp = pr->h_rowptr;
+  fid.assign((size_t)nc * 3, -1);
+  finfo.assign((size_t)nc, 0);
+  fbase.assign((size_t)nf, -1);
+  /* dof numbering */
+  for (int64_t c = 0; c < nc; ++c) {
+    const int32_t* d = cd + c * L;
+    for (int f = 0; f < 3; ++f) {
+      const int64_t q = (int64_t)d[3 + 3 * f] - F0;
+      if (q < 0 || q % (3 * P) != 0) return false;
+      fid[c * 3 + f] = (int32_t)(q / (3 * P));
+    }
+    for (int p = 0; p < P; ++p) {
+      for (int i = 0; i < 3; ++i) {
+        if (d[15 * p + i] != 6 * P * c + 6 * p + i) return false;
+        if (d[15 * p + 12 + i] != 6 * P * c + 6 * p + 3 + i) return false;
+      }
+      for (int f = 0; f < 3; ++f)
+        for (int k = 0; k < 3; ++k)
+          if (d[15 * p + 3 + 3 * f + k] != F0 + (int64_t)3 * P * fid[c * 3 + f] + 3 * p + k) return false;
+    }
+  }
+  /* facet sides: first cell = lower index; neighbour's local facet */
+  std::vector<uint8_t> fbnd((size_t)nf, 0);
+  for (int64_t c = 0; c < nc; ++c) {
+    int32_t info = 0;
+    for (int f = 0; f < 3; ++f) {
+      const int64_t cn = pr->h_cell_neighbors[c * 3 + f];
+      if (cn >= nc || cn == c) return false;
+      if (cn < 0) { info |= 1 << (4 * f); fbnd[fid[c * 3 + f]] = 1; continue; }
+      int f2 = -1;
+      for (int q = 0; q < 3; ++q)
+        if (fid[cn * 3 + q] == fid[c * 3 + f] && pr->h_cell_neighbors[cn * 3 + q] == c) f2 = q;
+      if (f2 < 0) return false;
+      if (cn < c) info |= 2 << (4 * f);
+      info |= f2 << (4 * f + 2);
+      info |= (int32_t)(pr->h_cell_jump_mask[c * 3 + f] & 0xF) << (12 + 4 * f);
+    }
+    const double* tpc = pr->h_tag_params + (size_t)pr->h_cell_tag[c] * SB_TAG_STRIDE;
+    for (int k = 0; k < model->n_bands; ++k)
+      if (tpc[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0) info |= 1 << (24 + k);
+    finfo[c] = info;
+  }
+  /* row pointers */
+  for (int64_t c = 0; c < nc; ++c) {
+    int64_t off = c * CB;
+    for (int p = 0; p < P; ++p) {
+      for (int i = 0; i < 3; ++i, off += RDG)
+        if (rp[6 * P * c + 6 * p + i] != off) return false;
+      const int ri = p == 0 ? 15 : 18;
+      for (int i = 0; i < 3; ++i, off += ri)
+        if (rp[6 * P * c + 6 * p + 3 + i] != off) return false;
+    }
+    if (rp[6 * P * (c + 1)] != off) return false;
+  }
+  for (int64_t f = 0; f < nf; ++f) {
+    int64_t off = rp[F0 + 3 * P * f];
+    fbase[f] = off;
+    for (int p = 0; p < P; ++p) {
+      const int rl = fbnd[f] ? (p == 0 ? 15 : 18) : (p == 0 ? 27 : 33);
+      for (int k = 0; k < 3; ++k, off += rl)
+        if (rp[F0 + 3 * P * f + 3 * p + k] != off) return false;
+    }
+    if (rp[F0 + 3 * P * (f + 1)] != off) return false;
+  }
+  /* rank patterns: once per (pattern id, side bits) */
+  std::vector<uint8_t> checked((size_t)pr->n_patterns * 8, 0);
+  for (int64_t c = 0; c < nc; ++c) {
+    int side = 0;
+    for (int f = 0; f < 3; ++f) if ((finfo[c] >> (4 * f)) & 2) side |= 1 << f;
+    const int32_t q = pr->h_cell_pattern[c];
+    if (q < 0 || q >= pr->n_patterns) return false;
+    if (checked[(size_t)q * 8 + side]) continue;
+    checked[(size_t)q * 8 + side] = 1;
+    const uint8_t* pat = pr->h_patterns + (size_t)q * L * L;
+    for (int i = 0; i < L; ++i) {
+      const int p = i / 15, r = i % 15;
+      const int fr = (r >= 3 && r < 12) ? (r - 3) / 3 : -1;
+      const int nrun = p == 0 ? 12 : 15;
+      for (int j = 0; j < L; ++j) {
+        const int pj = j / 15, rj = j % 15;
+        int want = 0xFF;
+        if (rj >= 3) {                                   /* BDM column */
+          if (pj == p) {
+            const int m = rj - 3;
+            if (fr < 0) want = m;
+            else if (m / 3 == fr) want = m - 3 * fr;
+            else want = 3 + (m < 3 * fr ? m : m - 3);
+          }
+        } else if (r < 3) {
+          want = 12 + 3 * pj + rj;                       /* DG row: DG(q) of every q */
+        } else if (pj == p || pj == 0) {
+          want = (fr < 0 ? 12 : 12) + rj + ((pj == 0 && p > 0) ? 3 : 0);
+        }
+        if (want != 0xFF && fr >= 0 && ((side >> fr) & 1) && want >= 3) want += nrun;
+        if (pat[i * L + j] != want) return false;
+      }
+    }
+  }
+  /* Dirichlet dofs: boundary facets only */
+  for (int64_t i = 0; i < pr->n_bc; ++i) {
+    const int64_t d = pr->h_bc_dofs[i];
+    if (d < F0 || !fbnd[(d - F0) / (3 * P)]) return false;
+  }
+  *dofF0 = F0;
+  return true;
+}

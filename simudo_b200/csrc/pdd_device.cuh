@@ -555,7 +555,7 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
                            const double* dgv, const double* w0, const SbBandK* K,
                            bool need_u0, int trap, double beta_pt,
                            const double* thmeq6, const double* phi_opt, int64_t field_stride,
-                           double* gk, double* dphik, double* dwk) {
+                           double* gk, double* dphik, double* dwk, uint32_t pmask = 0xFFFFFFFFu) {
   const double X = T.gX[n], Y = T.gY[n];
   const double l0 = 1.0 - X - Y;
   const double phi = dgv[0] * l0 + dgv[1] * X + dgv[2] * Y;
@@ -603,6 +603,7 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
   }
 #pragma unroll 1
   for (int p = 0; p < M.n_procs; ++p) {
+    if (!((pmask >> p) & 1u)) continue;         /* process switched off in this cell's region */
     double g, dphi, dw[NB > 0 ? NB : 1];
     sb_process_point<NB>(M, tp, p, beta_pt, B, phi_clip, g, dphi, dw);
 #pragma unroll
@@ -625,7 +626,7 @@ template <int NB>
 SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
                          const double (*dgv)[3], const double* w0, const bool* inside,
                          const double* thmeq6, const double* phi_opt, int64_t field_stride,
-                         double (*mG)[SB_NG]) {
+                         double (*mG)[SB_NG], bool region_mask = false) {
 #pragma unroll
   for (int k = 0; k < NB; ++k)
 #pragma unroll
@@ -635,6 +636,26 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   bool need_u0;
   int trap;
   sb_phaseB_scan(M, need_u0, trap);
+  /* Processes whose parameters are all zero in this cell's region (missing Spatial rule =
+     0.0, fem/expr.py:148-153: e.g. the IB processes outside the IB layer) contribute exact
+     zeros: skip them.  SRH divides by its lifetimes and is never skipped.              */
+  uint32_t pmask = 0xFFFFFFFFu;
+  if (region_mask) {
+    pmask = 0u;
+    bool any_trap = false;
+    for (int p = 0; p < M.n_procs; ++p) {
+      const double* pp = tp + SB_TP_PROC0 + 8 * p;
+      bool on = (M.proc_kind[p] == SB_PROC_SRH) || pp[SB_TPP_P0] != 0.0;
+#pragma unroll
+      for (int f = 0; f < SB_MAX_FIELDS; ++f) on = on || pp[SB_TPP_FIELD0 + f] != 0.0;
+      if (on) {
+        pmask |= 1u << p;
+        any_trap = any_trap || M.proc_kind[p] == SB_PROC_SR_TRAP ||
+                   (M.proc_kind[p] == SB_PROC_RAD_IB && M.proc_radiative[p]);
+      }
+    }
+    if (!any_trap) trap = -1;                   /* no expm1 against the trap band needed */
+  }
   const double beta_pt = 1.0 / tp[SB_TP_KT];
 #pragma unroll
   for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
@@ -646,7 +667,7 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   for (int n = 0; n < T.ng; ++n) {
     double gk[NB > 0 ? NB : 1], dphik[NB > 0 ? NB : 1], dwk[NB > 0 ? NB * NB : 1];
     sb_phaseB_point<NB>(T, M, tp, n, &dgv[0][0], w0, K, need_u0, trap, beta_pt, thmeq6, phi_opt,
-                        field_stride, gk, dphik, dwk);
+                        field_stride, gk, dphik, dwk, pmask);
     const double* wp = T.gwpsi[n];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -678,7 +699,16 @@ struct SbIO {
   uint32_t mhi;              /* bits 64..74                                 */
   double* vals;              /* may be NULL                                 */
   double* b;                 /* may be NULL                                 */
+  /* native layout (csrc/native.inl): the (facet dof, facet dof) block of an interior facet
+     is written once, by the facet's first cell, as own + neighbour contribution         */
+  int nat;                   /* 0: two cells add atomically onto zeroed slots          */
+  int32_t finfo;             /* per local facet f, bits 4f..: 1 boundary, 2 second cell */
+  const double* snb;         /* [3][6] neighbour's block of this sub-problem per facet */
 };
+
+SB_HD constexpr int sb_sym3(int k, int k2) {      /* packed index of a symmetric 3 x 3 */
+  return (k <= k2) ? (k * 3 - (k * (k - 1)) / 2 + (k2 - k)) : (k2 * 3 - (k2 * (k2 - 1)) / 2 + (k - k2));
+}
 
 SB_HD bool sb_is_bc(const SbIO& io, int l) {
   return l < 64 ? ((io.mlo >> l) & 1ull) : ((io.mhi >> (l - 64)) & 1u);
@@ -716,8 +746,18 @@ SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, do
   double* dst = io.vals + rowbase + rk;
   /* two cells add into the same slot only for (facet dof, facet dof) pairs of
      one facet; two addends onto a zeroed slot commute -> deterministic       */
-  if (fi >= 0 && sb_local_facet(j) == fi) SB_ATOMIC_ADD(dst, val);
-  else *dst = val;
+  if (fi >= 0 && sb_local_facet(j) == fi) {
+    if (io.nat) {
+      const int bits = (io.finfo >> (4 * fi)) & 3;
+      if (bits & 2) return;                                   /* the first cell writes it */
+      if (!(bits & 1)) val += io.snb[6 * fi + sb_sym3((i % 15 - 3) % 3, (j % 15 - 3) % 3)];
+      *dst = val;
+    } else {
+      SB_ATOMIC_ADD(dst, val);
+    }
+  } else {
+    *dst = val;
+  }
 }
 
 /* final residual value of local row i */
@@ -758,7 +798,8 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
                         const double* mC, const double* Q,
                         const double* fl /*[12] flux dofs*/, const double* sl /*[3] scalar dofs*/,
                         double jump0, double jump1, double jump2,
-                        const int32_t* nat_row, const double* nat_val, int nb0, int nb1) {
+                        const int32_t* nat_row, const double* nat_val, int nb0, int nb1,
+                        bool mC_is_W = false /* mC already holds the 21 values of W */) {
   const int r0 = sb_lbdm(p, 0);
   double W[21];
   double V[2][6][3];
@@ -766,8 +807,12 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
 #pragma unroll
     for (int e = 0; e < 21; ++e) {
       double v = 0.0;
+      if (mC_is_W) {
+        v = mC[e];
+      } else {
 #pragma unroll
-      for (int t = 0; t < 15; ++t) v += T.G22u[e][t] * mC[t];
+        for (int t = 0; t < 15; ++t) v += T.G22u[e][t] * mC[t];
+      }
       W[e] = v;
     }
 #pragma unroll

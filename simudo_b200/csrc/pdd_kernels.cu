@@ -74,6 +74,16 @@ struct PlanDev {
   const int32_t* natbc_row;      /* sorted by cell                           */
   const SbTables* tables;        /* global copy for lane-varying indexing    */
   double* scratch;               /* [(nb*44 + nb_dof*SB_NG)][n_cells] moments  */
+  /* closed-form layout (native.inl): 'b200' numbering + 'native' pattern      */
+  int native;
+  const int32_t* nat_fid;        /* [n_cells][3] facet ids                    */
+  const int32_t* nat_finfo;      /* [n_cells] per local facet f, bits 4f..: 1 boundary,
+                                    2 this cell is the facet's second cell, (4|8) the
+                                    facet's local number inside the neighbour; bits
+                                    12 + 4f + k: base_w jump of band k on facet f ('+' side);
+                                    bits 24 + k: cell inside the subdomain of band k */
+  const int64_t* nat_fbase;      /* [n_facets] vals index of the facet's row block */
+  int64_t nat_dofF0;             /* first facet dof = 6 P n_cells             */
 };
 
 struct sb_plan {
@@ -151,6 +161,8 @@ __device__ __forceinline__ double* momG_ptr(const PlanDev& pl, int k, int64_t c)
 #ifndef SB_MB_ROWS
 #define SB_MB_ROWS 2
 #endif
+#include "native.inl"
+
 /* zero the (facet dof, facet dof) Jacobian slots of sub-problem p on the facets this
  * cell owns (boundary facet, or lower cell index of the pair): both cells of a facet
  * atomically add into them later in the stream */
@@ -338,6 +350,21 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
   io.u = st.u; io.bc_values = st.bc_values;
   io.vals = vals; io.b = b;
   io.mlo = 0; io.mhi = 0; io.bcidx = nullptr;
+  io.nat = pl.native; io.finfo = 0; io.snb = nullptr;
+  double snb[18];
+  if (pl.native) {
+    /* the neighbours' (facet, facet) blocks of this sub-problem, for the facets this
+       cell writes (native.inl) */
+    io.finfo = pl.nat_finfo[c];
+    for (int f = 0; f < 3; ++f) {
+      const bool mine = ((io.finfo >> (4 * f)) & 3) == 0;
+      const int64_t cn = mine ? pl.cell_neighbors[c * 3 + f] : c;
+      const int f2 = (io.finfo >> (4 * f + 2)) & 3;
+      const double* sn = (p == 0) ? natS0_ptr(pl, cn) : natA_ptr(pl, p - 1, cn) + (int64_t)SB_NAT_S * nc;
+      for (int t = 0; t < 6; ++t) snb[6 * f + t] = mine ? sn[(int64_t)(6 * f2 + t) * nc] : 0.0;
+    }
+    io.snb = snb;
+  }
   int nb0 = 0, nb1 = 0;
   const int32_t spc = pl.cell_special[c];
   if (spc >= 0) {
@@ -364,15 +391,16 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
 #pragma unroll
       for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
     for (int k = 0; k < pl.nb; ++k) {
-      const double* o = momA_ptr(pl, k, c);
+      const double* o = pl.native ? natA_ptr(pl, k, c) + (int64_t)SB_NAT_RX * nc
+                                  : momA_ptr(pl, k, c) + (int64_t)(SB_NMC + SB_NQ) * nc;
 #pragma unroll
       for (int t = 0; t < SB_NRX; ++t) {
-        const double v = o[(int64_t)(SB_NMC + SB_NQ + t) * nc];
+        const double v = o[(int64_t)t * nc];
         mX[0][t] += v;
         if (k < NB) mX[1 + k][t] = v;
       }
 #pragma unroll
-      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NMC + SB_NQ + SB_NRX + t) * nc];
+      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NRX + t) * nc];
     }
     /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
     mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
@@ -393,8 +421,14 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
   const int k = p - 1;
   const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
   {
-    double mC[SB_NMC], Q[SB_NQ];
-    if (inside) {
+    double mC[21], Q[SB_NQ];                       /* native: mC holds W (21 values) */
+    if (inside && pl.native) {
+      const double* o = natA_ptr(pl, k, c);
+#pragma unroll
+      for (int t = 0; t < 21; ++t) mC[t] = o[(int64_t)(SB_NAT_W + t) * nc];
+#pragma unroll
+      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NAT_Q + t) * nc];
+    } else if (inside) {
       const double* o = momA_ptr(pl, k, c);
 #pragma unroll
       for (int t = 0; t < SB_NMC; ++t) mC[t] = o[(int64_t)t * nc];
@@ -416,15 +450,15 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
     const int mode = inside ? 1 : 2;
     if (sp)
       sb_rows_flux<true>(c_T, c_M, io, g, p, mode, mC, Q, fl, sl, jumpf[0], jumpf[1], jumpf[2],
-                         pl.natbc_row, st.natbc_values, nb0, nb1);
+                         pl.natbc_row, st.natbc_values, nb0, nb1, pl.native != 0);
     else
       sb_rows_flux<false>(c_T, c_M, io, g, p, mode, mC, Q, fl, sl, jumpf[0], jumpf[1], jumpf[2],
-                          pl.natbc_row, st.natbc_values, nb0, nb1);
+                          pl.natbc_row, st.natbc_values, nb0, nb1, pl.native != 0);
   }
   {
     double mG[SB_NG];
     if (inside) {
-      const double* o = momG_ptr(pl, k, c);
+      const double* o = pl.native ? natG_ptr(pl, k, c) : momG_ptr(pl, k, c);
 #pragma unroll
       for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = o[(int64_t)t * nc];
     }
@@ -936,6 +970,7 @@ extern "C" int sb_version(void) { return 100; }
 extern "C" int64_t sb_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t sb_tables_size(void) { return (int64_t)sizeof(SbTables); }
 extern "C" int64_t sb_plan_nnz(const sb_plan* p) { return p ? p->d.nnz : -1; }
+extern "C" int sb_plan_is_native(const sb_plan* p) { return p ? p->d.native : 0; }
 
 extern "C" void sb_plan_destroy(sb_plan* pl) {
   if (!pl) return;
@@ -1113,9 +1148,24 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   const double* tmp = nullptr;
   if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc, &tmp);
   pl->tmp_cells = const_cast<double*>(tmp);
+  /* closed-form layout?  (native.inl) */
+  d.native = 0; d.nat_fid = nullptr; d.nat_finfo = nullptr; d.nat_fbase = nullptr; d.nat_dofF0 = 0;
+  {
+    std::vector<int32_t> fid, finfo;
+    std::vector<int64_t> fbase;
+    int64_t F0 = 0;
+    if (rc == SB_OK && detect_native(model, pr, fid, finfo, fbase, &F0)) {
+      UP(nat_fid, fid.data(), fid.size());
+      UP(nat_finfo, finfo.data(), finfo.size());
+      UP(nat_fbase, fbase.data(), fbase.size());
+      d.nat_dofF0 = F0;
+      d.native = 1;
+    }
+  }
   const double* scr = nullptr;
-  if (rc == SB_OK)
-    rc = upload<double>(pl, nullptr, (size_t)nc * ((size_t)model->n_bands * 44 + (size_t)nbd * SB_NG), &scr);
+  const size_t per_cell = d.native ? ((size_t)model->n_bands * (SB_NAT_NA + SB_NG) + 18)
+                                   : ((size_t)model->n_bands * 44 + (size_t)nbd * SB_NG);
+  if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc * per_cell, &scr);
   d.scratch = const_cast<double*>(scr);
 #undef UP
   if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }
@@ -1131,6 +1181,14 @@ static int bind_tables(sb_plan* pl, cudaStream_t s) {
                                    cudaMemcpyHostToDevice, s));
   g_tables_owner = pl;
   return SB_OK;
+}
+
+static inline void rec_stage_event(sb_plan* pl, int i, cudaStream_t s) {
+#ifndef SB_EMUL_BUILD
+  if (pl->profiling) cudaEventRecord(pl->evs[i], s);
+#else
+  (void)pl; (void)i; (void)s;
+#endif
 }
 
 extern "C" int sb_plan_zero_values(sb_plan* pl, double* d_vals, void* stream) {
@@ -1165,6 +1223,42 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
   if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev0, s));
 #endif
   const unsigned nblk = (unsigned)((nc + SB_TILE - 1) / SB_TILE);
+  if (pl->d.native) {
+    /* closed-form path (native.inl): moments, generation, one row launch per sub-problem,
+       boundary cells through the generic emitter; no slot is zeroed, no atomic on vals */
+    const PlanDev& d = pl->d;
+    SB_LAUNCH(k_moments_nat, nblk * (unsigned)d.nb, SB_TILE, 0, s, d, sd, (int)nblk);
+#ifndef SB_EMUL_BUILD
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->evs[0], s));
+#endif
+#define SB_NAT_CASE(NBV)                                                                      \
+    case NBV:                                                                                 \
+      SB_LAUNCH(k_generation_nat<NBV>, nblk, SB_TILE, 0, s, d, sd);                           \
+      rec_stage_event(pl, 1, s);                                                              \
+      NatRowsLauncher<NBV, NBV>::go(d, sd, d_vals, d_b, nblk, s);                             \
+      rec_stage_event(pl, 2, s);                                                              \
+      if (d.n_special > 0) {                                                                  \
+        const unsigned nsb = (unsigned)((d.n_special + SB_TILE - 1) / SB_TILE);               \
+        SB_LAUNCH(k_rows_special<NBV>, nsb * (unsigned)d.P, SB_TILE, 0, s, d, sd, d_vals,     \
+                  d_b, (int)nsb);                                                             \
+      }                                                                                       \
+      break;
+#ifdef SB_PROBE_NB          /* developer builds (tools/probe_build.sh): one band count only */
+    switch (d.nb_dof) { default: SB_NAT_CASE(SB_PROBE_NB) }
+#else
+    switch (d.nb_dof) {
+      SB_NAT_CASE(1) SB_NAT_CASE(2) SB_NAT_CASE(3)
+      default: SB_NAT_CASE(4)
+    }
+#endif
+#undef SB_NAT_CASE
+#ifndef SB_EMUL_BUILD
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev1, s));
+#endif
+    g_launches += 2 + d.P + (d.n_special > 0 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return SB_OK;
+  }
   int nl = 1;
   if (pl->d.nb > 0) {
     SB_LAUNCH(k_moments, nblk * (unsigned)pl->d.nb, SB_TILE, 0, s, pl->d, sd, (int)nblk, d_vals);
@@ -1174,8 +1268,13 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) { CUDA_TRY(cudaEventRecord(pl->evs[0], s)); eg = pl->evs[1]; ef = pl->evs[2]; }
 #endif
+#ifdef SB_PROBE_NB
+  switch (0) {
+#else
   switch (pl->d.nb_dof) {
+#endif
     case 0: launch_rows<0>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); break;
+#ifndef SB_PROBE_NB
     case 1: SB_LAUNCH(k_generation<1>, nblk, SB_TILE, 0, s, pl->d, sd);
             launch_rows<1>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
     case 2: SB_LAUNCH(k_generation<2>, nblk, SB_TILE, 0, s, pl->d, sd);
@@ -1184,6 +1283,7 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
             launch_rows<3>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
     default: SB_LAUNCH(k_generation<4>, nblk, SB_TILE, 0, s, pl->d, sd);
              launch_rows<4>(pl->d, sd, d_vals, d_b, nblk, s, eg, ef); ++nl; break;
+#endif
   }
   nl += pl->d.P + (pl->d.n_special > 0 ? 1 : 0) - 1;
 #ifndef SB_EMUL_BUILD

@@ -37,6 +37,8 @@ typedef struct SbTables {
   double M1[3][3];        /* int lam_i lam_j                                     */
   double trI[3];          /* int_0^1 of the 3 edge trace functions               */
   double pad_;
+  double D3[12][3][20];   /* sum_r bdmC[i][a][r] G21[r][l][t] at [i][l][10 a + t]:
+                             <xi_i . j dc/dchi lam_l> |detJ| = sum D3[i][l][.] Q[.]  */
   SbRule rho;             /* rule of the rho term                                */
   SbRule sup;             /* rule of the xi.j/(mu u) term                        */
   /* generation rule, unfactored: point n, X, Y, weight*Psi_t, P2 Lagrange       */

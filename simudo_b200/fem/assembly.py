@@ -166,5 +166,9 @@ class AssemblyPlan(object):
         return dict(zip(('k_moments', 'k_generation', 'k_rows_fast', 'k_rows_special'),
                         [float(x) for x in ms]))
 
+    def is_native(self):
+        """True when the plan runs the closed-form kernels (csrc/native.inl)."""
+        return bool(self.lib.sb_plan_is_native(self._h))
+
     def launch_count(self):
         return int(self.lib.sb_launch_count())

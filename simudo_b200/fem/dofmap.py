@@ -132,7 +132,7 @@ class CsrStructure(object):
         self._mesh = mesh
         if pattern == 'dolfin':
             S = np.ones((L, L), dtype=bool)
-        elif pattern == 'structural':
+        elif pattern in ('structural', 'native'):
             S = structural_mask(P)
         else:
             raise ValueError(pattern)
@@ -187,9 +187,54 @@ class CsrStructure(object):
         r = i % 15
         return (r - 3) // 3 if 3 <= r < 12 else -1
 
+    def _native_ranks_of_row(self, i, cells):
+        """``pattern='native'``: same entries as 'structural', columns of a row in the
+        *emission order* of the device kernels instead of ascending, so that every
+        cell's contribution to a row is one contiguous run (csrc/native.inl):
+
+        * DG1 row of sub-problem p:       [BDM(p) m = 0..11 | DG(q) l = 0..2, q = 0..P-1]
+        * interior BDM row:               [BDM(p) m = 0..11 | DG(p) | DG(0) if p > 0]
+        * facet BDM row (facet f, dof k): [the 3 dofs of f | run A | run B], run X =
+          [the 9 other BDM(p) dofs of cell X, ascending m | DG(p) of X | DG(0) of X if p > 0];
+          A = ``facet_cells[f, 0]`` (the owner, lower cell index), B the other cell
+          (absent on the boundary)."""
+        S = self.mask
+        cols = np.nonzero(S[i])[0]
+        p, r = divmod(i, 15)
+        f = self._row_facet(i)
+        n = len(cells)
+        rk = np.empty(len(cols), dtype=np.int64)
+        nrun = 12 if p == 0 else 15                 # length of run A / B of a facet row
+        for a, j in enumerate(cols):
+            q, rj = divmod(j, 15)
+            if rj >= 3:                             # BDM column (q == p)
+                m = rj - 3
+                if f < 0:
+                    rk[a] = m
+                elif m // 3 == f:
+                    rk[a] = m - 3 * f
+                else:
+                    rk[a] = 3 + (m if m < 3 * f else m - 3)
+            elif r < 3:                             # DG row: DG(q) for every q
+                rk[a] = 12 + 3 * q + rj
+            else:                                   # BDM row: DG(p), then DG(0)
+                off = 12 if f < 0 else 3 + 9
+                rk[a] = off + rj + (3 if (q == 0 and p > 0) else 0)
+        ranks = np.broadcast_to(rk, (n, len(cols))).copy()
+        if f < 0:
+            return ranks, np.full(n, len(cols), dtype=np.int64)
+        nb = self._nbr[cells, f]
+        has = nb >= 0
+        side_b = has & (nb < cells)                 # this cell is the second cell of the facet
+        shift = np.where(rk >= 3, nrun, 0)
+        ranks[side_b] += shift[None, :]
+        return ranks, np.where(has, 3 + 2 * nrun, 3 + nrun).astype(np.int64)
+
     def _ranks_of_row(self, i, cells):
         """Rank of each structural column of local row i inside its global row,
         for the given cells: ``(ranks[len(cells), n_i], row_length[len(cells)])``."""
+        if self.pattern == 'native':
+            return self._native_ranks_of_row(i, np.asarray(cells))
         cd, L, S = self._cd, self.L, self.mask
         cols = np.nonzero(S[i])[0]
         own = cd[cells][:, cols]                              # [n, n_i]

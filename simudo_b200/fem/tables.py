@@ -32,6 +32,7 @@ class SbTables(C.Structure):
                 ('M1', (C.c_double * 3) * 3),
                 ('trI', C.c_double * 3),
                 ('pad_', C.c_double),
+                ('D3', ((C.c_double * 20) * 3) * 12),
                 ('rho', SbRule), ('sup', SbRule),
                 ('ng', C.c_int32), ('pad2_', C.c_int32),
                 ('gX', C.c_double * QG), ('gY', C.c_double * QG),
@@ -71,6 +72,7 @@ def pack_tables(model):
     _set(t.Dhat, T.bdm_div_p1)
     _set(t.M1, T.p1_mass)
     _set(t.trI, [2.0 / 3.0, -1.0 / 3.0, 2.0 / 3.0])
+    _set(t.D3, np.einsum('iar,rlt->ilat', T.bdm_C, T.G21).reshape(12, 3, 20))
     _pack_rule(t.rho, T, model.quad_m_rho)
     _pack_rule(t.sup, T, model.quad_m_super)
     pts, w = collapsed_rule(model.quad_m_g)

@@ -121,6 +121,16 @@ static inline double __shfl_down_sync(unsigned, double v, int o) {
   __syncwarp();
   return r;
 }
+static inline int __any_sync(unsigned, int pred) {
+  auto& c = *emul::g_ctx;
+  const unsigned t = emul::t_tid;
+  c.shfl[t] = pred ? 1.0 : 0.0;
+  __syncwarp();
+  int r = 0;
+  for (unsigned q = (t / 32) * 32; q < (t / 32) * 32 + 32 && q < c.shfl.size(); ++q) r |= c.shfl[q] != 0.0;
+  __syncwarp();
+  return r;
+}
 using std::isnan;
 
 #define SB_EMUL 1

@@ -29,11 +29,16 @@ def _oracle(pa, st):
                                st['bc_values'], st['natbc_values'])
 
 
+def pattern_of(kw):
+    return kw.get('pattern', 'structural')
+
+
 def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
     pa = maker(nx=nx, ny=ny, numbering=numbering, with_bcs=with_bcs, **kw)
     st = syn.synthetic_state(pa)
     vals0, b0 = _oracle(pa, st)
     plan = AssemblyPlan(pa)
+    assert plan.is_native() == (pattern_of(kw) == 'native' and numbering == 'b200')
     vals, b = run_plan(plan, st)
     vals, b = vals.cpu().numpy(), b.cpu().numpy()
     assert np.isfinite(vals).all() and np.isfinite(b).all()

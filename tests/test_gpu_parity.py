@@ -31,6 +31,15 @@ from simudo_b200 import synthetic as syn   # noqa: E402
     (syn.pn_problem, 40, 33, 'b200', True, 'structural'),  # 2 496 cells, many CTAs
     (syn.ib_problem, 30, 21, 'b200', True, 'structural'),
     (syn.ib_problem, 30, 21, 'b200', True, 'dolfin'),
+    # closed-form kernels (csrc/native.inl)
+    (syn.pn_problem, 5, 3, 'b200', True, 'native'),
+    (syn.ib_problem, 6, 3, 'b200', True, 'native'),
+    (syn.ib_problem, 5, 2, 'b200', False, 'native'),
+    (syn.pn_problem, 67, 2, 'b200', True, 'native'),
+    (syn.ib_problem, 279, 2, 'b200', True, 'native'),
+    (syn.pn_problem, 40, 33, 'b200', True, 'native'),
+    (syn.ib_problem, 30, 21, 'b200', True, 'native'),
+    (syn.ib_problem, 30, 21, 'ufc', True, 'native'),       # 'native' columns, generic kernels
 ])
 def test_assembly_parity(maker, nx, ny, numbering, bcs, pattern):
     hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)
