@@ -47,11 +47,13 @@ def parse_args():
     ap.add_argument('--nx', type=int, default=708, help='x points of the product mesh')
     ap.add_argument('--ny', type=int, default=708, help='y points per rank strip')
     ap.add_argument('--kind', default='ib', choices=['ib', 'pn'])
-    ap.add_argument('--pattern', default='native', choices=['native', 'structural', 'dolfin'],
+    ap.add_argument('--pattern', default='native', choices=['bsr3', 'native', 'structural', 'dolfin'],
                     help="CSR layout: 'native' = structural non-zeros, columns in kernel emission "
                          "order (closed-form kernels); 'structural' = same entries, ascending "
                          "columns; 'dolfin' = dense cell blocks")
     ap.add_argument('--no-e2e', action='store_true', help='kernel experiments: skip the host-buffer arm')
+    ap.add_argument('--outputs', default='Ab', choices=['Ab', 'A', 'b'],
+                    help='kernel experiments: assemble Jacobian and residual, or only one of them')
     ap.add_argument('--cpu-cells', type=int, default=40000,
                     help='cells of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -226,7 +228,8 @@ def run_b200(args):
         if world > 1:
             halo.step(dist, d['u'], d['base_w'])
         plan.assemble(d['u'], d.get('base_w'), d.get('thmeq_phi'), d.get('phi_opt'),
-                      bcv, nat, vals, b)
+                      bcv, nat, vals if 'A' in args.outputs else None,
+                      b if 'b' in args.outputs else None)
 
     # end-to-end arm: host buffers in, residual out, through the public pipelined API
     # (copies of neighbouring steps overlap the kernels; every step still moves all of
@@ -356,6 +359,7 @@ def run_b200(args):
                 sub_problems=pa.P, local_dofs=pa.L, optical_fields=pa.model.n_fields,
                 pattern={'structural': 'structural non-zeros of the dolfin cell blocks, ascending columns',
                          'native': 'structural non-zeros of the dolfin cell blocks, columns in emission order',
+                         'bsr3': 'structural non-zeros of the dolfin cell blocks as block CSR with 3 x 3 blocks',
                          'dolfin': 'dolfin dense cell blocks'}[pa.pattern],
                 numbering=pa.numbering, native_kernels=plan.is_native(),
                 parallelism=('y-strips x%d, NCCL ghost exchange %d B/rank/step' % (world, halo.bytes_per_exchange)) if world > 1 else 'single GPU',

@@ -86,11 +86,8 @@ class Oracle(object):
         # the C restatement inserts by binary search in ascending columns (like PETSc's
         # MatSetValues); layouts with another column order inside a row ('native') are
         # assembled in sorted order and permuted back into the caller's layout
-        rp = pa.csr.rowptr
-        rows = np.repeat(np.arange(pa.N, dtype=np.int64), np.diff(rp))
-        self._perm = np.lexsort((self.colidx, rows))
+        self._rowptr_csr, self._colidx_sorted, self._perm = pa.csr.sorted_csr()
         self._sorted = bool((self._perm == np.arange(len(self._perm))).all())
-        self._colidx_sorted = np.ascontiguousarray(self.colidx[self._perm])
         self._rules = {}
         m = pa.model
         self.rule_default = self._make_rule(*fl.default_triangle_scheme(4))
@@ -123,7 +120,7 @@ class Oracle(object):
             cell_vertices=pa.cell_vertices, cell_tag=pa.cell_tag,
             cell_dofs=pa.cell_dofs, cell_neighbors=pa.cell_neighbors,
             cell_jump_mask=pa.cell_jump_mask, tag_params=pa.tag_params,
-            rowptr=pa.csr.rowptr, colidx=self._colidx_sorted, bc_dofs=pa.bc_dofs,
+            rowptr=self._rowptr_csr, colidx=self._colidx_sorted, bc_dofs=pa.bc_dofs,
             natbc_cell=pa.natbc_cell, natbc_row=pa.natbc_row,
             facet_w=self.facet_w, facet_trace=self.facet_trace)
         nb, nc, nf = pa.model.n_bands, pa.n_cells, pa.model.n_fields
@@ -182,7 +179,7 @@ class Oracle(object):
 
     def to_scipy(self, vals):
         import scipy.sparse as sp
-        return sp.csr_matrix((vals, self.colidx, self.pa.csr.rowptr),
+        return sp.csr_matrix((np.asarray(vals)[self._perm], self._colidx_sorted, self._rowptr_csr),
                              shape=(self.pa.N, self.pa.N))
 
 

@@ -12,7 +12,8 @@ import os
 from .fem.model import SbModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, 'csrc', 'libsimudo_b200.so')
+# SIMUDO_B200_SO: developer override (kernel experiments with alternative nvcc builds)
+SO_PATH = os.environ.get('SIMUDO_B200_SO') or os.path.join(_HERE, 'csrc', 'libsimudo_b200.so')
 
 _LIB = None
 _EMULATED = False

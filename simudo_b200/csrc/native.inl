@@ -29,24 +29,35 @@
  */
 
 /* moment scratch of the native path, [quantity][cell]:
- *   band k:   (k * SB_NAT_NA + q):  W 21 | Q 20 | Rx 6 | R 3 | S 18
+ *   band k:   (k * SB_NAT_NA + q):  W 21 | D 36 | Rx 6 | R 3 | S 18
+ *             W = packed int c pi_r pi_s; D[3 i + l] = <xi_i . j dc/dchi lam_l> (the
+ *             (xi, delta_w) / (xi, phi) coupling of BDM row i); S = (facet, facet) blocks
  *   then      generation moments   (nb * SB_NAT_NA + k * SB_NG + t)
  *   then      S of the Poisson sub-problem, 18                                  */
-#define SB_NAT_NA 68
+#define SB_NAT_NA 84
 #define SB_NAT_W 0
-#define SB_NAT_Q 21
-#define SB_NAT_RX 41
-#define SB_NAT_R 47
-#define SB_NAT_S 50
+#define SB_NAT_D 21
+#define SB_NAT_RX 57
+#define SB_NAT_R 63
+#define SB_NAT_S 66
 
+/* tile-blocked: quantity q of cell c at ((c / 32) * NQT + q) * 32 + c % 32, NQT quantities
+ * per cell -- everything a warp (32 cells) reads or writes is one contiguous block of
+ * NQT * 256 bytes instead of NQT segments 8 * n_cells bytes apart (one DRAM page / TLB
+ * entry per quantity)                                                                  */
+#define SB_NQS 32                                   /* stride between quantities of a cell */
+__device__ __forceinline__ int sb_nat_nqt(const PlanDev& pl) { return pl.nb * (SB_NAT_NA + SB_NG) + 18; }
+__device__ __forceinline__ double* natQ_ptr(const PlanDev& pl, int q, int64_t c) {
+  return pl.scratch + (((c >> 5) * sb_nat_nqt(pl) + q) << 5) + (c & 31);
+}
 __device__ __forceinline__ double* natA_ptr(const PlanDev& pl, int k, int64_t c) {
-  return pl.scratch + (int64_t)k * SB_NAT_NA * pl.n_cells + c;
+  return natQ_ptr(pl, k * SB_NAT_NA, c);
 }
 __device__ __forceinline__ double* natG_ptr(const PlanDev& pl, int k, int64_t c) {
-  return pl.scratch + ((int64_t)pl.nb * SB_NAT_NA + (int64_t)k * SB_NG) * pl.n_cells + c;
+  return natQ_ptr(pl, pl.nb * SB_NAT_NA + k * SB_NG, c);
 }
 __device__ __forceinline__ double* natS0_ptr(const PlanDev& pl, int64_t c) {
-  return pl.scratch + (int64_t)pl.nb * (SB_NAT_NA + SB_NG) * pl.n_cells + c;
+  return natQ_ptr(pl, pl.nb * (SB_NAT_NA + SB_NG), c);
 }
 
 /* (facet dof, facet dof) blocks of the cell's flux mass matrix <xi_i . xi_m c> / |detJ|:
@@ -177,13 +188,22 @@ k_moments_nat(PlanDev pl, StateDev st, int nblk) {
   }
   double* o = natA_ptr(pl, k, c);
 #pragma unroll
-  for (int t = 0; t < SB_NRX; ++t) o[(int64_t)(SB_NAT_RX + t) * nc] = mRx[t];
+  for (int t = 0; t < SB_NRX; ++t) o[(int64_t)(SB_NAT_RX + t) * SB_NQS] = mRx[t];
 #pragma unroll
-  for (int t = 0; t < SB_NR; ++t) o[(int64_t)(SB_NAT_R + t) * nc] = mR[t];
+  for (int t = 0; t < SB_NR; ++t) o[(int64_t)(SB_NAT_R + t) * SB_NQS] = mR[t];
   double S[18];
   if (dd) {
+    /* d_il = (1 / |detJ|) sum_t D3[i][l][t] Q[t]: the register-hungry contraction is done
+       here, where nothing else is live, so that the row kernel never holds Q */
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i)
 #pragma unroll
-    for (int t = 0; t < SB_NQ; ++t) o[(int64_t)(SB_NAT_Q + t) * nc] = Q[t];
+      for (int l = 0; l < 3; ++l) {
+        double d = 0.0;
+#pragma unroll
+        for (int t = 0; t < SB_NQ; ++t) d = fma(c_T.D3[i][l][t], Q[t], d);
+        o[(int64_t)(SB_NAT_D + 3 * i + l) * SB_NQS] = d * g.iad;
+      }
     double W[21];
 #pragma unroll
     for (int e = 0; e < 21; ++e) {
@@ -191,19 +211,19 @@ k_moments_nat(PlanDev pl, StateDev st, int nblk) {
 #pragma unroll
       for (int t = 0; t < 15; ++t) v += c_T.G22u[e][t] * mC[t];
       W[e] = v;
-      o[(int64_t)(SB_NAT_W + e) * nc] = v;
+      o[(int64_t)(SB_NAT_W + e) * SB_NQS] = v;
     }
     sb_facet_blocks(c_T, g, W, 1.0, S);
   } else {
     sb_facet_blocks(c_T, g, nullptr, c_M.ext_j_coef, S);
   }
 #pragma unroll
-  for (int t = 0; t < 18; ++t) o[(int64_t)(SB_NAT_S + t) * nc] = S[t];
+  for (int t = 0; t < 18; ++t) o[(int64_t)(SB_NAT_S + t) * SB_NQS] = S[t];
   if (k == 0) {                                   /* Poisson <psi_i . psi_m> blocks */
     sb_facet_blocks(c_T, g, nullptr, 1.0, S);
     double* o0 = natS0_ptr(pl, c);
 #pragma unroll
-    for (int t = 0; t < 18; ++t) o0[(int64_t)t * nc] = S[t];
+    for (int t = 0; t < 18; ++t) o0[(int64_t)t * SB_NQS] = S[t];
   }
 }
 
@@ -245,7 +265,7 @@ k_generation_nat(PlanDev pl, StateDev st) {
     if (!inside_k[k]) continue;
     double* o = natG_ptr(pl, k, c);
 #pragma unroll
-    for (int t = 0; t < 9 + 6 * NB; ++t) o[(int64_t)t * nc] = mG[k][t];
+    for (int t = 0; t < 9 + 6 * NB; ++t) o[(int64_t)t * SB_NQS] = mG[k][t];
   }
 }
 
@@ -258,122 +278,16 @@ k_generation_nat(PlanDev pl, StateDev st) {
  *            first cell, RB otherwise), staged [row][entry] and flushed by the warp with
  *            lane = entry: one store instruction covers up to two row runs.           */
 #define SB_NAT_FROW 18                              /* staging slots per facet row */
+#define SB_NAT_FSTR 57                              /* block CSR: staging doubles per lane of a facet warp */
+#ifndef SB_MB_ROWS_BSR
+#define SB_MB_ROWS_BSR 3                            /* CTAs per SM of the block-CSR row kernels */
+#endif
 #define SB_NAT_STR(P) ((((3 * (12 + 3 * (P))) > 3 * SB_NAT_FROW ? (3 * (12 + 3 * (P))) : 3 * SB_NAT_FROW) + 2) | 1)
 
 struct SbNatMeta {
   int64_t gb[3][32];        /* vals index of the cell's run in row k = 0 of facet f      */
   int32_t rn[3][32];        /* row length | entries per run << 16 (0: nothing to store)  */
 };
-
-/* One BDM row I (compile-time: every table operand is a constant-bank immediate) of
- * sub-problem PS in native order.  MODE 0 Poisson, 1 band inside its subdomain, 2 outside.
- *   run  -> where the row's non-(facet, facet) entries start in the staging area
- *   W    packed int c pi_r pi_s (MODE 1);  Q the 20 moments of c' g^a (MODE 1)
- *   jc   Dubiner coefficients of the cell's flux, jc[b][s] = sum_m fl_m C_m[b][s]: the
- *        flux part of the residual is sum GY_i[b][s] jc[b][s] (no second pass over fl)
- * returns the residual of the row (jump term not included).                             */
-template <int PS, int MODE, int I>
-__device__ __forceinline__ double sb_nat_row(const SbTables& T, double g11, double g12, double g22,
-                                             double iad, double divsign, const double* W,
-                                             const double* Q, const double (*jc)[6],
-                                             const double* fl, const double* sl, double* run) {
-  constexpr int GRP = I < 9 ? I / 3 : 3;
-  constexpr int dg0 = GRP < 3 ? 9 : 12;
-  double Fi = 0.0;
-  if (MODE == 1) {
-    double GY0[6], GY1[6];
-#pragma unroll
-    for (int s2 = 0; s2 < 6; ++s2) {
-      double y0 = 0.0, y1 = 0.0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        y0 = fma(T.bdmC[I][0][r], W[sb_sym21(r, s2)], y0);
-        y1 = fma(T.bdmC[I][1][r], W[sb_sym21(r, s2)], y1);
-      }
-      GY0[s2] = g11 * y0 + g12 * y1;
-      GY1[s2] = g12 * y0 + g22 * y1;
-      Fi = fma(GY1[s2], jc[1][s2], fma(GY0[s2], jc[0][s2], Fi));
-    }
-#pragma unroll
-    for (int m = 0; m < 12; ++m) {
-      if (GRP < 3 && m / 3 == GRP) continue;
-      double v = 0.0;
-#pragma unroll
-      for (int s2 = 0; s2 < 6; ++s2)
-        v = fma(GY1[s2], T.bdmC[m][1][s2], fma(GY0[s2], T.bdmC[m][0][s2], v));
-      run[GRP < 3 ? (m < 3 * GRP ? m : m - 3) : m] = v;
-    }
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      const double dv = divsign * T.Dhat[I][l];
-      Fi = fma(dv, sl[l], Fi);
-      double d = 0.0;
-#pragma unroll
-      for (int t = 0; t < 20; ++t) d = fma(T.D3[I][l][t], Q[t], d);
-      d *= iad;
-      run[dg0 + l] = dv + d;
-      run[dg0 + 3 + l] = d;
-    }
-  } else {
-#pragma unroll
-    for (int m = 0; m < 12; ++m) {
-      const double v = g11 * T.Mhat[I][m][0] + g12 * T.Mhat[I][m][1] + g22 * T.Mhat[I][m][2];
-      Fi = fma(v, fl[m], Fi);
-      if (GRP < 3 && m / 3 == GRP) continue;
-      run[GRP < 3 ? (m < 3 * GRP ? m : m - 3) : m] = v;
-    }
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      if (MODE == 0) {
-        const double dv = divsign * T.Dhat[I][l];
-        Fi = fma(dv, sl[l], Fi);
-        run[dg0 + l] = dv;
-      } else {                                   /* structural entries that vanish outside */
-        run[dg0 + l] = 0.0;
-        run[dg0 + 3 + l] = 0.0;
-      }
-    }
-  }
-  return Fi;
-}
-
-/* compiler-only fence between the unrolled rows: without it ptxas interleaves the rows of a
- * group for ILP and spills their operands */
-#if defined(__CUDA_ARCH__)
-#define SB_ROW_FENCE() asm volatile("" ::: "memory")
-#else
-#define SB_ROW_FENCE() ((void)0)
-#endif
-
-/* the three BDM rows of group GRP (0..2: facet GRP, 3: interior) into st[k * rowstr + ..];
- * lead: 3 when the staged run starts with the 3 (facet, facet) entries (this cell is the
- * facet's first cell), else 0; S: their values (own + neighbour block, packed symmetric).
- * g11, g12, g22: J^T J scaled by coef / |detJ|; divsign: sign of the divergence block (0:
- * none, band outside its subdomain); iad: 1 / |detJ|.                                     */
-template <int PS, int MODE, int GRP>
-__device__ __forceinline__ void sb_nat_flux_group(
-    const SbTables& T, double g11, double g12, double g22, double iad, double divsign,
-    const double* W, const double* Q, const double (*jc)[6], const double* fl, const double* sl,
-    double jf, int lead, const double* S, double* st, int rowstr, double* Fout) {
-  if (GRP < 3 && lead) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int k2 = 0; k2 < 3; ++k2) st[k * rowstr + k2] = S[sb_sym3(k, k2)];
-  }
-  Fout[0] = sb_nat_row<PS, MODE, 3 * GRP + 0>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
-                                              st + lead);
-  SB_ROW_FENCE();
-  Fout[1] = sb_nat_row<PS, MODE, 3 * GRP + 1>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
-                                              st + rowstr + lead);
-  SB_ROW_FENCE();
-  Fout[2] = sb_nat_row<PS, MODE, 3 * GRP + 2>(T, g11, g12, g22, iad, divsign, W, Q, jc, fl, sl,
-                                              st + 2 * rowstr + lead);
-  if (MODE == 1 && GRP < 3) {                     /* base_w jump: facet dofs */
-#pragma unroll
-    for (int k = 0; k < 3; ++k) Fout[k] -= jf * T.trI[k];
-  }
-}
 
 /* warp flush of one staged facet group: cell after cell, lane = (row, entry) */
 __device__ __forceinline__ void sb_nat_flush_facet(const SbNatMeta& meta, int f, const double* wst,
@@ -394,34 +308,44 @@ __device__ __forceinline__ void sb_nat_flush_facet(const SbNatMeta& meta, int f,
   }
 }
 
-/* the 12 BDM rows of one cell and sub-problem: three facet groups (staged, flushed by the
- * warp) and the interior group (bulk copy); see k_rows_nat                                */
-template <int NB, int PS, int MODE>
+/* The 12 BDM rows of one cell and sub-problem PS: three facet groups (staged, flushed by
+ * the warp with lane = entry) and the interior group (bulk copy).  One rolled loop over the
+ * groups (small code: the fully unrolled variant, 11 k instructions, ran 1.6x slower out of
+ * the instruction cache).  Per group the three rows are computed together:
+ *   GY_k[b][s] = (coef / |detJ|) sum_a G_ab sum_r C_i[a][r] W_rs        i = 3 grp + k
+ *   A_im       = sum_{b,s} GY_k[b][s] C_m[b][s]
+ * so that the 12 constants of column m are fetched once for three rows (sm_100a FP64
+ * instructions take no constant-bank operand: every table value costs a load).
+ * MODE 0: Poisson (W = identity), 1: band, moment-driven (a lane outside the band's
+ * subdomain runs it with W = identity, no divergence block, penalty coefficient: exactly
+ * the out-of-subdomain form :288-289), 2: whole warp outside the subdomain.            */
+template <int NB, int PS, int MODE, int LAY>
 __device__ __forceinline__ void sb_nat_flux_part(
     const PlanDev& pl, const StateDev& st, double* __restrict__ vals, double* __restrict__ b,
     const SbNatMeta& meta, double* wst, double* stg, double* stg16, int lane, int64_t cc,
     bool active, bool bulk, int32_t finfo, const int32_t* fid, const SbCellGeom& g,
-    const double* fl, const double* sl, bool inside, int64_t g0, int64_t dof0) {
+    const double* fl, const double* sl, bool inside, int64_t g0, int64_t dof0, int grp) {
   constexpr int P = NB + 1;
   constexpr int RDG = 12 + 3 * P;
   constexpr int RI = PS == 0 ? 15 : 18;
   constexpr int STR = SB_NAT_STR(P);
   constexpr int kb = PS > 0 ? PS - 1 : 0;
   const int64_t nc = pl.n_cells;
-  double W[21], Q[SB_NQ], jc[2][6];
+  const SbTables& T = c_T;
+  const bool momdrv = (MODE == 1) && inside;      /* W, D from the moment scratch */
+  double W[21];
   double jumpf[3] = {0.0, 0.0, 0.0};
   double sc = g.iad, divsign = (MODE == 0) ? -g.sdet : g.sdet;
-  const double* sa_base = (PS == 0) ? natS0_ptr(pl, cc) : natA_ptr(pl, kb, cc) + (int64_t)SB_NAT_S * nc;
+  const double* sa_base = (PS == 0) ? natS0_ptr(pl, cc) : natA_ptr(pl, kb, cc) + (int64_t)SB_NAT_S * SB_NQS;
+  const double* ob = natA_ptr(pl, kb, cc);
   if (MODE == 1) {
     if (inside) {
-      const double* o = natA_ptr(pl, kb, cc);
 #pragma unroll
-      for (int e = 0; e < 21; ++e) W[e] = o[(int64_t)(SB_NAT_W + e) * nc];
-#pragma unroll
-      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NAT_Q + t) * nc];
+      for (int e = 0; e < 21; ++e) W[e] = ob[(int64_t)(SB_NAT_W + e) * SB_NQS];
       const double w0 = st.base_w[(int64_t)kb * nc + cc];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
+        if (f != grp) continue;
         if ((finfo >> (12 + 4 * f + kb)) & 1) {
           const int64_t cn = pl.cell_neighbors[cc * 3 + f];
           const double ref_out = (f == 1) ? -1.0 : 1.0;
@@ -433,78 +357,154 @@ __device__ __forceinline__ void sb_nat_flux_part(
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int s2 = r; s2 < 6; ++s2) W[sb_sym21(r, s2)] = (r == s2) ? 1.0 : 0.0;
-#pragma unroll
-      for (int t = 0; t < SB_NQ; ++t) Q[t] = 0.0;
       sc = c_M.ext_j_coef * g.iad;
       divsign = 0.0;
     }
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        double v = 0.0;
-#pragma unroll
-        for (int m = 0; m < 12; ++m) v = fma(fl[m], c_T.bdmC[m][a][r], v);
-        jc[a][r] = v;
-      }
   } else if (MODE == 2) {
     sc = c_M.ext_j_coef * g.iad;
+    divsign = 0.0;
   }
   const double g11 = g.G11 * sc, g12 = g.G12 * sc, g22 = g.G22 * sc;
 
-#define SB_NAT_FACET_GROUP(GRP)                                                              \
-  {                                                                                          \
-    const int bits = (finfo >> (4 * GRP)) & 3;                                               \
-    const int lead = (bits & 2) ? 0 : 3;                                                     \
-    double S[6];                                                                             \
-    if (lead) {                                                                              \
-      _Pragma("unroll") for (int t = 0; t < 6; ++t) S[t] = sa_base[(int64_t)(6 * GRP + t) * nc]; \
-      if (bits == 0) {                            /* interior facet, this cell is first */  \
-        const int64_t cn = pl.cell_neighbors[cc * 3 + GRP];                                  \
-        const int f2 = (finfo >> (4 * GRP + 2)) & 3;                                         \
-        const double* sn = sa_base + (cn - cc);                                              \
-        _Pragma("unroll") for (int t = 0; t < 6; ++t) S[t] += sn[(int64_t)(6 * f2 + t) * nc]; \
-      }                                                                                      \
-    }                                                                                        \
-    double Fr[3];                                                                            \
-    sb_bulk_wait_read();                          /* previous bulk copy has left the slot */ \
-    if (active) {                                                                            \
-      sb_nat_flux_group<PS, MODE, GRP>(c_T, g11, g12, g22, g.iad, divsign, W, Q, jc, fl, sl, \
-                                       jumpf[GRP], lead, S, stg, SB_NAT_FROW, Fr);           \
-      if (b) {                                                                               \
-        double* bd = b + pl.nat_dofF0 + (int64_t)3 * P * fid[GRP] + 3 * PS;                  \
-        _Pragma("unroll") for (int k = 0; k < 3; ++k) SB_ATOMIC_ADD(bd + k, Fr[k]);          \
-      }                                                                                      \
-    }                                                                                        \
-    __syncwarp();                                                                            \
-    if (vals) sb_nat_flush_facet(meta, GRP, wst, STR, vals, lane);                           \
-    __syncwarp();                                                                            \
-  }
-  SB_NAT_FACET_GROUP(0)
-  SB_NAT_FACET_GROUP(1)
-  SB_NAT_FACET_GROUP(2)
-#undef SB_NAT_FACET_GROUP
-
-  /* interior BDM rows: owned, bulk copy */
   {
-    const int64_t g1 = g0 + 3 * RDG;
+    constexpr bool BSR = (LAY == 2);
+    constexpr int RB = PS == 0 ? 12 : 15;
+    const bool facet = grp < 3;
+    const int bits = facet ? ((finfo >> (4 * grp)) & 3) : 2;
+    const int lead = (bits & 2) ? 0 : 3;          /* run starts with the (facet, facet) entries */
+    const int rowstr = facet ? SB_NAT_FROW : RI;
+    /* vals index of what this thread copies out itself: the interior block, or (block CSR)
+       its run in the facet's block row */
+    int64_t g1 = g0 + 3 * RDG;
+    if (BSR && facet) {
+      const bool bnd = bits & 1;
+      const int32_t fd = grp == 0 ? fid[0] : (grp == 1 ? fid[1] : fid[2]);
+      const int rowoff = PS == 0 ? 0 : (bnd ? 45 + 3 * (PS - 1) * 18 : 81 + 3 * (PS - 1) * 33);
+      g1 = pl.nat_fbase[fd] + rowoff + ((bits & 2) ? 3 * (3 + RB) : 0);
+    }
     const int ph = (int)(g1 & 1);
-    double* sd = stg16 + ph;
-    double Fr[3];
-    if (active) {
-      sb_nat_flux_group<PS, MODE, 3>(c_T, g11, g12, g22, g.iad, divsign, W, Q, jc, fl, sl, 0.0, 0,
-                                     nullptr, sd, RI, Fr);
-      if (b) {
+    /* 16-byte phase of the bulk copy; CSR facet runs are flushed by the warp instead */
+    double* st0 = (facet && !BSR) ? stg : stg16 + ph;
+    /* staging index of (row k, position `slot` of the row's run): row-major run per row
+       (CSR), or 3 x 3 blocks, block-major (block CSR) */
+#define SB_NAT_IDX(k, slot) (BSR ? ((slot) / 3) * 9 + 3 * (k) + (slot) % 3 : (k) * rowstr + (slot))
+    /* operands that come from memory: issued first, used last */
+    double S[6] = {0, 0, 0, 0, 0, 0}, D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (lead) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) b[dof0 + 3 + k] = Fr[k];
+      for (int t = 0; t < 6; ++t) S[t] = sa_base[(int64_t)(6 * grp + t) * SB_NQS];
+      if (bits == 0) {                            /* interior facet, this cell is its first cell */
+        const int64_t cn = pl.cell_neighbors[cc * 3 + grp];
+        const int f2 = (finfo >> (4 * grp + 2)) & 3;
+        const double* sn = (PS == 0) ? natS0_ptr(pl, cn)
+                                     : natA_ptr(pl, kb, cn) + (int64_t)SB_NAT_S * SB_NQS;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) S[t] += sn[(int64_t)(6 * f2 + t) * SB_NQS];
       }
     }
-    if (bulk) sb_bulk_store_owned(vals + g1, stg16, ph, 3 * RI);
+    if (momdrv) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) D[t] = ob[(int64_t)(SB_NAT_D + 9 * grp + t) * SB_NQS];
+    }
+    double F[3] = {0.0, 0.0, 0.0};
+    if (active) {
+      double GY[3][12];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = 3 * grp + k;
+        if (MODE == 1) {
+#pragma unroll
+          for (int s2 = 0; s2 < 6; ++s2) {
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              y0 = fma(T.bdmC[i][0][r], W[sb_sym21(r, s2)], y0);
+              y1 = fma(T.bdmC[i][1][r], W[sb_sym21(r, s2)], y1);
+            }
+            GY[k][s2] = g11 * y0 + g12 * y1;
+            GY[k][6 + s2] = g12 * y0 + g22 * y1;
+          }
+        } else {                                  /* W = identity */
+#pragma unroll
+          for (int s2 = 0; s2 < 6; ++s2) {
+            const double y0 = T.bdmC[i][0][s2], y1 = T.bdmC[i][1][s2];
+            GY[k][s2] = g11 * y0 + g12 * y1;
+            GY[k][6 + s2] = g12 * y0 + g22 * y1;
+          }
+        }
+      }
+      sb_bulk_wait_read();                        /* an earlier bulk copy has left the slot */
+#pragma unroll
+      for (int m = 0; m < 12; ++m) {
+        double cm[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) cm[q] = T.bdmC[m][q / 6][q % 6];
+        double v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double a = 0.0;
+#pragma unroll
+          for (int q = 0; q < 12; ++q) a = fma(GY[k][q], cm[q], a);
+          v[k] = a;
+          F[k] = fma(a, fl[m], F[k]);
+        }
+        const int own = facet && (m / 3 == grp);
+        if (!own) {
+          const int slot = lead + (facet ? (m < 3 * grp ? m : m - 3) : m);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) st0[SB_NAT_IDX(k, slot)] = v[k];
+        }
+      }
+      const int dg0 = lead + (facet ? 9 : 12);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const double dv = divsign * T.Dhat[3 * grp + k][l];
+          F[k] = fma(dv, sl[l], F[k]);
+          st0[SB_NAT_IDX(k, dg0 + l)] = dv + D[3 * k + l];
+          if (PS > 0) st0[SB_NAT_IDX(k, dg0 + 3 + l)] = D[3 * k + l];
+        }
+        if (lead) {
+#pragma unroll
+          for (int k2 = 0; k2 < 3; ++k2) st0[SB_NAT_IDX(k, k2)] = S[sb_sym3(k, k2)];
+        }
+        if (MODE == 1 && facet) {                 /* base_w jump: facet dofs */
+          const double jf = grp == 0 ? jumpf[0] : (grp == 1 ? jumpf[1] : jumpf[2]);
+          F[k] -= jf * T.trI[k];
+        }
+      }
+      if (b) {
+        if (facet) {
+          const int32_t fd = grp == 0 ? fid[0] : (grp == 1 ? fid[1] : fid[2]);
+          double* bd = b + pl.nat_dofF0 + (int64_t)3 * P * fd + 3 * PS;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) SB_ATOMIC_ADD(bd + k, F[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) b[dof0 + 3 + k] = F[k];
+        }
+      }
+    } else {
+      sb_bulk_wait_read();
+    }
+#undef SB_NAT_IDX
+    if (facet && !BSR) {
+      __syncwarp();
+#ifndef SB_EXP_NOFLUSH
+      if (vals) sb_nat_flush_facet(meta, grp, wst, STR, vals, lane);
+#endif
+      __syncwarp();
+    } else if (bulk) {
+#ifndef SB_EXP_NOBULK
+      sb_bulk_store_owned(vals + g1, stg16, ph, facet ? 3 * (RB + lead) : 3 * RI);
+#endif
+    }
   }
 }
 
-template <int NB, int PS>
-__global__ void __launch_bounds__(SB_TILE, SB_MB_ROWS)
+template <int NB, int PS, int LAY>
+__global__ void __launch_bounds__(SB_TILE, (LAY == 2 ? SB_MB_ROWS_BSR : SB_MB_ROWS))
 k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restrict__ b) {
 #ifdef SB_EMUL_BUILD
   unsigned char* s_dyn = emul::dyn_smem();
@@ -520,12 +520,21 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   constexpr int OFF_DG = PS == 0 ? 0 : (3 * RDG + 45) + (PS - 1) * (3 * RDG + 54);
   constexpr int kb = PS > 0 ? PS - 1 : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* wst = reinterpret_cast<double*>(s_dyn) + (size_t)warp * 32 * STR;
+  /* staging: CSR: STR doubles per lane for every warp (+ flush metadata); block CSR: the
+     three facet warps need 54 + 2 doubles per lane, warp 3 the DG block (3 RDG + 2) */
+  const int lstr = (LAY == 2 && warp < 3) ? SB_NAT_FSTR : STR;
+  double* wst = reinterpret_cast<double*>(s_dyn) +
+                (LAY == 2 ? (size_t)warp * 32 * SB_NAT_FSTR : (size_t)warp * 32 * STR);
   SbNatMeta& meta = reinterpret_cast<SbNatMeta*>(s_dyn + sizeof(double) * 32 * STR * (SB_TILE / 32))[warp];
-  double* stg = wst + lane * STR;                 /* this lane's slot                   */
-  double* stg16 = stg + (lane & 1);               /* 16-byte aligned (STR is odd)       */
+  double* stg = wst + lane * lstr;                /* this lane's slot                   */
+  double* stg16 = stg + (lane & 1);               /* 16-byte aligned (odd strides)      */
   const int64_t nc = pl.n_cells;
-  const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
+  /* a CTA = 32 cells x 4 warps; warp `role` 0..2 emits the rows of facet `role`, warp 3 the
+     DG and interior rows: four short, independent instruction streams per cell tile
+     instead of one long one -- every warp issues all of its loads up front and pays one
+     memory latency, not one per row group                                              */
+  const int role = warp;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   const int64_t cc = c < nc ? c : nc - 1;
   const bool active = (c < nc) && (pl.cell_special[cc] < 0);
   const int32_t finfo = pl.nat_finfo[cc];
@@ -544,9 +553,10 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
 #pragma unroll
     for (int k = 0; k < 3; ++k) fl[3 * f + k] = uf[k];
   }
-  /* flush metadata of the three facet groups */
+  /* flush metadata of this warp's facet group */
 #pragma unroll
   for (int f = 0; f < 3; ++f) {
+    if (f != role || LAY == 2) continue;          /* block CSR: no warp flush, no metadata */
     const int bits = (finfo >> (4 * f)) & 3;
     const bool bnd = bits & 1, second = bits & 2;
     const int rl = bnd ? (PS == 0 ? 15 : 18) : (PS == 0 ? 27 : 33);
@@ -560,9 +570,11 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   const bool bulk = active && vals != nullptr;
 
   /* ---- group 0: DG rows ----------------------------------------------------------- */
-  {
+  if (role == 3) {
     const int ph = (int)(g0 & 1);
     double* sd = stg16 + ph;
+    /* staging index of (row i, position k of the row): see SB_NAT_IDX */
+#define SB_NAT_DGIDX(i, k) (LAY == 2 ? ((k) / 3) * 9 + 3 * (i) + (k) % 3 : (i) * RDG + (k))
     double F[3] = {0.0, 0.0, 0.0};
     if (PS == 0 || inside) {
       double mom[9 + 6 * (NB > 0 ? NB : 1)];     /* [0..2] P1 source | [3 + 6q ..] d/d(q) */
@@ -575,12 +587,12 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
           const double* o = natA_ptr(pl, kk, cc);
 #pragma unroll
           for (int t = 0; t < SB_NRX; ++t) {
-            const double v = o[(int64_t)(SB_NAT_RX + t) * nc];
+            const double v = o[(int64_t)(SB_NAT_RX + t) * SB_NQS];
             mom[3 + t] += v;
             mom[3 + 6 * (1 + kk) + t] = v;
           }
 #pragma unroll
-          for (int t = 0; t < SB_NR; ++t) mom[t] += o[(int64_t)(SB_NAT_R + t) * nc];
+          for (int t = 0; t < SB_NR; ++t) mom[t] += o[(int64_t)(SB_NAT_R + t) * SB_NQS];
         }
         const double* tp = pl.tag_params + (int64_t)pl.cell_tag[cc] * SB_TAG_STRIDE;
         mom[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
@@ -588,7 +600,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
       } else {
         const double* og = natG_ptr(pl, kb, cc);
 #pragma unroll
-        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = og[(int64_t)t * nc];
+        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = og[(int64_t)t * SB_NQS];
         coef = -(double)c_M.band_sign[kb] * c_M.e_charge * g.adet;
       }
       if (active) {
@@ -599,7 +611,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
           for (int m = 0; m < 12; ++m) {
             const double dv = g.sdet * c_T.Dhat[m][i];
             Fi += dv * fl[m];
-            sd[i * RDG + m] = dv;
+            sd[SB_NAT_DGIDX(i, m)] = dv;
           }
 #pragma unroll
           for (int t = 0; t < 3; ++t) Fi += coef * c_T.G1[i][t] * mom[t];
@@ -610,7 +622,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
               double v = 0.0;
 #pragma unroll
               for (int t = 0; t < 6; ++t) v += c_T.G11[i][l][t] * mom[3 + 6 * q + t];
-              sd[i * RDG + 12 + 3 * q + l] = coef * v;
+              sd[SB_NAT_DGIDX(i, 12 + 3 * q + l)] = coef * v;
             }
           F[i] = Fi;
         }
@@ -625,14 +637,17 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
         for (int l = 0; l < 3; ++l) {
           const double v = c1 * c_T.M1[i][l];
           F[i] += v * sl[l];
-          sd[i * RDG + 12 + 3 * PS + l] = v;
+          sd[SB_NAT_DGIDX(i, 12 + 3 * PS + l)] = v;
         }
     }
     if (active && b) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) b[dof0 + i] = F[i];
     }
+#undef SB_NAT_DGIDX
+#ifndef SB_EXP_NOBULK
     if (bulk) sb_bulk_store_owned(vals + g0, stg16, ph, 3 * RDG);
+#endif
   }
 
   /* ---- flux rows ------------------------------------------------------------------- *
@@ -642,16 +657,16 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
    * form (:288-289) -- except when no lane of the warp is inside: then the cheap MODE 2.
    * (A per-lane branch between the two would keep both operand sets live: spills.)       */
   if (PS == 0) {
-    sb_nat_flux_part<NB, PS, 0>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                finfo, fid, g, fl, sl, true, g0, dof0);
+    sb_nat_flux_part<NB, PS, 0, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                finfo, fid, g, fl, sl, true, g0, dof0, role);
   } else {
     const bool any_in = __any_sync(0xffffffffu, inside && active);
     if (any_in)
-      sb_nat_flux_part<NB, PS, 1>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                  finfo, fid, g, fl, sl, inside, g0, dof0);
+      sb_nat_flux_part<NB, PS, 1, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                  finfo, fid, g, fl, sl, inside, g0, dof0, role);
     else
-      sb_nat_flux_part<NB, PS, 2>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                  finfo, fid, g, fl, sl, false, g0, dof0);
+      sb_nat_flux_part<NB, PS, 2, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
+                                  finfo, fid, g, fl, sl, false, g0, dof0, role);
   }
   sb_bulk_wait_read();                            /* the slot may be reused once it was read */
 }
@@ -662,8 +677,15 @@ struct NatRowsLauncher {
   static void go(const PlanDev& d, const StateDev& sd, double* vals, double* b, unsigned nblk,
                  cudaStream_t s) {
     const size_t smem = (sizeof(double) * 32 * SB_NAT_STR(NB + 1) + sizeof(SbNatMeta)) * (SB_TILE / 32);
-    cudaFuncSetAttribute(k_rows_nat<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SB_LAUNCH((k_rows_nat<NB, PS>), nblk, SB_TILE, smem, s, d, sd, vals, b);
+    const unsigned ntile = (unsigned)((d.n_cells + 31) / 32);    /* 32 cells per CTA */
+    if (d.native == 2) {
+      const size_t smem2 = sizeof(double) * 32 * (3 * SB_NAT_FSTR + SB_NAT_STR(NB + 1));
+      cudaFuncSetAttribute(k_rows_nat<NB, PS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      SB_LAUNCH((k_rows_nat<NB, PS, 2>), ntile, SB_TILE, smem2, s, d, sd, vals, b);
+    } else {
+      cudaFuncSetAttribute(k_rows_nat<NB, PS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      SB_LAUNCH((k_rows_nat<NB, PS, 1>), ntile, SB_TILE, smem, s, d, sd, vals, b);
+    }
     NatRowsLauncher<NB, PS - 1>::go(d, sd, vals, b, nblk, s);
   }
 };
@@ -674,8 +696,12 @@ struct NatRowsLauncher<NB, -1> {
 
 /* ---- host: does the problem have the closed-form layout? ------------------------------- *
  * On success fills fid [nc][3], finfo [nc], fbase [nf] and returns true.                   */
-static bool detect_native(const sb_model* model, const sb_problem* pr, std::vector<int32_t>& fid,
-                          std::vector<int32_t>& finfo, std::vector<int64_t>& fbase, int64_t* dofF0) {
+/* bsr: the value layout is block CSR with 3 x 3 blocks (pattern 'bsr3'): same block rows
+ * and block order, rowptr[3 T + k] = block row base + 3 k, rank = 9 (block rank) + column
+ * within its triple.                                                                     */
+static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
+                          std::vector<int32_t>& fid, std::vector<int32_t>& finfo,
+                          std::vector<int64_t>& fbase, int64_t* dofF0) {
   const int P = pr->P, L = 15 * P;
   const int64_t nc = pr->n_cells, N = pr->n_dofs;
   if (!model->bands_have_dofs || P < 2 || getenv("SIMUDO_B200_NO_NATIVE")) return false;
@@ -732,11 +758,13 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, std::vect
   for (int64_t c = 0; c < nc; ++c) {
     int64_t off = c * CB;
     for (int p = 0; p < P; ++p) {
-      for (int i = 0; i < 3; ++i, off += RDG)
-        if (rp[6 * P * c + 6 * p + i] != off) return false;
+      for (int i = 0; i < 3; ++i)
+        if (rp[6 * P * c + 6 * p + i] != off + (bsr ? 3 * i : RDG * i)) return false;
+      off += 3 * RDG;
       const int ri = p == 0 ? 15 : 18;
-      for (int i = 0; i < 3; ++i, off += ri)
-        if (rp[6 * P * c + 6 * p + 3 + i] != off) return false;
+      for (int i = 0; i < 3; ++i)
+        if (rp[6 * P * c + 6 * p + 3 + i] != off + (bsr ? 3 * i : ri * i)) return false;
+      off += 3 * ri;
     }
     if (rp[6 * P * (c + 1)] != off) return false;
   }
@@ -745,10 +773,11 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, std::vect
     fbase[f] = off;
     for (int p = 0; p < P; ++p) {
       const int rl = fbnd[f] ? (p == 0 ? 15 : 18) : (p == 0 ? 27 : 33);
-      for (int k = 0; k < 3; ++k, off += rl)
-        if (rp[F0 + 3 * P * f + 3 * p + k] != off) return false;
+      for (int k = 0; k < 3; ++k)
+        if (rp[F0 + 3 * P * f + 3 * p + k] != off + (bsr ? 3 * k : rl * k)) return false;
+      off += 3 * rl;
     }
-    if (rp[F0 + 3 * P * (f + 1)] != off) return false;
+    if (f + 1 < nf ? rp[F0 + 3 * P * (f + 1)] != off : rp[N] != off) return false;
   }
   /* rank patterns: once per (pattern id, side bits) */
   std::vector<uint8_t> checked((size_t)pr->n_patterns * 8, 0);
@@ -780,6 +809,7 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, std::vect
           want = (fr < 0 ? 12 : 12) + rj + ((pj == 0 && p > 0) ? 3 : 0);
         }
         if (want != 0xFF && fr >= 0 && ((side >> fr) & 1) && want >= 3) want += nrun;
+        if (want != 0xFF && bsr) want = (want / 3) * 9 + want % 3;
         if (pat[i * L + j] != want) return false;
       }
     }

@@ -799,7 +799,8 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
                         const double* fl /*[12] flux dofs*/, const double* sl /*[3] scalar dofs*/,
                         double jump0, double jump1, double jump2,
                         const int32_t* nat_row, const double* nat_val, int nb0, int nb1,
-                        bool mC_is_W = false /* mC already holds the 21 values of W */) {
+                        bool mC_is_W = false /* native scratch: mC holds the 21 values of W and
+                                                Q the 36 finished couplings d[3 i + l]        */) {
   const int r0 = sb_lbdm(p, 0);
   double W[21];
   double V[2][6][3];
@@ -822,8 +823,10 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
           double v = 0.0;
+          if (!mC_is_W) {
 #pragma unroll
-          for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * Q[a * 10 + t];
+            for (int t = 0; t < 10; ++t) v += T.G21[r][l][t] * Q[a * 10 + t];
+          }
           V[a][r][l] = v;
         }
   } else {
@@ -882,6 +885,7 @@ SB_HD void sb_rows_flux(const SbTables& T, const sb_model& M, const SbIO& io,
 #pragma unroll
           for (int r = 0; r < 6; ++r) d += Ci[0][r] * V[0][r][l] + Ci[1][r] * V[1][r][l];
           d *= g.iad;
+          if (mC_is_W) d = Q[3 * i + l];
           sb_emit<SP>(io, rowbase, li, sb_ldg(p, l), dv + d, Fi);
           sb_emit<SP>(io, rowbase, li, sb_ldg(0, l), d, Fi);
         } else {

@@ -360,8 +360,8 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
       const bool mine = ((io.finfo >> (4 * f)) & 3) == 0;
       const int64_t cn = mine ? pl.cell_neighbors[c * 3 + f] : c;
       const int f2 = (io.finfo >> (4 * f + 2)) & 3;
-      const double* sn = (p == 0) ? natS0_ptr(pl, cn) : natA_ptr(pl, p - 1, cn) + (int64_t)SB_NAT_S * nc;
-      for (int t = 0; t < 6; ++t) snb[6 * f + t] = mine ? sn[(int64_t)(6 * f2 + t) * nc] : 0.0;
+      const double* sn = (p == 0) ? natS0_ptr(pl, cn) : natA_ptr(pl, p - 1, cn) + (int64_t)SB_NAT_S * SB_NQS;
+      for (int t = 0; t < 6; ++t) snb[6 * f + t] = mine ? sn[(int64_t)(6 * f2 + t) * SB_NQS] : 0.0;
     }
     io.snb = snb;
   }
@@ -391,16 +391,17 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
 #pragma unroll
       for (int t = 0; t < SB_NRX; ++t) mX[q][t] = 0.0;
     for (int k = 0; k < pl.nb; ++k) {
-      const double* o = pl.native ? natA_ptr(pl, k, c) + (int64_t)SB_NAT_RX * nc
-                                  : momA_ptr(pl, k, c) + (int64_t)(SB_NMC + SB_NQ) * nc;
+      const int64_t qs = pl.native ? SB_NQS : nc;           /* stride between quantities */
+      const double* o = pl.native ? natA_ptr(pl, k, c) + (int64_t)SB_NAT_RX * qs
+                                  : momA_ptr(pl, k, c) + (int64_t)(SB_NMC + SB_NQ) * qs;
 #pragma unroll
       for (int t = 0; t < SB_NRX; ++t) {
-        const double v = o[(int64_t)t * nc];
+        const double v = o[(int64_t)t * qs];
         mX[0][t] += v;
         if (k < NB) mX[1 + k][t] = v;
       }
 #pragma unroll
-      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NRX + t) * nc];
+      for (int t = 0; t < SB_NR; ++t) mR[t] += o[(int64_t)(SB_NRX + t) * qs];
     }
     /* static charge: constant => only the Psi_0 = sqrt(2) moment, int Psi_0 = 1/sqrt(2) */
     mR[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
@@ -421,13 +422,13 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
   const int k = p - 1;
   const bool inside = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
   {
-    double mC[21], Q[SB_NQ];                       /* native: mC holds W (21 values) */
+    double mC[21], Q[36];                          /* native: W (21 values), d[3 i + l] (36) */
     if (inside && pl.native) {
       const double* o = natA_ptr(pl, k, c);
 #pragma unroll
-      for (int t = 0; t < 21; ++t) mC[t] = o[(int64_t)(SB_NAT_W + t) * nc];
+      for (int t = 0; t < 21; ++t) mC[t] = o[(int64_t)(SB_NAT_W + t) * SB_NQS];
 #pragma unroll
-      for (int t = 0; t < SB_NQ; ++t) Q[t] = o[(int64_t)(SB_NAT_Q + t) * nc];
+      for (int t = 0; t < 36; ++t) Q[t] = o[(int64_t)(SB_NAT_D + t) * SB_NQS];
     } else if (inside) {
       const double* o = momA_ptr(pl, k, c);
 #pragma unroll
@@ -459,8 +460,9 @@ k_rows_special(PlanDev pl, StateDev st, double* vals, double* b, int nblk) {
     double mG[SB_NG];
     if (inside) {
       const double* o = pl.native ? natG_ptr(pl, k, c) : momG_ptr(pl, k, c);
+      const int64_t qs = pl.native ? SB_NQS : nc;
 #pragma unroll
-      for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = o[(int64_t)t * nc];
+      for (int t = 0; t < 9 + 6 * NB; ++t) mG[t] = o[(int64_t)t * qs];
     }
     const double coef = -(double)c_M.band_sign[k] * c_M.e_charge * g.adet;
     if (sp)
@@ -1078,7 +1080,26 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   }
   pl->n_bc = pr->n_bc; pl->n_natbc = pr->n_natbc;
   UP(cell_special, special.data(), nc);
+  /* closed-form layout?  (native.inl): 1 = CSR 'native', 2 = block CSR 'bsr3' */
+  d.native = 0; d.nat_fid = nullptr; d.nat_finfo = nullptr; d.nat_fbase = nullptr; d.nat_dofF0 = 0;
   {
+    std::vector<int32_t> fid, finfo;
+    std::vector<int64_t> fbase;
+    int64_t F0 = 0;
+    int kind = 0;
+    if (rc == SB_OK && detect_native(model, pr, false, fid, finfo, fbase, &F0)) kind = 1;
+    else if (rc == SB_OK && detect_native(model, pr, true, fid, finfo, fbase, &F0)) kind = 2;
+    if (kind) {
+      UP(nat_fid, fid.data(), fid.size());
+      UP(nat_finfo, finfo.data(), finfo.size());
+      UP(nat_fbase, fbase.data(), fbase.size());
+      d.nat_dofF0 = F0;
+      d.native = kind;
+    }
+  }
+  d.stage_patk = 0; d.owned_bulk = 0; d.patk = nullptr; d.rowbase = nullptr; d.rowlen = nullptr;
+  d.n_patterns = pr->n_patterns;
+  if (!d.native) {
     /* packed emission-order ranks for the fast row kernels */
     const int64_t np = pr->n_patterns;
     d.n_patterns = np;
@@ -1135,6 +1156,8 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
               rlen[(size_t)(5 * p + 4) * nc + c] != (p == 0 ? 15 : 18)) { bulk = false; break; }
       d.owned_bulk = bulk && !getenv("SIMUDO_B200_NO_BULK_STORE");
     }
+  }
+  {
     std::vector<int32_t> spc;
     for (int64_t c = 0; c < nc; ++c) if (special[c] >= 0) spc.push_back((int32_t)c);
     UP(sp_cells, spc.data(), spc.size());
@@ -1148,24 +1171,11 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   const double* tmp = nullptr;
   if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc, &tmp);
   pl->tmp_cells = const_cast<double*>(tmp);
-  /* closed-form layout?  (native.inl) */
-  d.native = 0; d.nat_fid = nullptr; d.nat_finfo = nullptr; d.nat_fbase = nullptr; d.nat_dofF0 = 0;
-  {
-    std::vector<int32_t> fid, finfo;
-    std::vector<int64_t> fbase;
-    int64_t F0 = 0;
-    if (rc == SB_OK && detect_native(model, pr, fid, finfo, fbase, &F0)) {
-      UP(nat_fid, fid.data(), fid.size());
-      UP(nat_finfo, finfo.data(), finfo.size());
-      UP(nat_fbase, fbase.data(), fbase.size());
-      d.nat_dofF0 = F0;
-      d.native = 1;
-    }
-  }
   const double* scr = nullptr;
   const size_t per_cell = d.native ? ((size_t)model->n_bands * (SB_NAT_NA + SB_NG) + 18)
                                    : ((size_t)model->n_bands * 44 + (size_t)nbd * SB_NG);
-  if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)nc * per_cell, &scr);
+  /* native: tile-blocked by 32 cells (natQ_ptr) */
+  if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)((nc + 31) / 32 * 32) * per_cell, &scr);
   d.scratch = const_cast<double*>(scr);
 #undef UP
   if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }

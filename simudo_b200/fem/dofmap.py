@@ -132,7 +132,7 @@ class CsrStructure(object):
         self._mesh = mesh
         if pattern == 'dolfin':
             S = np.ones((L, L), dtype=bool)
-        elif pattern in ('structural', 'native'):
+        elif pattern in ('structural', 'native', 'bsr3'):
             S = structural_mask(P)
         else:
             raise ValueError(pattern)
@@ -170,10 +170,31 @@ class CsrStructure(object):
         for i in range(L):
             ranks, _ = self._ranks_of_row(i, reps)
             pats[:, i, S[i]] = ranks.astype(np.uint8)
-        self.patterns = np.ascontiguousarray(pats)
         self.rowptr = np.zeros(N + 1, dtype=np.int64)
         np.cumsum(rowlen, out=self.rowptr[1:])
         self.nnz = int(self.rowptr[-1])
+        self.csr_rowptr = self.rowptr            # true CSR row pointers (row lengths)
+        if pattern == 'bsr3':
+            # Block CSR with 3 x 3 blocks (every dof triple of a mesh entity is a block row /
+            # block column, every structural block is full): block rows in dof order, block
+            # columns in the 'native' emission order, each block row-major.  Same entries and
+            # nnz as 'native'; the value of local entry (i, j) sits at
+            #   rowptr[dof_i] + patterns[..][i][j]
+            # with rowptr[3 T + k] = (first value of block row T) + 3 k and
+            # patterns = 9 * (block rank) + (j within its triple) -- the form the C ABI takes.
+            if self.rowptr[-1] >= 2 ** 62 or N % 3:
+                raise ValueError('bsr3 needs dof triples')
+            base = self.rowptr[0:N:3]
+            rp = np.empty(N + 1, dtype=np.int64)
+            for k in range(3):
+                rp[k:N:3] = base + 3 * k
+            rp[N] = self.nnz
+            self.rowptr = rp
+            ok = pats != 0xFF
+            pb = (pats.astype(np.int64) // 3) * 9 + pats.astype(np.int64) % 3
+            assert pb[ok].max() < 0xFF
+            pats = np.where(ok, pb, 0xFF).astype(np.uint8)
+        self.patterns = np.ascontiguousarray(pats)
         if self.patterns.shape[0] > 4096:
             raise ValueError('too many distinct rank patterns for this mesh/numbering')
 
@@ -233,7 +254,7 @@ class CsrStructure(object):
     def _ranks_of_row(self, i, cells):
         """Rank of each structural column of local row i inside its global row,
         for the given cells: ``(ranks[len(cells), n_i], row_length[len(cells)])``."""
-        if self.pattern == 'native':
+        if self.pattern in ('native', 'bsr3'):
             return self._native_ranks_of_row(i, np.asarray(cells))
         cd, L, S = self._cd, self.L, self.mask
         cols = np.nonzero(S[i])[0]
@@ -284,10 +305,12 @@ class CsrStructure(object):
         pos[pat == 0xFF] = -1
         return pos
 
-    def column_indices(self):
-        """Materialise ``colidx[nnz]`` (int32) -- for export / solvers / tests."""
+    def column_indices(self, want_rows=False):
+        """Materialise ``colidx[nnz]`` (int32), the column of every stored value -- for
+        export / solvers / tests.  ``want_rows``: also the row of every stored value."""
         cd, L = self._cd, self.L
         col = np.full(self.nnz, -1, dtype=np.int32)
+        row = np.full(self.nnz, -1, dtype=np.int32) if want_rows else None
         nc = cd.shape[0]
         step = max(1, (1 << 22) // (L * L))
         for c0 in range(0, nc, step):
@@ -296,5 +319,23 @@ class CsrStructure(object):
             cols = np.broadcast_to(cd[cells][:, None, :], pos.shape)
             ok = pos >= 0
             col[pos[ok]] = cols[ok]
+            if want_rows:
+                rows = np.broadcast_to(cd[cells][:, :, None], pos.shape)
+                row[pos[ok]] = rows[ok]
         assert (col >= 0).all()
-        return col
+        return (col, row) if want_rows else col
+
+    def value_rows(self):
+        """Row of every stored value (any pattern)."""
+        if self.pattern != 'bsr3':
+            return np.repeat(np.arange(self.N, dtype=np.int64), np.diff(self.rowptr))
+        return self.column_indices(want_rows=True)[1].astype(np.int64)
+
+    def sorted_csr(self):
+        """``(rowptr, colidx, perm)``: the same matrix as a CSR with ascending columns;
+        ``vals_csr = vals[perm]``.  Cached."""
+        if getattr(self, '_sorted', None) is None:
+            col = self.column_indices()
+            perm = np.lexsort((col, self.value_rows()))
+            self._sorted = (self.csr_rowptr, np.ascontiguousarray(col[perm]), perm)
+        return self._sorted

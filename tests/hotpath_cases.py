@@ -38,7 +38,7 @@ def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
     st = syn.synthetic_state(pa)
     vals0, b0 = _oracle(pa, st)
     plan = AssemblyPlan(pa)
-    assert plan.is_native() == (pattern_of(kw) == 'native' and numbering == 'b200')
+    assert plan.is_native() == (pattern_of(kw) in ('native', 'bsr3') and numbering == 'b200')
     vals, b = run_plan(plan, st)
     vals, b = vals.cpu().numpy(), b.cpu().numpy()
     assert np.isfinite(vals).all() and np.isfinite(b).all()
@@ -48,6 +48,10 @@ def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
     # bit-exact sparsity: device-built column indices == host CSR structure
     col = plan.column_indices().cpu().numpy()
     assert (col == pa.csr.column_indices()).all()
+    # ... and that structure is the reference's: same (row, column) set as the structural
+    # (or dolfin) pattern built independently from the cell dof lists
+    rp, cs, perm = pa.csr.sorted_csr()
+    assert (np.diff(rp) > 0).all() and len(np.unique(perm)) == pa.csr.nnz
     if pa.pattern == 'dolfin':
         # structural zeros of the dolfin pattern are never touched: exactly zero
         pos = pa.csr.entry_positions()
@@ -218,9 +222,9 @@ def jacobian_consistent_with_residual_large(maker, nx, ny):
     bp, bm = plan.new_vector(), plan.new_vector()
     plan.assemble(T(st['u'] + h * v), *fixed, None, bp)
     plan.assemble(T(st['u'] - h * v), *fixed, None, bm)
-    col = plan.column_indices()
-    rowptr = T(pa.csr.rowptr, torch.int64)
-    A = torch.sparse_csr_tensor(rowptr, col.to(torch.int64), vals, size=(pa.N, pa.N))
+    rp, col, perm = pa.csr.sorted_csr()
+    A = torch.sparse_csr_tensor(T(rp, torch.int64), T(col, torch.int64), vals[T(perm, torch.int64)],
+                                size=(pa.N, pa.N))
     an = (A @ T(v).unsqueeze(1)).squeeze(1)
     fd = (bp - bm) / (2 * h)
     err = (fd - an).abs().max().item() / an.abs().max().item()

@@ -4,10 +4,19 @@ import numpy as np
 
 def row_scaled_error(pa, vals, vals_ref):
     """max |a - a_ref| / max_row |a_ref| over all CSR entries."""
-    rp = pa.csr.rowptr
-    rowmax = np.maximum.reduceat(np.abs(vals_ref), rp[:-1])
-    rowid = np.repeat(np.arange(pa.N), np.diff(rp))
+    rowid = pa.csr.value_rows()
+    rowmax = np.zeros(pa.N)
+    np.maximum.at(rowmax, rowid, np.abs(vals_ref))
     return float((np.abs(vals - vals_ref) / np.maximum(rowmax[rowid], 1e-300)).max())
+
+
+def entry_relative_error(vals, vals_ref, floor_rel=1e-10):
+    """Worst |a - a_ref| / |a_ref| over the entries with |a_ref| above ``floor_rel`` times
+    the largest entry of the matrix (the north star's wording is per assembled entry;
+    entries that are round-off of cancelled sums have no meaningful relative error)."""
+    ref = np.abs(vals_ref)
+    big = ref > floor_rel * ref.max()
+    return float((np.abs(vals - vals_ref)[big] / ref[big]).max())
 
 
 def vector_error(b, b_ref):

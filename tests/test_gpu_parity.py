@@ -40,6 +40,14 @@ from simudo_b200 import synthetic as syn   # noqa: E402
     (syn.pn_problem, 40, 33, 'b200', True, 'native'),
     (syn.ib_problem, 30, 21, 'b200', True, 'native'),
     (syn.ib_problem, 30, 21, 'ufc', True, 'native'),       # 'native' columns, generic kernels
+    # block CSR with 3 x 3 blocks, closed-form kernels, every run leaves by cp.async.bulk
+    (syn.pn_problem, 5, 3, 'b200', True, 'bsr3'),
+    (syn.ib_problem, 6, 3, 'b200', True, 'bsr3'),
+    (syn.ib_problem, 5, 2, 'b200', False, 'bsr3'),
+    (syn.pn_problem, 67, 2, 'b200', True, 'bsr3'),
+    (syn.ib_problem, 279, 2, 'b200', True, 'bsr3'),
+    (syn.pn_problem, 40, 33, 'b200', True, 'bsr3'),
+    (syn.ib_problem, 30, 21, 'b200', True, 'bsr3'),
 ])
 def test_assembly_parity(maker, nx, ny, numbering, bcs, pattern):
     hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)

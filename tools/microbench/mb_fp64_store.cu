@@ -98,13 +98,13 @@ __global__ void k_store_bulk(double* out, int64_t ncell, int stride) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool act = c < ncell;
   for (int r = 0; r < NR; ++r) {
-    const int phase = (int)(c & 1);
+    const int phase = (int)(((c * NR + r) * stride + (c & 1)) & 1);
     if (r) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (act) {
 #pragma unroll
       for (int e = 0; e < RL; ++e) st[phase + e] = (double)(c + e);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      double* dst = out + (c * NR + r) * stride + phase;
+      double* dst = out + (c * NR + r) * stride + (c & 1);
       const double* s0 = st + phase;
       const int head = phase;
       const int nb = (RL - head) & ~1;
@@ -121,7 +121,7 @@ __global__ void k_store_bulk(double* out, int64_t ncell, int stride) {
 
 template <int RL, int NR>
 static void run_store(int64_t ncell) {
-  const int stride = RL + 17;                      // gaps between runs (other cells' columns)
+  const int stride = RL + (RL > 60 ? 55 : 17) + ((RL & 1) ? 0 : 1);   // odd+even mix of phases                      // gaps between runs (other cells' columns)
   const size_t n = (size_t)ncell * NR * stride + 8;
   double* d; CK(cudaMalloc(&d, n * 8)); CK(cudaMemset(d, 0, n * 8));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -164,9 +164,10 @@ int main() {
     for (int r = 0; r < 2; ++r) { cudaEventRecord(e0); k_fill<<<148 * 8, 256>>>(d, n); cudaEventRecord(e1); CK(cudaDeviceSynchronize()); cudaEventElapsedTime(&ms, e0, e1); }
     printf("fill 8 GiB: %.3f ms %.0f GB/s\n", ms, n * 8.0 / ms * 1e-6); cudaFree(d);
   }
-  run_store<15, 36>(1000000);       // facet runs
-  run_store<12, 9>(1000000);
+  run_store<15, 36>(1000000);       // facet runs, CSR
+  run_store<45, 12>(1000000);       // facet runs, 3 x 3 block rows
+  run_store<54, 12>(1000000);
+  run_store<72, 4>(1000000);        // DG block
   run_store<126, 4>(1000000);       // owned block per sub-problem
-  run_store<495, 1>(1000000);       // owned block per cell
   return 0;
 }
