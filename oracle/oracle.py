@@ -69,7 +69,7 @@ def _problem_struct():
             ('n_facet_q', C.c_int32), ('facet_w', C.c_void_p),
             ('facet_trace', C.c_void_p),
             ('u', C.c_void_p), ('base_w', C.c_void_p), ('thmeq_phi', C.c_void_p),
-            ('phi_opt', C.c_void_p), ('n_threads', C.c_int32)]
+            ('phi_opt', C.c_void_p), ('n_threads', C.c_int32), ('cols_sorted', C.c_int32)]
     return _Problem
 
 
@@ -78,16 +78,25 @@ def _ptr(a):
 
 
 class Oracle(object):
-    def __init__(self, pa, n_threads=1):
+    def __init__(self, pa, n_threads=1, colidx=None):
+        """``colidx``: the column of every stored value if the caller already has it (large
+        meshes: materialising it on the host takes minutes); default ``pa.csr``'s."""
         self.pa = pa
         self.n_threads = n_threads
         self._keep = []
-        self.colidx = pa.csr.column_indices()
-        # the C restatement inserts by binary search in ascending columns (like PETSc's
-        # MatSetValues); layouts with another column order inside a row ('native') are
-        # assembled in sorted order and permuted back into the caller's layout
-        self._rowptr_csr, self._colidx_sorted, self._perm = pa.csr.sorted_csr()
-        self._sorted = bool((self._perm == np.arange(len(self._perm))).all())
+        # The C restatement inserts by searching the column in the row (like PETSc's
+        # MatSetValues).  CSR layouts are assembled in place (linear search when the columns
+        # of a row are not ascending: 'native'); the block layout 'bsr3' is assembled as a
+        # sorted CSR and permuted back into the caller's layout.
+        if pa.csr.pattern == 'bsr3':
+            self._rowptr_csr, self._colidx_sorted, self._perm = pa.csr.sorted_csr()
+            self._sorted, self._inplace_sorted = False, True
+            self.colidx = None
+        else:
+            self.colidx = pa.csr.column_indices() if colidx is None else np.ascontiguousarray(colidx, dtype=np.int32)
+            self._rowptr_csr, self._colidx_sorted, self._perm = pa.csr.rowptr, self.colidx, None
+            self._sorted = True
+            self._inplace_sorted = pa.csr.pattern != 'native'
         self._rules = {}
         m = pa.model
         self.rule_default = self._make_rule(*fl.default_triangle_scheme(4))
@@ -149,6 +158,7 @@ class Oracle(object):
         q.rule_super, q.rule_g = self.rule_super, self.rule_g
         q.n_facet_q = len(self.facet_w)
         q.n_threads = self.n_threads
+        q.cols_sorted = 1 if self._inplace_sorted else 0
         return q, keep
 
     def assemble(self, u, base_w=None, thmeq_phi=None, phi_opt=None,
@@ -179,8 +189,8 @@ class Oracle(object):
 
     def to_scipy(self, vals):
         import scipy.sparse as sp
-        return sp.csr_matrix((np.asarray(vals)[self._perm], self._colidx_sorted, self._rowptr_csr),
-                             shape=(self.pa.N, self.pa.N))
+        v = np.asarray(vals) if self._perm is None else np.asarray(vals)[self._perm]
+        return sp.csr_matrix((v, self._colidx_sorted, self._rowptr_csr), shape=(self.pa.N, self.pa.N))
 
 
 # ---------------------------------------------------------------------------

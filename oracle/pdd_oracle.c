@@ -107,6 +107,8 @@ typedef struct {
   const double* thmeq_phi;        /* [nc][6] or NULL */
   const double* phi_opt;          /* [n_fields][nc][6] or NULL */
   int32_t n_threads;
+  int32_t cols_sorted;            /* 1: ascending columns per row (binary search);
+                                     0: any order inside a row (linear search) */
 } oracle_problem;
 
 static double fd_f(double x) { return 1.0 / (1.0 + exp(x)); }
@@ -214,6 +216,11 @@ static dual generation(const sb_model* M, const double* tp, int k,
 
 static int64_t find_col(const oracle_problem* Q, int64_t row, int32_t col) {
   int64_t lo = Q->rowptr[row], hi = Q->rowptr[row + 1] - 1;
+  if (!Q->cols_sorted) {
+    for (int64_t k = lo; k <= hi; ++k)
+      if (Q->colidx[k] == col) return k;
+    return -1;
+  }
   while (lo <= hi) {
     int64_t mid = (lo + hi) >> 1;
     int32_t c = Q->colidx[mid];

@@ -564,6 +564,8 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
 #pragma unroll
   for (int l = 0; l < NB; ++l) {
     B.w[l] = w0[l] + dgv[3 + 3 * l] * l0 + dgv[4 + 3 * l] * X + dgv[5 + 3 * l] * Y;
+    /* (skipping the bands without states in this region, N = 0, was measured slower: the
+       branch splits the point's basic block and its exp chains no longer interleave) */
     sb_band_u_kind(K[l], M.band_kind[l], phi + B.w[l], B.u[l], B.du[l]);
     B.u0[l] = 0.0;
   }

@@ -18,7 +18,7 @@ from simudo_b200.fem.assembly import AssemblyPlan
 from simudo_b200.fem.problem_arrays import ProblemArrays
 from simudo_b200.mesh import Product2DMesh
 
-from parity_util import row_scaled_error, vector_error, run_plan
+from parity_util import row_scaled_error, vector_error, run_plan, entry_relative_error
 
 A_TOL = 1e-12
 B_TOL = 1e-12
@@ -59,6 +59,59 @@ def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
         S = structural_mask(pa.P)
         assert (vals[pos[:, ~S]] == 0.0).all()
     return pa, st, plan, vals, b, vals0, b0
+
+
+def assembly_parity_at_scale(nx, ny):
+    """The benchmarked configuration (bench.py: IB cell, nx x ny points, BCs on) against the
+    oracle: what small cases cannot see -- 64-bit value offsets past 2^31, full grids, the
+    closed forms at 1e9 non-zeros.  CSR 'native' layout against the oracle (all host
+    threads, ~15 s per 1M cells); the block layout 'bsr3' bit for bit against 'native'
+    entry by entry.  Returns (cells, row-relative, entry-relative, residual) errors."""
+    import os
+    pa = syn.ib_problem(nx=nx, ny=ny, pattern='native')
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    assert plan.is_native()
+    vals, b = run_plan(plan, st)
+    col = plan.column_indices().cpu().numpy()
+    # structure: the device-built columns against the host pattern on a sample of cells
+    # (entry-wise on the whole mesh at the small sizes of assembly_parity)
+    rng = np.random.default_rng(0)
+    cells = np.unique(np.concatenate([np.arange(64), pa.n_cells - 1 - np.arange(64),
+                                      rng.integers(0, pa.n_cells, 4096)]))
+    pos = pa.csr.entry_positions(cells)
+    cols = np.broadcast_to(pa.cell_dofs[cells][:, None, :], pos.shape)
+    ok = pos >= 0
+    assert (col[pos[ok]] == cols[ok]).all()
+    nthr = orc_mod.lib().pdd_oracle_max_threads()
+    orc = Oracle(pa, n_threads=nthr, colidx=col)
+    vals0, b0 = orc.assemble(st['u'], st['base_w'], st['thmeq_phi'], st['phi_opt'],
+                             st['bc_values'], st['natbc_values'])
+    v = vals.cpu().numpy()
+    assert np.isfinite(v).all()
+    ea = row_scaled_error(pa, v, vals0)
+    ee = entry_relative_error(v, vals0)
+    eb = vector_error(b.cpu().numpy(), b0)
+    assert ea < A_TOL, 'Jacobian row-scaled error %.3e' % ea
+    assert eb < B_TOL, 'residual error %.3e' % eb
+    assert ee < 1e-9, 'worst entry-relative error %.3e' % ee
+    del v, vals0, orc
+    # block layout: same arithmetic, other placement -> identical bits, entry by entry
+    pa2 = syn.ib_problem(nx=nx, ny=ny, pattern='bsr3')
+    plan2 = AssemblyPlan(pa2)
+    assert plan2.is_native()
+    vals2, b2 = run_plan(plan2, st)
+    assert torch.equal(b2, b)
+    T = plan.tensor
+    step = 1 << 14
+    for c0 in range(0, pa.n_cells, step):
+        cs = np.arange(c0, min(pa.n_cells, c0 + step))
+        p1 = pa.csr.entry_positions(cs).ravel()
+        p2 = pa2.csr.entry_positions(cs).ravel()
+        ok = p1 >= 0
+        assert ((p2 >= 0) == ok).all()
+        assert torch.equal(vals[T(p1[ok], torch.int64)], vals2[T(p2[ok], torch.int64)])
+    return pa.n_cells, ea, ee, eb
 
 
 def thermal_equilibrium_mode():

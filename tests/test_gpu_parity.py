@@ -53,6 +53,17 @@ def test_assembly_parity(maker, nx, ny, numbering, bcs, pattern):
     hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)
 
 
+def test_assembly_parity_at_bench_scale():
+    """bench.py's configuration (IB cell, 708 x 708 points, 1 003 940 cells, 1.07e9 non-zeros)
+    against the oracle; SIMUDO_B200_SCALE_N=<points per axis> shrinks it for quick runs."""
+    import os
+    n = int(os.environ.get('SIMUDO_B200_SCALE_N', '708'))
+    cells, ea, ee, eb = hc.assembly_parity_at_scale(n, n)
+    print('at scale: %d cells, row-relative %.2e, entry-relative %.2e, residual %.2e'
+          % (cells, ea, ee, eb))
+    assert cells > 2 * (n - 1) ** 2 - 1
+
+
 def test_thermal_equilibrium_mode():
     hc.thermal_equilibrium_mode()
 
