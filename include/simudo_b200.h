@@ -166,7 +166,9 @@ int64_t sb_launch_count(void);
  * exterior-facet natural terms, the base_w interior-facet jump term, and the
  * element-wise symmetric Dirichlet application with x0 lifting.
  * d_vals [nnz] (dolfin pattern; structural zeros are written once by
- * sb_plan_zero_values and never touched again), d_b [N].  Either may be NULL.  */
+ * sb_plan_zero_values and never touched again), d_b [N].  Either may be NULL.
+ * d_vals must be 16-byte aligned (bulk copies; SB_ERR_ARG otherwise) -- any cudaMalloc'ed
+ * array is, a slice at an odd element offset is not.                              */
 int sb_assemble(sb_plan* plan, const sb_state* state,
                 double* d_vals, double* d_b, void* stream);
 int sb_plan_zero_values(sb_plan* plan, double* d_vals, void* stream);
@@ -229,6 +231,14 @@ int  sb_band_set_refinement(sb_band_solver* s, int32_t steps);
  * 0 = ok, j+1 = zero pivot in column j (synchronises the stream when given).        */
 int  sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_t vstride,
                    const double* d_b, double* d_x, int32_t* h_info, void* stream);
+
+/* r = b - A x with a compensated (double-double) row sum for a device CSR matrix: the
+ * residual the refinement steps of the Newton linear solve need (a Newton row mixes entries
+ * of size 1 and 1e28).  MUMPS does the analogous work internally (ICNTL(10), scaling
+ * ICNTL(6)/(8), simudo/fem/newton_solver.py:140-146).                               */
+int sb_csr_residual_dd(int64_t n, const int64_t* d_rowptr, const int32_t* d_colidx,
+                       const double* d_vals, const double* d_x, const double* d_b,
+                       double* d_r, void* stream);
 
 /* ---- a10: optical sub-problems -------------------------
  * One scalar photon-flux field per (photon energy, direction) on CG2 over the PDD

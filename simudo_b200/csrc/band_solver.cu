@@ -24,6 +24,7 @@
 #define SBB_THREADS 1024
 #endif
 #include <math.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -271,6 +272,27 @@ __global__ void k_band_residual_dd(int64_t n, const int64_t* rowptr, const int32
   }
 }
 
+/* r = b - A x for a general CSR matrix, same compensated accumulation (used by the
+ * multifrontal solver's iterative refinement, simudo_b200/fem/multifrontal.py) */
+__global__ void k_csr_residual_dd(int64_t n, const int64_t* rowptr, const int32_t* colidx,
+                                  const double* vals, const double* x, const double* b, double* r) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n;
+       row += (int64_t)gridDim.x * blockDim.x) {
+    double hi = b[row], lo = 0.0;
+    for (int64_t k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const double a = -vals[k], xv = x[colidx[k]];
+      const double p = a * xv;
+      const double pe = fma(a, xv, -p);
+      const double s = hi + p;
+      const double bb = s - hi;
+      const double se = (hi - (s - bb)) + (p - bb);
+      hi = s;
+      lo += se + pe;
+    }
+    r[row] = hi + lo;
+  }
+}
+
 /* x[r] += cs[r] * work[perm[r]] */
 __global__ void k_band_accumulate(int64_t n, const int32_t* perm, const double* cs,
                                   const double* work, double* x, int64_t xstride) {
@@ -438,5 +460,27 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
     memcpy(h_info, s->info, nsys * sizeof(int32_t));
 #endif
   }
+  return SB_OK;
+}
+
+/* r = b - A x in double-double accumulation for a device CSR matrix (rows contiguous,
+ * any column order).  Replaces nothing in the reference (MUMPS refines internally,
+ * newton_solver.py:140-146); used by the multifrontal solver's refinement steps.   */
+extern "C" int sb_csr_residual_dd(int64_t n, const int64_t* d_rowptr, const int32_t* d_colidx,
+                                  const double* d_vals, const double* d_x, const double* d_b,
+                                  double* d_r, void* stream) {
+  if (n < 0 || !d_rowptr || !d_colidx || !d_vals || !d_x || !d_b || !d_r) {
+    snprintf(g_sb_err, sizeof g_sb_err, "bad argument to sb_csr_residual_dd");
+    return SB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  (void)st;
+#ifdef SB_EMUL_BUILD
+  SBB_LAUNCH(k_csr_residual_dd, 2u, 32, 0, st, n, d_rowptr, d_colidx, d_vals, d_x, d_b, d_r);
+#else
+  const unsigned gx = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  SBB_LAUNCH(k_csr_residual_dd, gx ? gx : 1u, 256, 0, st, n, d_rowptr, d_colidx, d_vals, d_x, d_b, d_r);
+#endif
+  BTRY(cudaGetLastError());
   return SB_OK;
 }

@@ -33,7 +33,18 @@ __constant__ sb_model c_M;
 thread_local char g_sb_err[512] = "";   /* shared with band_solver.cu */
 #define g_err g_sb_err
 static std::atomic<long long> g_launches{0};
-static const void* g_tables_owner = nullptr;
+/* which plan's tables sit in the __constant__ copies, per device (one copy per device) */
+#define SB_MAX_DEVICES 64
+static const void* g_tables_owner[SB_MAX_DEVICES] = {nullptr};
+static int current_device_slot() {
+#ifdef SB_EMUL_BUILD
+  return 0;
+#else
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < SB_MAX_DEVICES) ? dev : 0;
+#endif
+}
 
 #define CUDA_TRY(x)                                                          \
   do {                                                                       \
@@ -774,12 +785,9 @@ struct RowsLauncher {
     if (d.stage_patk) {
       const size_t smem = (sizeof(double) * 32 * SB_STAGE_STRIDE + sizeof(SbWarpMeta))
                           * (SB_TILE / 32) + (size_t)SB_MAX_SMEM_PATTERNS * 15 * 32;
-      static bool attr_set = false;        /* per instantiation */
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_rows_staged<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-        attr_set = true;
-      }
+      /* per device and cheap: set on every launch (a process may drive several GPUs) */
+      cudaFuncSetAttribute(k_rows_staged<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
       SB_LAUNCH((k_rows_staged<NB, PS>), nblk, SB_TILE, smem, s, d, sd, vals, b);
     } else
       SB_LAUNCH((k_rows_fast<NB, PS>), nblk, SB_TILE, 0, s, d, sd, vals, b);
@@ -983,7 +991,8 @@ extern "C" void sb_plan_destroy(sb_plan* pl) {
     for (int i = 0; i < 3; ++i) cudaEventDestroy(pl->evs[i]);
   }
 #endif
-  if (g_tables_owner == pl) g_tables_owner = nullptr;
+  for (int i = 0; i < SB_MAX_DEVICES; ++i)
+    if (g_tables_owner[i] == pl) g_tables_owner[i] = nullptr;
   delete pl;
 }
 
@@ -1183,13 +1192,16 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   return SB_OK;
 }
 
+/* The tables are shared __constant__ state: plans of one device must be used from one
+ * stream at a time (the copy is stream-ordered on the caller's stream).              */
 static int bind_tables(sb_plan* pl, cudaStream_t s) {
-  if (g_tables_owner == pl) return SB_OK;
+  const int slot = current_device_slot();
+  if (g_tables_owner[slot] == pl) return SB_OK;
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_T, &pl->tables, sizeof(SbTables), 0,
                                    cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_M, &pl->model, sizeof(sb_model), 0,
                                    cudaMemcpyHostToDevice, s));
-  g_tables_owner = pl;
+  g_tables_owner[slot] = pl;
   return SB_OK;
 }
 
@@ -1218,6 +1230,11 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
   }
   if ((pl->n_bc && !st->d_bc_values) || (pl->n_natbc && !st->d_natbc_values)) {
     snprintf(g_err, sizeof g_err, "bc_values / natbc_values required"); return SB_ERR_ARG;
+  }
+  /* rows that one cell owns leave the SM as cp.async.bulk copies whose 16-byte phase is
+     taken from the value index: the array itself must be 16-byte aligned */
+  if (d_vals && (pl->d.native || pl->d.owned_bulk) && ((uintptr_t)d_vals & 15)) {
+    snprintf(g_err, sizeof g_err, "d_vals must be 16-byte aligned"); return SB_ERR_ARG;
   }
   cudaStream_t s = (cudaStream_t)stream;
   int rc = bind_tables(pl, s);

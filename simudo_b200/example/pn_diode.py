@@ -30,16 +30,19 @@ def topology_standard_contacts(cell_regions, facet_regions):
     F.nonconductive = F.exterior - F.contacts.both()
 
 
-def build(length=0.5, product2d_Ys=None):
+def build(length=0.5, product2d_Ys=None, mesh_start=0.001, mesh_factor=1.2, edge_length=None):
+    """``mesh_start`` / ``mesh_factor`` / ``edge_length``: the tutorial's geometric x-mesh
+    (pn_diode.py:49-65: 1e-3 um, 1.2, length / 20 -> 67 points); finer values give the
+    2D configurations of BASELINE.json (configs[2]: ~224 x 224 points)."""
     U = make_unit_registry(("mesh_unit = 1 micrometer",))
     layers = [
         dict(name='pSi', material='Si', thickness=length / 2,
-             mesh=dict(type="geometric", start=0.001, factor=1.2)),
+             mesh=dict(type="geometric", start=mesh_start, factor=mesh_factor)),
         dict(name='nSi', material='Si', thickness=length / 2,
-             mesh=dict(type="geometric", start=0.001, factor=1.2)),
+             mesh=dict(type="geometric", start=mesh_start, factor=mesh_factor)),
     ]
     ls = ConstructionHelperLayeredStructure()
-    ls.params = dict(edge_length=length / 20, layers=layers, extra_regions=[],
+    ls.params = dict(edge_length=edge_length or length / 20, layers=layers, extra_regions=[],
                      mesh_unit=U.mesh_unit)
     if product2d_Ys is not None:
         ls.params['product2d_Ys'] = product2d_Ys
@@ -48,8 +51,8 @@ def build(length=0.5, product2d_Ys=None):
 
 
 def run(output_prefix=None, voltages=None, backend_factory=None, product2d_Ys=None,
-        return_problem=False):
-    U, mesh_data = build(product2d_Ys=product2d_Ys)
+        return_problem=False, mesh=None):
+    U, mesh_data = build(product2d_Ys=product2d_Ys, **(mesh or {}))
     R = CellRegions()
     F = FacetRegions()
     topology_standard_contacts(R, F)

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .assembly import AssemblyPlan
-from .linear_solver import BandSolver
+from .linear_solver import BandSolver, make_solver
 
 __all__ = ['CudaBackend', 'CudaLCNBackend']
 
@@ -78,7 +78,8 @@ class CudaBackend(object):
 
     def solve(self):
         if self._solver is None:
-            self._solver = BandSolver(self.pa, self.device)
+            # symbolic phase once per lowered problem, reused by every Newton step
+            self._solver = make_solver(self.pa, self.device)
         self._solver.solve(self.vals, self.b, self.du)
 
     def newton_update(self, tol, omega, max_du, rel_tol, abs_tol):

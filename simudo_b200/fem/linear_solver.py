@@ -13,7 +13,25 @@ import torch
 
 from .. import _lib
 
-__all__ = ['x_major_permutation', 'BandSolver']
+__all__ = ['x_major_permutation', 'BandSolver', 'make_solver']
+
+# band storage above which a mesh is treated as genuinely two-dimensional
+BAND_LIMIT_BYTES = 256 << 20
+
+
+def make_solver(pa, device, band_limit_bytes=None):
+    """The linear solver of a lowered problem: banded LU for product meshes that are thin in
+    y (the 1D examples, BASELINE configs 1, 2, 5), multifrontal LU on nested dissection
+    otherwise (configs 3, 4).  Both keep their symbolic phase for all later solves."""
+    if band_limit_bytes is None:
+        band_limit_bytes = BAND_LIMIT_BYTES
+    try:
+        return BandSolver(pa, device, max_band_bytes=band_limit_bytes)
+    except RuntimeError as e:
+        if 'status -5' not in str(e):            # SB_ERR_UNSUPPORTED: band too wide
+            raise
+    from .multifrontal import MultifrontalSolver
+    return MultifrontalSolver(pa, device)
 
 
 def x_major_permutation(pa):

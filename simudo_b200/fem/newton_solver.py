@@ -91,7 +91,11 @@ class NewtonSolver(object):
 
     # -- iteration ---------------------------------------------------------------
     def get_omega(self):
-        cb = self.parameters.get('omega_callback', None) or self.parameters.get('omega_cb', None)
+        # only 'omega_callback' is read (newton_solver.py:354-361); the 'omega_cb' entries the
+        # stage solvers and steppers put into their parameters are dead in the reference too,
+        # so the damping that applies is relaxation_parameter for the first
+        # num_damped_iterations (5) iterations, then a full step
+        cb = self.parameters.get('omega_callback', None)
         if cb is not None:
             return cb(self)
         if self.iteration <= self.parameters.get('num_damped_iterations', 5):

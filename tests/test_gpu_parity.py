@@ -109,6 +109,22 @@ def test_jacobian_consistent_with_residual_at_scale(maker, nx, ny):
     assert n > 40000
 
 
+def test_misaligned_values_are_refused():
+    """The bulk-copy paths need a 16-byte aligned value array: an odd element offset into a
+    larger buffer is refused instead of faulting on the device."""
+    import torch
+    from simudo_b200.fem.assembly import AssemblyPlan
+    for pattern in ('bsr3', 'structural'):
+        pa = syn.pn_problem(nx=5, ny=3, pattern=pattern)
+        st = syn.synthetic_state(pa)
+        plan = AssemblyPlan(pa)
+        T = plan.tensor
+        buf = torch.zeros(plan.nnz + 1, dtype=torch.float64, device=plan.device)
+        with pytest.raises(RuntimeError, match='aligned'):
+            plan.assemble(T(st['u']), T(st['base_w']), T(st['thmeq_phi']), None, T(st['bc_values']),
+                          T(plan.natbc_device_order(st['natbc_values'])), buf[1:], plan.new_vector())
+
+
 def test_no_cpu_fallback():
     """The product must refuse to run without CUDA tensors."""
     import torch

@@ -93,3 +93,31 @@ def test_jv_sweep_on_gpu_matches_oracle_fixture():
     for (V, J), (V0, J0) in zip(jv[1:], ref[1:]):
         assert V == pytest.approx(V0)
         assert J == pytest.approx(J0, rel=1e-6), (V, J, J0)
+
+
+@pytest.mark.gpu
+def test_2d_pn_diode_newton_solve_on_gpu_multifrontal():
+    """BASELINE configs[2] at test size: the tutorial diode on a genuinely two-dimensional
+    product mesh (67 x 9 points) solved through the CUDA backend -- assembly by the native
+    kernels, Newton systems by the multifrontal LU (the band of this mesh is too wide for
+    the banded solver).  Data and contacts do not depend on y, so the discrete solution is
+    the 1D one: J(V) must reproduce the oracle fixture of the 1D sweep to 1e-6."""
+    from simudo_b200.example import pn_diode
+    from simudo_b200.fem.multifrontal import MultifrontalSolver
+    from simudo_b200.fem import linear_solver
+    old = linear_solver.BAND_LIMIT_BYTES
+    linear_solver.BAND_LIMIT_BYTES = 4 << 20        # force the 2D path at this small size
+    try:
+        jv, problem, _ = pn_diode.run(voltages=[0.0, 0.3, 0.6], return_problem=True,
+                                      product2d_Ys=np.linspace(0.0, 1.0, 9))
+    finally:
+        linear_solver.BAND_LIMIT_BYTES = old
+    be = problem.pdd.system.backend
+    assert isinstance(be._solver, MultifrontalSolver)
+    ref = {round(v, 2): j for v, j in _golden('pn_diode_JV_oracle.json')}
+    for v, j in jv:
+        j0 = ref[round(v, 2)]
+        if v == 0.0:
+            assert abs(j) < 1e-9 * abs(ref[0.3])
+        else:
+            assert abs(j - j0) <= 1e-6 * abs(j0), (v, j, j0)

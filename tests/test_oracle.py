@@ -136,3 +136,34 @@ def test_oracle_manufactured_mixed_poisson_converges():
         _, b2 = orc.assemble(u, bc_values=np.zeros(len(pa.bc_dofs)), want_A=False)
         assert np.abs(b2).max() < 1e-10
     assert errs[1] < errs[0] / 3.0          # at least second-order in h
+
+
+def test_multifrontal_solver_matches_sparse_lu_on_2d_meshes():
+    """The nested-dissection multifrontal LU (simudo_b200/fem/multifrontal.py; numeric phase
+    in batched torch ops, here on host tensors) on genuinely two-dimensional Newton matrices
+    against scipy's SuperLU: residual of the equilibrated system and solution."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch
+    from simudo_b200.fem.multifrontal import MultifrontalSolver
+    for mk, nx, ny, leaf in ((syn.pn_problem, 12, 9, 8), (syn.ib_problem, 14, 7, 16)):
+        pa = mk(nx=nx, ny=ny, pattern='native')
+        st = syn.synthetic_state(pa)
+        orc = Oracle(pa, n_threads=4)
+        vals, b = orc.assemble(st['u'], st['base_w'], st['thmeq_phi'], st['phi_opt'],
+                               st['bc_values'], st['natbc_values'])
+        mf = MultifrontalSolver(pa, 'cpu', leaf_cells=leaf)
+        x = mf.solve(torch.as_tensor(vals), torch.as_tensor(b)).numpy()
+        A = orc.to_scipy(vals).tocsc()
+        r = 1.0 / np.abs(A).max(axis=1).toarray().ravel()
+        As = sp.diags(r) @ A
+        c = 1.0 / np.abs(As).max(axis=0).toarray().ravel()
+        x0 = c * spla.splu((As @ sp.diags(c)).tocsc()).solve(r * b)
+        res = np.abs(r * (A @ x - b)).max() / np.abs(r * b).max()
+        assert res < 1e-12, res
+        assert np.abs(x - x0).max() <= 1e-4 * np.abs(x0).max()
+        # second solve with the same symbolic phase and another matrix / right-hand side
+        vals2 = vals * (1.0 + 0.01 * np.cos(np.arange(len(vals))))
+        x2 = mf.solve(torch.as_tensor(vals2), torch.as_tensor(b)).numpy()
+        A2 = orc.to_scipy(vals2).tocsr()
+        assert np.abs(r * (A2 @ x2 - b)).max() / np.abs(r * b).max() < 1e-11
