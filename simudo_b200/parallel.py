@@ -18,7 +18,7 @@ assembly itself:
 import numpy as np
 import torch
 
-__all__ = ['StripHalo', 'shard_round_robin']
+__all__ = ['StripHalo', 'StripDecomposition', 'shard_round_robin']
 
 
 def shard_round_robin(n_items, rank, world):
@@ -102,3 +102,148 @@ class StripHalo(object):
         self.pack(u, base_w)
         self.exchange(dist)
         self.unpack(u)
+
+
+class StripDecomposition(object):
+    """Domain decomposition of ONE product mesh into y-strips (BASELINE configs[3]: the 1M-cell
+    mesh on 1/2/4/8 GPUs; SURVEY.md section 8e row 3 -- the reference has none: its MUMPS
+    runs sequentially, ``newton_solver.py:144-146``).
+
+    Rank r assembles the cells of its rows [j0, j1) plus one ghost row of quads on every
+    interior side (``synthetic.*_problem(strip=(r, world))`` builds that local problem).
+    *Owner computes*: a cell belongs to the rank of its row, a facet to the lowest rank
+    among its cells' ranks; every row of the Jacobian / residual that belongs to an owned
+    dof is complete after the local assembly (the ghost cells are recomputed, no reduction),
+    rows of ghost dofs are discarded.  Per Newton step the only communication is the ghost
+    update of ``u`` and ``base_w``: every rank sends the values it owns of the dofs in its
+    neighbours' ghost rows (grouped point-to-point sends: NCCL on the GPUs, gloo in the CPU
+    tests).  Both sides order the exchanged dofs by a global entity key computed from the
+    mesh geometry, so no set-up communication is needed.
+
+    ``gkey[N]``: global key of every local dof (identical on every rank holding the dof);
+    ``owned[N]``: this rank owns the dof (its row of the system is complete here).
+    """
+
+    def __init__(self, pa, device='cpu'):
+        s = pa.strip
+        if s is None:
+            raise ValueError('pa was not built as a strip (synthetic.*_problem(strip=...))')
+        self.pa, self.info = pa, s
+        self.rank, self.world = s['rank'], s['world']
+        mesh = pa.mesh
+        nXg = len(np.unique(mesh.coordinates[:, 0]))
+        nYl = len(np.unique(mesh.coordinates[:, 1]))
+        nYg = s['n_rows_global'] + 1
+        row0 = s['row0']
+        # local vertex v = ix * nYl + iy  (mesh/product2d.py)
+        def vij(v):
+            return v // nYl, v % nYl + row0
+        # cells: row and global index 2 (ix (nYg - 1) + row) + t, t = position inside the quad
+        cv = mesh.cells.astype(np.int64)
+        cix, ciy = vij(cv.min(axis=1))
+        t = (np.arange(mesh.num_cells) % 2).astype(np.int64)
+        cell_key = 2 * (cix * (nYg - 1) + ciy) + t
+        cell_row = ciy
+        # facets: horizontal (on line j), vertical / diagonal (inside row j)
+        fv = mesh.facet_vertices.astype(np.int64)
+        ax, ay = vij(fv[:, 0])
+        bx, by = vij(fv[:, 1])
+        horiz = ay == by
+        vert = ax == bx
+        ftype = np.where(horiz, 0, np.where(vert, 1, 2)).astype(np.int64)
+        fix, fj = np.minimum(ax, bx), np.minimum(ay, by)
+        facet_key = (ftype * nXg + fix) * nYg + fj
+        # owner ranks: row j -> rank; horizontal line j -> rank of row j - 1 (row 0 for j = 0)
+        rows = np.arange(nYg - 1)
+        rank_of_row = np.searchsorted(
+            np.array([(s['n_rows_global'] * (r + 1)) // self.world for r in range(self.world)]),
+            rows, side='right')
+        frow = np.where(horiz, np.maximum(fj - 1, 0), fj)
+        cell_owner = rank_of_row[cell_row]
+        facet_owner = rank_of_row[frow]
+        # per dof
+        N, P = pa.N, pa.P
+        lay = pa.layout()
+        cd = pa.cell_dofs.astype(np.int64)
+        nkey = 2 * (nXg - 1) * (nYg - 1) + 3 * nXg * nYg        # cells, then facets
+        gkey = np.full(N, -1, dtype=np.int64)
+        owner = np.full(N, -1, dtype=np.int64)
+        for p in range(P):
+            for i in range(3):
+                for slot, loc in ((i, lay['dg'][p][i]), (3 + i, lay['interior'][p][i])):
+                    d = cd[:, loc]
+                    gkey[d] = (cell_key * P + p) * 6 + slot
+                    owner[d] = cell_owner
+            for f in range(3):
+                fa = mesh.cell_facets[:, f].astype(np.int64)
+                for k in range(3):
+                    d = cd[:, lay['facet'][p][f][k]]
+                    gkey[d] = nkey * P * 6 + (facet_key[fa] * P + p) * 3 + k
+                    owner[d] = facet_owner[fa]
+        assert (gkey >= 0).all()
+        self.gkey, self.owner = gkey, owner
+        self.owned = owner == self.rank
+        self.cell_key, self.cell_owner = cell_key, cell_owner
+        self.owned_cells = cell_owner == self.rank
+        # exchange lists with the neighbours, ordered by global key on both sides.
+        # A dof owned by rank q exists on rank q +- 1 iff its entity lies in that rank's
+        # ghost row: send what I own and the neighbour holds, receive what the neighbour owns.
+        dev = torch.device(device)
+        self.send, self.recv, self.send_cells, self.recv_cells = {}, {}, {}, {}
+        n_rows = s['n_rows_global']
+        for q in (self.rank - 1, self.rank + 1):
+            if q < 0 or q >= self.world:
+                continue
+            qj0, qj1 = (n_rows * q) // self.world, (n_rows * (q + 1)) // self.world
+            qlo, qhi = qj0 - int(q > 0), qj1 + int(q < self.world - 1)      # rows held by q
+            in_q_cell = (cell_row >= qlo) & (cell_row < qhi)
+            in_q_facet = np.where(horiz, (fj >= qlo) & (fj <= qhi), (fj >= qlo) & (fj < qhi))
+            dof_in_q = np.zeros(N, dtype=bool)
+            for p in range(P):
+                for i in range(3):
+                    dof_in_q[cd[in_q_cell][:, lay['dg'][p][i]]] = True
+                    dof_in_q[cd[in_q_cell][:, lay['interior'][p][i]]] = True
+            fmask = in_q_facet[mesh.cell_facets]
+            for p in range(P):
+                for f in range(3):
+                    for k in range(3):
+                        d = cd[:, lay['facet'][p][f][k]]
+                        dof_in_q[d[fmask[:, f]]] = True
+            snd = np.nonzero(self.owned & dof_in_q)[0]
+            rcv = np.nonzero(owner == q)[0]
+            snd = snd[np.argsort(gkey[snd], kind='stable')]
+            rcv = rcv[np.argsort(gkey[rcv], kind='stable')]
+            self.send[q] = torch.as_tensor(snd, device=dev)
+            self.recv[q] = torch.as_tensor(rcv, device=dev)
+            sc = np.nonzero(self.owned_cells & in_q_cell)[0]
+            rc = np.nonzero(cell_owner == q)[0]
+            self.send_cells[q] = torch.as_tensor(sc[np.argsort(cell_key[sc], kind='stable')], device=dev)
+            self.recv_cells[q] = torch.as_tensor(rc[np.argsort(cell_key[rc], kind='stable')], device=dev)
+        nb = pa.model.n_bands if pa.model.bands_have_dofs else 0
+        self.n_bands = nb
+        mk = lambda n: torch.zeros(n, dtype=torch.float64, device=dev)
+        self._sbuf = {q: mk(len(self.send[q]) + nb * len(self.send_cells[q])) for q in self.send}
+        self._rbuf = {q: mk(len(self.recv[q]) + nb * len(self.recv_cells[q])) for q in self.recv}
+
+    @property
+    def bytes_per_exchange(self):
+        return 8 * sum(b.numel() for b in self._sbuf.values())
+
+    def exchange(self, dist, u, base_w=None):
+        """Ghost update of ``u`` (and ``base_w``) from their owners, in place."""
+        ops = []
+        for q, idx in self.send.items():
+            buf = self._sbuf[q]
+            buf[:len(idx)] = u[idx]
+            if self.n_bands:
+                buf[len(idx):] = base_w[:, self.send_cells[q]].reshape(-1)
+            ops.append(dist.P2POp(dist.isend, buf, q))
+            ops.append(dist.P2POp(dist.irecv, self._rbuf[q], q))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for q, idx in self.recv.items():
+            buf = self._rbuf[q]
+            u[idx] = buf[:len(idx)]
+            if self.n_bands:
+                base_w[:, self.recv_cells[q]] = buf[len(idx):].view(self.n_bands, -1)

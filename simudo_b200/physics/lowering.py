@@ -101,7 +101,7 @@ class PDDSystem(_SystemBase):
     """goal 'thermal equilibrium' (Poisson unknowns only, bands at qfl = 0) or
     'full' (Poisson + one MixedQfl pair per band)."""
 
-    def __init__(self, pdd, numbering='b200', pattern='structural'):
+    def __init__(self, pdd, numbering='b200', pattern='native'):
         super().__init__(pdd)
         goal = pdd.problem_data.goal
         self.full = (goal == 'full')

@@ -33,6 +33,29 @@ def _graded(n, length, junctions):
     return x
 
 
+def strip_rows(n_rows, rank, world):
+    """Quad rows [j0, j1) of y-strip ``rank`` of ``world`` (balanced)."""
+    j0 = (n_rows * rank) // world
+    j1 = (n_rows * (rank + 1)) // world
+    return j0, j1
+
+
+def _strip_Ys(Ys, strip):
+    """Local y-lines of a strip with one ghost row of quads on every interior side
+    (simudo_b200/parallel.py: StripDecomposition) and the bookkeeping that goes with it."""
+    if strip is None:
+        return Ys, None
+    rank, world = strip
+    n_rows = len(Ys) - 1
+    if n_rows < 2 * world:
+        raise ValueError('every strip needs at least two rows of quads')
+    j0, j1 = strip_rows(n_rows, rank, world)
+    g_lo, g_hi = int(rank > 0), int(rank < world - 1)
+    info = dict(rank=rank, world=world, j0=j0, j1=j1, g_lo=g_lo, g_hi=g_hi, row0=j0 - g_lo,
+                n_rows_global=n_rows, Ys_global=np.asarray(Ys, dtype=float))
+    return Ys[j0 - g_lo:j1 + g_hi + 1], info
+
+
 def _boundary_setup(mesh, pa_P, cell_dofs_fn=None):
     bf = mesh.boundary_facets()
     n = mesh.boundary_outward_normals(bf)
@@ -43,10 +66,11 @@ def _boundary_setup(mesh, pa_P, cell_dofs_fn=None):
 
 
 def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=True,
-               pattern='structural'):
-    """2D Si pn junction: CB + VB Boltzmann bands, SRH (BASELINE config 1/3)."""
+               pattern='structural', strip=None):
+    """2D Si pn junction: CB + VB Boltzmann bands, SRH (BASELINE config 1/3).
+    ``strip=(rank, world)``: the y-strip of that rank with its ghost rows."""
     Xs = _graded(nx, length, [length / 2])
-    Ys = np.linspace(0.0, height, ny)
+    Ys, sinfo = _strip_Ys(np.linspace(0.0, height, ny), strip)
     mesh = Product2DMesh(Xs, Ys).mesh
     xc = mesh.coordinates[mesh.cells].mean(axis=1)[:, 0]
     cell_tag = (xc > length / 2).astype(np.int32)          # 0 = p side, 1 = n side
@@ -76,13 +100,15 @@ def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=Tr
     jmask = np.full(nf, 0b11, dtype=np.uint8)
     pa = ProblemArrays(mesh, cell_tag, model, tp, numbering=numbering,
                        jump_facet_mask=jmask, pattern=pattern)
+    pa.strip = sinfo
+    pa.extent = (length, height)
     if with_bcs:
         _attach_bcs(pa, mesh, n_dof_bands=2, minority_left=[0], minority_right=[1])
     return pa
 
 
 def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
-               const_mobility=True, pattern='structural'):
+               const_mobility=True, pattern='structural', strip=None):
     """Four-layer FSF/p/IB/n intermediate-band cell (BASELINE config 2/4):
     CB, IB, VB; two Shockley-Read traps, radiative CV, radiative CI/IV with
     absorption, three optical fields."""
@@ -92,7 +118,7 @@ def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
     Xs = _graded(nx, length, list(edges[1:-1]))
     # make sure every layer owns at least one x-interval
     Xs = np.unique(np.concatenate([Xs, edges]))
-    Ys = np.linspace(0.0, height, ny)
+    Ys, sinfo = _strip_Ys(np.linspace(0.0, height, ny), strip)
     mesh = Product2DMesh(Xs, Ys).mesh
     xc = mesh.coordinates[mesh.cells].mean(axis=1)[:, 0]
     cell_tag = (np.searchsorted(edges, xc) - 1).astype(np.int32)   # 0 fsf,1 p,2 I,3 n
@@ -154,6 +180,8 @@ def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
     jmask[both_I] |= 0b010
     pa = ProblemArrays(mesh, cell_tag, model, tp, numbering=numbering,
                        jump_facet_mask=jmask, pattern=pattern)
+    pa.strip = sinfo
+    pa.extent = (length, height)
     if with_bcs:
         _attach_bcs(pa, mesh, n_dof_bands=3, minority_left=[0], minority_right=[2],
                     extra_all=[1])
@@ -166,6 +194,13 @@ def _attach_bcs(pa, mesh, n_dof_bands, minority_left, minority_right, extra_all=
     all j on the horizontal (non-conductive) sides, zero minority current at
     each contact; natural phi terms on both contacts."""
     left, right, horiz = _boundary_setup(mesh, pa.P)
+    sinfo = getattr(pa, 'strip', None)
+    if sinfo is not None:
+        # the artificial bottom / top of a strip (outer edge of its ghost rows) is no boundary
+        ymid = mesh.facet_midpoints()[horiz][:, 1]
+        Yg = sinfo['Ys_global']
+        horiz = horiz[(np.abs(ymid - Yg[0]) < 1e-12 * max(1.0, abs(Yg[-1]))) |
+                      (np.abs(ymid - Yg[-1]) < 1e-12 * max(1.0, abs(Yg[-1])))]
     bc = [pa.facet_dofs(0, horiz).ravel()]
     for k in range(n_dof_bands):
         bc.append(pa.facet_dofs(1 + k, horiz).ravel())
@@ -194,6 +229,29 @@ def _attach_bcs(pa, mesh, n_dof_bands, minority_left, minority_right, extra_all=
     pa.contacts = dict(left=left, right=right, horiz=horiz)
 
 
+def dof_coordinates(pa):
+    """(x, y) of the mesh entity carrying every global dof (cell centroid / facet midpoint)
+    and the dof's index inside its entity triple: a numbering-independent label."""
+    mesh, lay = pa.mesh, pa.layout()
+    xy = np.zeros((pa.N, 2))
+    kk = np.zeros(pa.N)
+    cc = pa.cell_vertices.mean(axis=1)
+    fm = mesh.facet_midpoints()
+    cd = pa.cell_dofs
+    for p in range(pa.P):
+        for i in range(3):
+            xy[cd[:, lay['dg'][p][i]]] = cc
+            xy[cd[:, lay['interior'][p][i]]] = cc
+            kk[cd[:, lay['dg'][p][i]]] = i + 10 * p
+            kk[cd[:, lay['interior'][p][i]]] = i + 3 + 10 * p
+        for f in range(3):
+            for k in range(3):
+                d = cd[:, lay['facet'][p][f][k]]
+                xy[d] = fm[mesh.cell_facets[:, f]]
+                kk[d] = k + 6 + 10 * p
+    return xy, kk
+
+
 def synthetic_state(pa, bias=0.3, y_amp=1e-3):
     """Smooth, physically scaled state: returns dict(u, base_w, thmeq_phi,
     phi_opt, bc_values, natbc_values)."""
@@ -204,6 +262,8 @@ def synthetic_state(pa, bias=0.3, y_amp=1e-3):
     X = mesh.coordinates
     Lx = X[:, 0].max()
     Ly = max(X[:, 1].max(), 1e-30)
+    if getattr(pa, 'extent', None) is not None:
+        Lx, Ly = pa.extent[0], max(pa.extent[1], 1e-30)     # the global domain, also on a strip
     tp = pa.tag_params
     kT = tp[0, M.TP_KT]
 
@@ -230,15 +290,18 @@ def synthetic_state(pa, bias=0.3, y_amp=1e-3):
             base_w[k] = wfun(xc[:, 0], xc[:, 1])
             wv = wfun(xv[:, :, 0], xv[:, :, 1])
             u[pa.cell_dofs[:, lay['dg'][1 + k]]] = wv - base_w[k][:, None]
-        # fluxes: small smooth values scaled like 1 V/um fields, 1e-9 A/um^2 currents
-        rng_phase = np.arange(pa.N) * 0.61803398875
+        # fluxes: small values scaled like 1 V/um fields, 1e-9 A/um^2 currents; a function of
+        # the dof's mesh entity, not of its number (same state on any numbering / strip)
+        dxy, dk = dof_coordinates(pa)
+        rng_phase = 37.1 * dxy[:, 0] + 19.7 * dxy[:, 1] + 1.3 * dk
         for p in range(pa.P):
             d = np.unique(pa.cell_dofs[:, lay['bdm'][p]])
             scale = 0.5 if p == 0 else 1e-9
             u[d] = scale * np.sin(rng_phase[d])
     else:
+        dxy, dk = dof_coordinates(pa)
         d = np.unique(pa.cell_dofs[:, lay['bdm'][0]])
-        u[d] = 0.5 * np.sin(np.arange(pa.N)[d] * 0.61803398875)
+        u[d] = 0.5 * np.sin(37.1 * dxy[d, 0] + 19.7 * dxy[d, 1] + 1.3 * dk[d])
     out['u'] = u
     out['base_w'] = base_w
     nfld = model.n_fields
@@ -250,6 +313,14 @@ def synthetic_state(pa, bias=0.3, y_amp=1e-3):
         out['phi_opt'] = phi_opt
     else:
         out['phi_opt'] = None
-    out['bc_values'] = 1e-12 * np.cos(np.arange(len(pa.bc_dofs)) * 0.7)
-    out['natbc_values'] = 0.3 * np.sin(np.arange(len(pa.natbc_cell)) * 1.3)
+    dxy, dk = dof_coordinates(pa)
+    bd = pa.bc_dofs
+    out['bc_values'] = 1e-12 * np.cos(31.0 * dxy[bd, 0] + 17.0 * dxy[bd, 1] + dk[bd])
+    # natural-BC values in the caller's order (before the plan's sort by cell)
+    ncell = np.empty(len(pa.natbc_cell), dtype=np.int64)
+    nrow = np.empty(len(pa.natbc_cell), dtype=np.int64)
+    ncell[pa.natbc_order] = pa.natbc_cell
+    nrow[pa.natbc_order] = pa.natbc_row
+    cc = pa.cell_vertices.mean(axis=1)
+    out['natbc_values'] = 0.3 * np.sin(23.0 * cc[ncell, 0] + 11.0 * cc[ncell, 1] + 1.3 * nrow)
     return out

@@ -107,3 +107,79 @@ def test_sweep_ensemble_sharded_equals_serial_world2():
     # heavier doping -> larger built-in potential -> smaller forward current at 0.6 V
     j06 = [dict((round(v, 2), j) for v, j in r)[0.6] for r in serial]
     assert j06[0] > j06[2] > 0
+
+
+def _dd_worker(rank, world, port, q, pattern):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import conftest
+    from simudo_b200 import _lib
+    _lib._use_library_for_tests(conftest.build_emulation_library())
+    from simudo_b200 import synthetic as syn
+    from simudo_b200.fem.assembly import AssemblyPlan
+    from simudo_b200.parallel import StripDecomposition
+    from parity_util import run_plan
+    pa = syn.ib_problem(nx=7, ny=9, pattern=pattern, strip=(rank, world))
+    dd = StripDecomposition(pa)
+    st = syn.synthetic_state(pa)
+    # ghosts start as garbage: the exchange must restore them from their owners
+    u = torch.as_tensor(st['u']).clone()
+    bw = torch.as_tensor(st['base_w']).clone()
+    u[torch.as_tensor(~dd.owned)] = 1e30
+    bw[:, torch.as_tensor(~dd.owned_cells)] = -1e30
+    dd.exchange(dist, u, bw)
+    assert np.array_equal(u.numpy(), st['u']) and np.array_equal(bw.numpy(), st['base_w'])
+    st['u'], st['base_w'] = u.numpy(), bw.numpy()
+    plan = AssemblyPlan(pa)
+    assert plan.is_native()
+    vals, b = run_plan(plan, st)
+    col, row = pa.csr.column_indices(want_rows=True)
+    own = dd.owned[row]
+    q.put(dict(rank=rank, bytes=dd.bytes_per_exchange, rk=dd.gkey[row][own], ck=dd.gkey[col][own],
+               v=vals.numpy()[own], bk=dd.gkey[dd.owned], b=b.numpy()[dd.owned],
+               n_owned_cells=int(dd.owned_cells.sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('pattern', ['bsr3', 'native'])
+def test_strip_domain_decomposition_reproduces_single_domain_world2(emulated_lib, pattern):
+    """One IB mesh split into two y-strips (one ghost row of quads each, owner computes, ghost
+    update of u / base_w over gloo): the Jacobian and residual rows every rank owns are,
+    bit for bit, the rows of the single-domain assembly; together they are all rows."""
+    from simudo_b200 import synthetic as syn
+    from simudo_b200.fem.assembly import AssemblyPlan
+    from simudo_b200.parallel import StripDecomposition
+    from parity_util import run_plan
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (7 if pattern == 'native' else 0)
+    procs = [ctx.Process(target=_dd_worker, args=(r, 2, port, q, pattern)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=300) for _ in procs], key=lambda d: d['rank'])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single domain, same kernels
+    g = syn.ib_problem(nx=7, ny=9, pattern=pattern)
+    g.strip = dict(rank=0, world=1, j0=0, j1=8, g_lo=0, g_hi=0, row0=0, n_rows_global=8,
+                   Ys_global=np.linspace(0.0, 1.0, 9))
+    G = StripDecomposition(g)
+    vals, b = run_plan(AssemblyPlan(g), syn.synthetic_state(g))
+    col, row = g.csr.column_indices(want_rows=True)
+    ref = {(int(r), int(c)): v for r, c, v in zip(G.gkey[row], G.gkey[col], vals.numpy())}
+    bref = dict(zip(G.gkey.tolist(), b.numpy().tolist()))
+    seen = 0
+    for o in out:
+        for r, c, v in zip(o['rk'], o['ck'], o['v']):
+            assert ref[(int(r), int(c))] == v          # bitwise
+        for k, v in zip(o['bk'], o['b']):
+            assert bref[int(k)] == v
+        seen += len(o['v'])
+    assert seen == g.csr.nnz                            # the owned rows are all rows, once
+    assert sum(o['n_owned_cells'] for o in out) == g.n_cells
+    assert out[0]['bytes'] > 0 and out[1]['bytes'] > 0
