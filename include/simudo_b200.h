@@ -199,6 +199,12 @@ int sb_rebase_w(sb_plan* plan, double* d_u, double* d_base_w,
 int sb_newton_update(sb_plan* plan, double* d_u, const double* d_du, const double* d_b,
                      const double* d_tol, double omega, double max_du,
                      double rel_tol, double abs_tol, double* d_out, void* stream);
+/* the same with NewtonSolverLogDamping's step (newton_solver.py:542-547, ref. Gaury 2018):
+ * the applied step is sign(du) log1p(log_alpha |du|) / log_alpha (log_alpha <= 0: off; the
+ * reference's default alpha is 1.72); the metrics use the raw du like the reference.   */
+int sb_newton_update_damped(sb_plan* plan, double* d_u, const double* d_du, const double* d_b,
+                            const double* d_tol, double omega, double max_du, double log_alpha,
+                            double rel_tol, double abs_tol, double* d_out, void* stream);
 
 /* ---- terminal current ----------------------------------------------
  * Replaces MetaExtractorIntegrals.add_surface_flux (simudo/io/output_writer.py:
@@ -299,6 +305,10 @@ int sb_plan_last_kernel_ms(sb_plan* plan, double* ms);
 /* the same pass split by stage: ms4 = {k_moments, k_generation, k_rows_fast x P,
  * k_rows_special}                                                                  */
 int sb_plan_last_stage_ms(sb_plan* plan, double* ms4);
+
+/* measured DFMA throughput of the current device in TFLOP/s (the FP64 roofline
+ * denominator bench.py reports beside the HBM one; synchronises)                        */
+int sb_measure_fp64_peak(double* tflops);
 
 /* layout of the packed reference tables expected in sb_problem.h_tables */
 int64_t sb_tables_size(void);

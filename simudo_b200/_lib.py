@@ -20,8 +20,8 @@ _EMULATED = False
 
 EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
-            'sb_plan_is_native',
-            'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update',
+            'sb_plan_is_native', 'sb_measure_fp64_peak',
+            'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update', 'sb_newton_update_damped',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
             'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
             'sb_band_solve', 'sb_band_set_refinement', 'sb_csr_residual_dd', 'sb_optics_create',
@@ -69,6 +69,8 @@ def _declare(lib):
     lib.sb_tables_size.restype = i64
     lib.sb_plan_nnz.argtypes = [vp]
     lib.sb_plan_nnz.restype = i64
+    lib.sb_measure_fp64_peak.argtypes = [C.POINTER(C.c_double)]
+    lib.sb_measure_fp64_peak.restype = C.c_int
     lib.sb_plan_is_native.argtypes = [vp]
     lib.sb_plan_is_native.restype = C.c_int
     lib.sb_assemble.argtypes = [vp, C.POINTER(SbState), vp, vp, vp]
@@ -81,6 +83,8 @@ def _declare(lib):
     lib.sb_rebase_w.restype = C.c_int
     lib.sb_newton_update.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
     lib.sb_newton_update.restype = C.c_int
+    lib.sb_newton_update_damped.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, vp, vp]
+    lib.sb_newton_update_damped.restype = C.c_int
     lib.sb_surface_flux.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp]
     lib.sb_surface_flux.restype = C.c_int
     lib.sb_plan_set_profiling.argtypes = [vp, C.c_int]

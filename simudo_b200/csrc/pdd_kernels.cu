@@ -860,7 +860,7 @@ __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
 
 __global__ void k_newton_update(int64_t N, double* u, const double* du, const double* b,
                                 const double* tol, double omega, double max_du,
-                                double rel_tol, double abs_tol, double* out) {
+                                double rel_tol, double abs_tol, double log_alpha, double* out) {
   double bmax = 0, dmax = 0, rsum = 0, cmax = 0, nanf = 0, cnt = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -868,6 +868,8 @@ __global__ void k_newton_update(int64_t N, double* u, const double* du, const do
     const double bi = b ? b[i] : 0.0;
     double step = di;
     if (max_du > 0.0) step = fmin(fmax(step, -max_du), max_du);
+    /* NewtonSolverLogDamping (newton_solver.py:542-547): sign(du) log1p(alpha |du|) / alpha */
+    if (log_alpha > 0.0) step = copysign(log1p(fabs(step) * log_alpha) / log_alpha, step);
     const double un = ui - omega * step;
     u[i] = un;
     /* the reference evaluates its metrics after the update, i.e. against the
@@ -1364,6 +1366,55 @@ extern "C" int sb_plan_last_stage_ms(sb_plan* pl, double* ms4) {
   return SB_OK;
 }
 
+/* ---- FP64 roofline denominator -----------------------------------------------------
+ * DFMA throughput of the device, measured: 8 independent FMA chains per thread, enough
+ * resident warps to cover the pipe latency (1024 threads x 2 CTAs per SM).             */
+__global__ void __launch_bounds__(1024, 2) k_dfma_peak(double* out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fma(v[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  if (s == 1.2345) out[0] = s;
+}
+
+extern "C" int sb_measure_fp64_peak(double* tflops) {
+  if (!tflops) return SB_ERR_ARG;
+  *tflops = 0.0;
+#ifndef SB_EMUL_BUILD
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int iters = 20000, grid = 2 * sms;
+  k_dfma_peak<<<grid, 1024>>>(d, 200, 1.0000001, 1e-9);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<grid, 1024>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double t = 2.0 * 8 * (double)iters * 1024.0 * grid / (ms * 1e-3) * 1e-12;
+    if (t > best) best = t;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  g_launches += 4;
+  *tflops = best;
+#endif
+  return SB_OK;
+}
+
 extern "C" int sb_plan_column_indices(sb_plan* pl, int32_t* d_colidx, void* stream) {
   if (!pl || !d_colidx) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
   SB_LAUNCH(k_colidx, (unsigned)pl->d.n_cells, 256, 0, (cudaStream_t)stream, pl->d, d_colidx);
@@ -1389,16 +1440,29 @@ extern "C" int sb_rebase_w(sb_plan* pl, double* d_u, double* d_base_w, int32_t b
   return SB_OK;
 }
 
+extern "C" int sb_newton_update_damped(sb_plan* pl, double* d_u, const double* d_du,
+                                       const double* d_b, const double* d_tol, double omega,
+                                       double max_du, double log_alpha, double rel_tol,
+                                       double abs_tol, double* d_out, void* stream);
+
 extern "C" int sb_newton_update(sb_plan* pl, double* d_u, const double* d_du, const double* d_b,
                                 const double* d_tol, double omega, double max_du,
                                 double rel_tol, double abs_tol, double* d_out, void* stream) {
+  return sb_newton_update_damped(pl, d_u, d_du, d_b, d_tol, omega, max_du, 0.0, rel_tol, abs_tol,
+                                 d_out, stream);
+}
+
+extern "C" int sb_newton_update_damped(sb_plan* pl, double* d_u, const double* d_du,
+                                       const double* d_b, const double* d_tol, double omega,
+                                       double max_du, double log_alpha, double rel_tol,
+                                       double abs_tol, double* d_out, void* stream) {
   if (!pl || !d_u || !d_du || !d_out) { snprintf(g_err, sizeof g_err, "null argument"); return SB_ERR_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaMemsetAsync(d_out, 0, 6 * sizeof(double), s));
   const int64_t N = pl->d.N;
   unsigned nblk = (unsigned)std::min<int64_t>((N + 255) / 256, 148 * 8);
   SB_LAUNCH(k_newton_update, nblk, 256, 0, s, N, d_u, d_du, d_b, d_tol, omega, max_du, rel_tol,
-                                       abs_tol, d_out);
+                                       abs_tol, log_alpha, d_out);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return SB_OK;

@@ -133,12 +133,13 @@ class AssemblyPlan(object):
                                         _p(bc_cells), _p(bc_avg), self._stream(stream)))
 
     def newton_update(self, u, du, b, tol, omega, max_du, rel_tol, abs_tol, out=None,
-                      stream=None):
+                      stream=None, log_alpha=None):
         if out is None:
             out = torch.zeros(6, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.sb_newton_update(
+        _lib.check(self.lib.sb_newton_update_damped(
             self._h, _p(u), _p(du), _p(b), _p(tol), float(omega),
-            float(max_du if max_du is not None else -1.0), float(rel_tol),
+            float(max_du if max_du is not None else -1.0),
+            float(log_alpha if log_alpha is not None else 0.0), float(rel_tol),
             float(abs_tol), _p(out), self._stream(stream)))
         return out
 

@@ -82,12 +82,12 @@ class CudaBackend(object):
             self._solver = make_solver(self.pa, self.device)
         self._solver.solve(self.vals, self.b, self.du)
 
-    def newton_update(self, tol, omega, max_du, rel_tol, abs_tol):
+    def newton_update(self, tol, omega, max_du, rel_tol, abs_tol, log_alpha=None):
         if not isinstance(tol, torch.Tensor):
             tol = self.T(tol)
             self._tol = tol
         out = self.plan.newton_update(self.u, self.du, self.b, tol, omega, max_du, rel_tol,
-                                      abs_tol, self._metrics).cpu().numpy()
+                                      abs_tol, self._metrics, log_alpha=log_alpha).cpu().numpy()
         return dict(b_norm=float(out[0]), du_norm=float(out[1]),
                     rel_du_norm=float(np.sqrt(out[2])) if out[5] > 0 else float('nan'),
                     combined_du_norm=float(out[3]), has_nans=bool(out[4] > 0))

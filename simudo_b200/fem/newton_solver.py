@@ -105,6 +105,9 @@ class NewtonSolver(object):
     def get_max_du(self):
         return None
 
+    def get_log_alpha(self):
+        return None
+
     def _tolerance_vector(self):
         tol = self.parameters.get('absolute_tolerance_vector', None)
         if tol is None:
@@ -122,9 +125,12 @@ class NewtonSolver(object):
         if getattr(self, '_tol_dev', None) is None:
             self._tol_dev = be.T(self._tolerance_vector()) if hasattr(be, 'T') \
                 else self._tolerance_vector()
+        extra = {}
+        if self.get_log_alpha() is not None:
+            extra['log_alpha'] = self.get_log_alpha()
         m = be.newton_update(self._tol_dev, self.get_omega(), self.get_max_du(),
                              self.parameters['relative_tolerance'],
-                             self.parameters['absolute_tolerance'])
+                             self.parameters['absolute_tolerance'], **extra)
         s = self.solution
         s.b_norm, s.du_norm = m['b_norm'], m['du_norm']
         s.rel_du_norm, s.combined_du_norm = m['rel_du_norm'], m['combined_du_norm']
@@ -178,8 +184,12 @@ class NewtonSolverMaxDu(NewtonSolver):
 
 
 class NewtonSolverLogDamping(NewtonSolver):
-    def do_iteration(self):
-        raise NotImplementedError('log damping is not lowered to the device yet')
+    """``newton_solver.py:542-547`` (ref. Gaury 2018): the applied step is
+    ``sign(du) log1p(alpha |du|) / alpha``; done inside the update kernel
+    (``sb_newton_update_damped``)."""
+
+    def get_log_alpha(self):
+        return self.parameters.get('logdamping_alpha', 1.72)
 
 
 class _BlockDiagonalMixin(object):

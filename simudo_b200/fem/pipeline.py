@@ -16,9 +16,12 @@ __all__ = ['PipelinedAssembler']
 
 class PipelinedAssembler(object):
     def __init__(self, plan, host_inputs, bc_values=None, natbc_values=None, depth=2,
-                 pre_assemble=None):
+                 pre_assemble=None, resident=None):
         """``host_inputs``: {name: pinned host tensor} with names among ``u``,
-        ``base_w``, ``thmeq_phi``, ``phi_opt`` (defines shapes); ``pre_assemble(d)``:
+        ``base_w``, ``thmeq_phi``, ``phi_opt`` (defines shapes): what the caller changes
+        between steps and is copied every step.  ``resident``: {name: device tensor} of the
+        inputs that do not change per Newton step (``thermal_equilibrium_phi``, the optical
+        flux between optical updates) and stay on the device.  ``pre_assemble(d)``:
         optional callable run on the compute stream before the assembly (e.g. the
         ghost exchange of a multi-GPU strip decomposition)."""
         self.plan = plan
@@ -31,6 +34,7 @@ class PipelinedAssembler(object):
         self.vals = plan.new_values()
         self.bc_values, self.natbc_values = bc_values, natbc_values
         self.pre_assemble = pre_assemble
+        self.resident = dict(resident or {})
         self.s_h2d = torch.cuda.Stream(dev)
         self.s_cmp = torch.cuda.Stream(dev)
         self.s_d2h = torch.cuda.Stream(dev)
@@ -56,6 +60,7 @@ class PipelinedAssembler(object):
                 self.s_cmp.wait_event(self.ev_d2h[s])      # b slot read back
             if self.pre_assemble is not None:
                 self.pre_assemble(d)
+            d = dict(self.resident, **d)
             self.plan.assemble(d['u'], d.get('base_w'), d.get('thmeq_phi'), d.get('phi_opt'),
                                self.bc_values, self.natbc_values, self.vals, self.dev_b[s],
                                stream=self.s_cmp)

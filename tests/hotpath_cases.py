@@ -231,6 +231,14 @@ def newton_update_parity():
     assert abs(out[3] - ref['combined_du_norm']) <= 1e-15 * ref['combined_du_norm']
     assert out[4] == 0.0
     assert np.abs(ud.cpu().numpy() - expect).max() == 0.0
+    # NewtonSolverLogDamping (newton_solver.py:542-547): damped step, metrics from the raw du
+    alpha = 1.72
+    ud = T(u).clone()
+    out = plan.newton_update(ud, T(du), T(b), T(tol), 0.7, None, 1e-4, 1.0,
+                             log_alpha=alpha).cpu().numpy()
+    expect = u - 0.7 * np.sign(du) * np.log1p(np.abs(du) * alpha) / alpha
+    assert np.abs(ud.cpu().numpy() - expect).max() <= 4e-16 * np.abs(expect).max()
+    assert out[1] == np.abs(du).max()
     # NaN poisoning is detected, not raised (newton_solver.py:84-89)
     u2 = u.copy(); u2[5] = np.nan
     out = plan.newton_update(T(u2), T(du), T(b), T(tol), 1.0, None, 1e-4, 1.0).cpu().numpy()

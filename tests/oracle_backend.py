@@ -90,8 +90,10 @@ class OracleBackend(object):
         if not np.isfinite(self.du).all():
             raise RuntimeError('singular Jacobian')
 
-    def newton_update(self, tol, omega, max_du, rel_tol, abs_tol):
+    def newton_update(self, tol, omega, max_du, rel_tol, abs_tol, log_alpha=None):
         step = self.du if (max_du is None or max_du <= 0) else np.clip(self.du, -max_du, max_du)
+        if log_alpha:
+            step = np.sign(step) * np.log1p(np.abs(step) * log_alpha) / log_alpha
         self.u = self.u - omega * step
         m = orc_mod.newton_metrics(self.u, self.du, self.b, np.asarray(tol), rel_tol, abs_tol)
         return {k: (bool(v) if k == 'has_nans' else float(v)) for k, v in m.items()}

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, 'include', 'simudo_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(sb_[a-z_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(sb_[a-z0-9_]+)\s*\(', src)))
 
 
 def test_header_symbols_exported_by_cuda_library():
