@@ -181,6 +181,21 @@ int sb_plan_is_native(const sb_plan* plan);
 /* materialise the CSR column indices (int32) on the device: for export/solvers */
 int sb_plan_column_indices(sb_plan* plan, int32_t* d_colidx, void* stream);
 
+/* ---- a8: natural boundary conditions (exterior-facet integrals) ------------------------
+ * Replaces the `ds(fv)` terms Spatial builds for natural BCs (simudo/fem/spatial.py:
+ * 237-273; poisson_drift_diffusion1.py1:47: + oint phi_bc psi . n): for every listed
+ * exterior facet (cell, local facet) the three integrals  oint g psi_k . n ds  of the
+ * facet's BDM2 dofs with g = d_c0[i] + sum_a d_p2[i][a] N2_a (P2 nodal values of the
+ * non-constant part on the facet's cell; either pointer may be NULL), 3 Gauss-Legendre
+ * points.  Results are written to d_natbc_values[d_slot[3 i + k]] -- the array
+ * sb_state.d_natbc_values of the next sb_assemble -- so a bias sweep only updates d_c0.
+ * h_tables: 84 doubles {w[3], N2[3 facets][3 points][6], trace[3 facets][3 dofs][3 points]}
+ * (simudo_b200/fem/reference_element.py: facet_gl_w, facet_p2, facet_bdm_trace).     */
+int sb_natbc_eval(sb_plan* plan, int64_t n_facets, const int32_t* d_cell,
+                  const int8_t* d_local, const int32_t* d_slot, const double* d_c0,
+                  const double* d_p2, const double* h_tables, int64_t n_tables,
+                  double* d_natbc_values, void* stream);
+
 /* ---- a9: qfl rebasing ----------------------------------------------------------
  * Replaces MixedQflBand.mixedqfl_do_rebase_w (poisson_drift_diffusion1.py1:339-383)
  * with default thresholds (0,0): base_w += cellavg(delta_w), BC-adjacent cells

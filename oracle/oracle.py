@@ -196,6 +196,43 @@ class Oracle(object):
 # ---------------------------------------------------------------------------
 # small numpy restatements (non-assembly rows of SURVEY 8a)
 # ---------------------------------------------------------------------------
+def natural_bc_integrals(pa, cells, local_facets, c0, p2):
+    """``oint g psi_k . n ds`` for the three BDM2 dofs k of exterior facets (cell, local
+    facet), ``g = c0 + P2 function`` given by nodal values on the cell -- the `ds` term of
+    ``poisson_drift_diffusion1.py1:47`` built by ``fem/spatial.py:237-273``.  Restated in
+    physical space, independent of the product's reference-trace tables: Piola-mapped BDM2
+    values (``fiat_like.tabulate_bdm2``) at the Gauss-Legendre points of the edge, the
+    geometric outward normal, ds = |edge| dt.  Returns [n, 3]."""
+    cells = np.asarray(cells, dtype=np.int64)
+    lf = np.asarray(local_facets, dtype=np.int64)
+    t, w = np.polynomial.legendre.leggauss(3)
+    t, w = 0.5 * (t + 1.0), 0.5 * w
+    ref_v = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    edge = [(1, 2), (0, 2), (0, 1)]                    # local facet i is opposite vertex i
+    out = np.zeros((len(cells), 3))
+    xv = pa.cell_vertices
+    for i, (c, l) in enumerate(zip(cells, lf)):
+        a, b = edge[l]
+        X = ref_v[a][None, :] + t[:, None] * (ref_v[b] - ref_v[a])[None, :]      # [q, 2]
+        val, _ = fl.tabulate_bdm2(X)                    # [q, 12, 2] reference values
+        val = np.asarray(val)
+        if val.shape[0] == 12:                          # accept [12, q, 2] too
+            val = np.transpose(val, (1, 0, 2))
+        x = xv[c]
+        J = np.stack([x[1] - x[0], x[2] - x[0]], axis=1)
+        det = np.linalg.det(J)
+        phys = np.einsum('ab,qkb->qka', J, val) / det   # contravariant Piola
+        e = x[b] - x[a]
+        n = np.array([e[1], -e[0]])
+        mid, opp = 0.5 * (x[a] + x[b]), x[l]
+        if np.dot(n, mid - opp) < 0:
+            n = -n                                      # outward, |n| = |edge|
+        g = c0[i] + np.asarray(fl.tabulate_p2(X)) @ p2[i]                         # [q]
+        for k in range(3):
+            out[i, k] = np.sum(w * g * (phys[:, 3 * l + k, :] @ n))
+    return out
+
+
 def rebase_w(pa, u, base_w, band, bc_cells=(), bc_avg=()):
     """``mixedqfl_do_rebase_w`` with thresholds (0, 0)
     (poisson_drift_diffusion1.py1:339-383, offset_partitioning.py:95-107):

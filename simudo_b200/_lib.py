@@ -21,7 +21,7 @@ _EMULATED = False
 EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
             'sb_plan_is_native', 'sb_measure_fp64_peak',
-            'sb_plan_column_indices', 'sb_rebase_w', 'sb_newton_update', 'sb_newton_update_damped',
+            'sb_plan_column_indices', 'sb_natbc_eval', 'sb_rebase_w', 'sb_newton_update', 'sb_newton_update_damped',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
             'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
             'sb_band_solve', 'sb_band_set_refinement', 'sb_csr_residual_dd', 'sb_optics_create',
@@ -79,6 +79,8 @@ def _declare(lib):
     lib.sb_plan_zero_values.restype = C.c_int
     lib.sb_plan_column_indices.argtypes = [vp, vp, vp]
     lib.sb_plan_column_indices.restype = C.c_int
+    lib.sb_natbc_eval.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp]
+    lib.sb_natbc_eval.restype = C.c_int
     lib.sb_rebase_w.argtypes = [vp, vp, vp, i32, i64, vp, vp, vp]
     lib.sb_rebase_w.restype = C.c_int
     lib.sb_newton_update.argtypes = [vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]

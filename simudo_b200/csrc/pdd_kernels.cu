@@ -1366,6 +1366,55 @@ extern "C" int sb_plan_last_stage_ms(sb_plan* pl, double* ms4) {
   return SB_OK;
 }
 
+/* ---- a8: exterior-facet integrals of the natural boundary conditions -----------------
+ * + oint g psi_i . n ds for the three facet dofs i of every listed exterior facet
+ * (the `ds` term of poisson_drift_diffusion1.py1:47 built by fem/spatial.py:237-273),
+ * g = c0 + (P2 function on the facet's cell), 3 Gauss-Legendre points (degree 4, SURVEY
+ * Appendix A6).  One thread per facet; results go straight to their slots of the
+ * natural-BC value array sb_assemble consumes.                                        */
+struct SbNatTables {
+  double w[3];            /* GL weights on [0, 1]                                     */
+  double p2[3][3][6];     /* [local facet][point][P2 node] Lagrange values            */
+  double tr[3][3][3];     /* [local facet][facet dof][point] BDM scaled-normal trace  */
+};
+
+__global__ void k_natbc_eval(PlanDev pl, int64_t n, const int32_t* cell, const int8_t* local,
+                             const int32_t* slot, const double* c0, const double* p2vals,
+                             SbNatTables T, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = cell[i];
+  const int l = local[i];
+  const SbCellGeom g = sb_geom(pl.cell_vertices + c * 6);
+  const double sgn = ((l == 1) ? -1.0 : 1.0) * g.sdet;       /* outward / reference normal */
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < 3; ++q) {
+    double v = c0 ? c0[i] : 0.0;
+    if (p2vals)
+      for (int a = 0; a < 6; ++a) v += p2vals[i * 6 + a] * T.p2[l][q][a];
+    for (int k = 0; k < 3; ++k) acc[k] += T.w[q] * v * T.tr[l][k][q];
+  }
+  for (int k = 0; k < 3; ++k) out[slot[3 * i + k]] = sgn * acc[k];
+}
+
+extern "C" int sb_natbc_eval(sb_plan* pl, int64_t n_facets, const int32_t* d_cell,
+                             const int8_t* d_local, const int32_t* d_slot, const double* d_c0,
+                             const double* d_p2, const double* h_tables, int64_t n_tables,
+                             double* d_natbc_values, void* stream) {
+  if (!pl || n_facets < 0 || !d_cell || !d_local || !d_slot || !h_tables || !d_natbc_values ||
+      n_tables != (int64_t)(sizeof(SbNatTables) / sizeof(double))) {
+    snprintf(g_err, sizeof g_err, "bad argument to sb_natbc_eval"); return SB_ERR_ARG;
+  }
+  if (n_facets == 0) return SB_OK;
+  SbNatTables T;
+  memcpy(&T, h_tables, sizeof T);
+  SB_LAUNCH(k_natbc_eval, (unsigned)((n_facets + 127) / 128), 128, 0, (cudaStream_t)stream, pl->d,
+            n_facets, d_cell, d_local, d_slot, d_c0, d_p2, T, d_natbc_values);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return SB_OK;
+}
+
 /* ---- FP64 roofline denominator -----------------------------------------------------
  * DFMA throughput of the device, measured: 8 independent FMA chains per thread, enough
  * resident warps to cover the pipe latency (1024 threads x 2 CTAs per SM).             */

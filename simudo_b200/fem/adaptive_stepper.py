@@ -23,6 +23,27 @@ class StepperError(Exception):
 
 
 class BaseAdaptiveStepper(SetattrInitMixin):
+    """Continuation toward a list of target values of one scalar parameter.
+
+    Written from the behaviour of the reference's stepper (``adaptive_stepper.py:82-257``),
+    with its public attribute and hook names, as an explicit state machine:
+
+    * state: the trail of attempts ``(parameter, converged?)``, a bounded set of
+      checkpoints (the ``keep_saved_solutions_count`` most recent converged states) and
+      the step size;
+    * the next attempt starts from the last converged parameter; after a failure the step
+      is multiplied by ``update_parameter_failure_factor`` and the last checkpoint is put
+      back (``user_solution_add(solution, 0, checkpoint, 1)``); after a success that used
+      the full step it is multiplied by ``update_parameter_success_factor``; the step never
+      overshoots the current target, and a failed clipped step shrinks from the clipped
+      length;
+    * a ``RuntimeError`` of the solver (dolfin / PETSc in the reference, the device library
+      here) is a failed attempt, except on the very first one;
+    * the march to a target ends when it has been reached, or -- ``StepperError`` -- when
+      an attempt failed and step / max(abs(parameter), initial step) < ``stepper_rel_tol``;
+    * after every target ``output_writer.write_output(solution, parameter)``; a true
+      ``break_criteria_cb(solution)`` ends the sweep.
+    """
     solution = None
     parameter_start_value = 0.0
     parameter_target_values = [1.0]
@@ -37,50 +58,61 @@ class BaseAdaptiveStepper(SetattrInitMixin):
     def __init__(self, **kwargs):
         super().__init__(**kwargs)
         self.parameter = self.parameter_start_value
-        self.prior_solutions = []
-        self._idx_ok = []
-        self._idx_saved = []
+        self._trail = []            # [(parameter, converged)]
+        self._checkpoints = []      # [(trail index, saved solution)], newest last
+        self.actual_step = None
+
+    # -- the trail ---------------------------------------------------------------------
+    @property
+    def prior_solutions(self):
+        """Every attempt so far as ``AdaptiveLogEntry`` (saved solutions only while kept)."""
+        kept = dict(self._checkpoints)
+        return [AdaptiveLogEntry(p, ok, kept.get(i)) for i, (p, ok) in enumerate(self._trail)]
 
     def add_prior_solution(self, parameter_value, solver_succeeded, saved_solution):
         if saved_solution is not None and not solver_succeeded:
             raise AssertionError('why save a failed solution?')
-        self.prior_solutions.append(
-            AdaptiveLogEntry(parameter_value, solver_succeeded, saved_solution))
-        i = len(self.prior_solutions) - 1
+        self._trail.append((parameter_value, bool(solver_succeeded)))
         if saved_solution is not None:
-            self._idx_saved.append(i)
-        if solver_succeeded:
-            self._idx_ok.append(i)
-        while len(self._idx_saved) > self.keep_saved_solutions_count:
-            k = self._idx_saved.pop(0)
-            self.prior_solutions[k] = self.prior_solutions[k]._replace(saved_solution=None)
+            self._checkpoints.append((len(self._trail) - 1, saved_solution))
+            del self._checkpoints[:-self.keep_saved_solutions_count or None]
 
     def get_last_successful(self, count):
-        return [self.prior_solutions[i] for i in self._idx_ok[-count:]]
+        kept = dict(self._checkpoints)
+        good = [i for i, (_, ok) in enumerate(self._trail) if ok][-count:]
+        return [AdaptiveLogEntry(self._trail[i][0], True, kept.get(i)) for i in good]
+
+    def _last_converged(self):
+        for i in range(len(self._trail) - 1, -1, -1):
+            if self._trail[i][1]:
+                return i
+        return None
 
     def reset_parameter_to_last_successful(self):
-        last_ok = self.get_last_successful(1)
-        self.parameter = last_ok[0].parameter if last_ok else self.parameter_start_value
+        i = self._last_converged()
+        self.parameter = self.parameter_start_value if i is None else self._trail[i][0]
 
+    # -- one attempt ---------------------------------------------------------------------
     def update_parameter(self):
-        last_ok = self.get_last_successful(1)
-        if not last_ok:
-            self.reset_parameter_to_last_successful()
+        i = self._last_converged()
+        if i is None:                       # nothing converged yet: (re)try the start value
+            self.parameter = self.parameter_start_value
             return
-        last_ok = last_ok[0]
-        last = self.prior_solutions[-1]
-        if not last.success:
+        base = self._trail[i][0]
+        failed = not self._trail[-1][1]
+        if failed:
             logging.getLogger('stepper').info('** Newton solver failed, trying smaller step size')
             self.step_size *= self.update_parameter_failure_factor
-        self.actual_step = min(self.step_size,
-                               abs(self.parameter_target_value - last_ok.parameter))
-        if (self.actual_step == self.step_size) and last.success:
+        room = abs(self.parameter_target_value - base)
+        clipped = room < self.step_size
+        self.actual_step = room if clipped else self.step_size
+        if failed:
+            if clipped:
+                self.step_size = self.actual_step * self.update_parameter_failure_factor
+            self.user_solution_add(self.solution, 0.0, dict(self._checkpoints).get(i), 1.0)
+        elif not clipped:
             self.step_size *= self.update_parameter_success_factor
-        if (self.actual_step < self.step_size) and not last.success:
-            self.step_size = self.actual_step * self.update_parameter_failure_factor
-        if not last.success:
-            self.user_solution_add(self.solution, 0.0, last_ok.saved_solution, 1.0)
-        self.parameter = last_ok.parameter + self.step_sign * self.actual_step
+        self.parameter = base + self.step_sign * self.actual_step
 
     def user_solver(self, solution, parameter):
         raise NotImplementedError()
@@ -94,43 +126,48 @@ class BaseAdaptiveStepper(SetattrInitMixin):
     def do_iteration(self):
         self.update_parameter()
         try:
-            success = self.user_solver(self.solution, self.parameter)
+            ok = bool(self.user_solver(self.solution, self.parameter))
         except RuntimeError:
-            success = False
-            if len(self.prior_solutions) == 0:
+            if not self._trail:
                 raise
-        saved = self.user_solution_save(self.solution) if success else None
-        self.add_prior_solution(self.parameter, success, saved)
+            ok = False
+        self.add_prior_solution(self.parameter, ok,
+                                self.user_solution_save(self.solution) if ok else None)
+
+    # -- the sweep -----------------------------------------------------------------------
+    def _stalled(self, initial_step):
+        if not self._trail or self._trail[-1][1]:
+            return False
+        scale = max(abs(self.parameter), initial_step)
+        return abs(self.step_size) / scale < self.stepper_rel_tol
 
     def do_loop(self):
-        sufficient_progress = True
-        initial_step_size = self.step_size
-        for val in self.parameter_target_values:
+        log = logging.getLogger('stepper')
+        initial_step = self.step_size
+        for target in self.parameter_target_values:
             self.reset_parameter_to_last_successful()
-            self.step_sign = -1. if self.parameter > val else 1.
-            self.parameter_target_value = val
+            self.parameter_target_value = target
+            self.step_sign = -1. if self.parameter > target else 1.
+            gave_up = False
             while True:
-                last_ok = self.get_last_successful(1)
-                failed_prev = bool(self.prior_solutions) and not self.prior_solutions[-1].success
-                if last_ok and last_ok[0].parameter == val:
+                i = self._last_converged()
+                if i is not None and self._trail[i][0] == target:
                     break
-                if (failed_prev and abs(self.step_size) / max(abs(self.parameter),
-                                                               initial_step_size)
-                        < self.stepper_rel_tol):
-                    sufficient_progress = False
+                if self._stalled(initial_step):
+                    gave_up = True
                     break
                 self.do_iteration()
-            if self.output_writer is not None and self.get_last_successful(1):
-                logging.getLogger('stepper').info('Writing output')
+            if self.output_writer is not None and self._last_converged() is not None:
+                log.info('Writing output')
                 self.output_writer.write_output(self.solution, self.parameter)
-            if not sufficient_progress:
-                logging.getLogger('stepper').error('Insufficient progress, stopping.')
+            if gave_up:
+                log.error('Insufficient progress, stopping.')
                 raise StepperError(
                     'Solver unable to progress. Among many possible causes of this error '
                     'are: poorly formed problem, incorrect boundary conditions, '
                     'inappropriate material parameters, or insufficient meshing.')
             if self.break_criteria_cb is not None and self.break_criteria_cb(self.solution):
-                logging.getLogger('stepper').info('*** Break criteria met, stopping.')
+                log.info('*** Break criteria met, stopping.')
                 break
 
 

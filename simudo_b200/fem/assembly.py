@@ -127,6 +127,23 @@ class AssemblyPlan(object):
         _lib.check(self.lib.sb_plan_column_indices(self._h, _p(col), self._stream(stream)))
         return col
 
+    def natbc_eval(self, cell, local, slot, c0, p2, out, stream=None):
+        """a8: exterior-facet integrals of the natural BCs into ``out`` (the
+        ``natbc_values`` argument of ``assemble``); see ``sb_natbc_eval``."""
+        from .reference_element import reference_tables
+        if getattr(self, '_nat_tables', None) is None:
+            T = reference_tables()
+            tab = np.concatenate([np.asarray(T.facet_gl_w, dtype=np.float64).ravel(),
+                                  np.transpose(T.facet_p2, (0, 2, 1)).ravel(),       # [l][q][a]
+                                  np.stack([T.facet_bdm_trace[l, 3 * l:3 * l + 3, :]
+                                            for l in range(3)]).ravel()])             # [l][k][q]
+            self._nat_tables = np.ascontiguousarray(tab, dtype=np.float64)
+        tab = self._nat_tables
+        _lib.check(self.lib.sb_natbc_eval(
+            self._h, int(cell.numel()), _p(cell), _p(local), _p(slot), _p(c0), _p(p2),
+            tab.ctypes.data_as(C.c_void_p), len(tab), _p(out), self._stream(stream)))
+        return out
+
     def rebase_w(self, u, base_w, band, bc_cells=None, bc_avg=None, stream=None):
         n = 0 if bc_cells is None else int(bc_cells.numel())
         _lib.check(self.lib.sb_rebase_w(self._h, _p(u), _p(base_w), band, n,

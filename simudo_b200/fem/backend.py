@@ -71,6 +71,29 @@ class CudaBackend(object):
     def set_natbc_values(self, v):
         self.natbc = self.T(self.plan.natbc_device_order(v)) if len(v) else None
 
+    def set_natbc(self, spec):
+        """Natural BCs as facet data (``PDDSystem.natbc_spec``): the exterior-facet integrals
+        are evaluated on the device (``sb_natbc_eval``); only what changed is uploaded -- in a
+        bias sweep the ``c0`` vector."""
+        if spec is None:
+            self.natbc = None
+            return
+        T = self.T
+        c = getattr(self, '_natbc_dev', None)
+        if c is None:
+            c = self._natbc_dev = dict(
+                cell=T(spec['cell'], torch.int32), local=T(spec['local'], torch.int8),
+                slot=T(spec['slot'], torch.int32), c0=None, p2=None, h_c0=None, h_p2=None)
+            self.natbc = torch.zeros(len(spec['slot']), dtype=torch.float64, device=self.device)
+        dirty = False
+        for k in ('c0', 'p2'):
+            if c['h_' + k] is None or not np.array_equal(c['h_' + k], spec[k]):
+                c['h_' + k] = spec[k].copy()
+                c[k] = T(spec[k])
+                dirty = True
+        if dirty:
+            self.plan.natbc_eval(c['cell'], c['local'], c['slot'], c['c0'], c['p2'], self.natbc)
+
     # -- hot loop ----------------------------------------------------------------
     def assemble(self):
         self.plan.assemble(self.u, self.base_w, self.thmeq, self.phi_opt, self.bc_values,

@@ -11,7 +11,7 @@ polynomial, DG0/DG1/DG2) and plain floats.  Nothing here is UFL.
 """
 import numpy as np
 
-__all__ = ['Expr', 'Constant', 'CellFunction', 'ZeroVec', 'ThermalEquilibriumU',
+__all__ = ['Expr', 'Constant', 'CellFunction', 'ZeroVec', 'UnitVec', 'ThermalEquilibriumU',
            'as_expr', 'p2_from_p1']
 
 
@@ -125,6 +125,38 @@ class ZeroVec(_Leaf):
 
     def is_zero(self):
         return True
+
+
+class UnitVec(_Leaf):
+    """``mesh_util.unitvec_x`` / ``unitvec_y`` (``fem/mesh_util1.py1:160-161``): constant unit
+    vector fields, for non-zero essential flux values.  ``vector_components`` turns a linear
+    combination of them into (vx, vy)."""
+    is_vector = True
+
+    def __init__(self, axis):
+        self.axis = int(axis)
+
+    def _eval_leaf(self, cells, ref_points):
+        raise TypeError('a vector field has no scalar value; use vector_components')
+
+
+def vector_components(expr):
+    """(vx, vy) of a linear combination of ZeroVec / UnitVec leaves (constant vector field)."""
+    v = [0.0, 0.0]
+    e = as_expr(expr)
+    if e.offset != 0.0:
+        raise TypeError('scalar offset in a vector-valued boundary value')
+    for a, leaf in e.terms:
+        if isinstance(leaf, ZeroVec):
+            continue
+        if isinstance(leaf, UnitVec):
+            v[leaf.axis] += a
+        elif isinstance(leaf, Constant):
+            raise TypeError('scalar Constant in a vector-valued boundary value')
+        else:
+            raise NotImplementedError('essential flux values must be constant vectors '
+                                      '(zerovec, unitvec_x, unitvec_y)')
+    return v[0], v[1]
 
 
 def _p1_basis(X):

@@ -20,7 +20,7 @@ backend (CUDA by default; tests inject an oracle-based one).
 import numpy as np
 
 from ..fem import model as M
-from ..fem.expr import Expr, ThermalEquilibriumU, as_expr, p2_from_p1
+from ..fem.expr import Expr, ThermalEquilibriumU, as_expr, p2_from_p1, vector_components
 from ..fem.problem_arrays import ProblemArrays
 from ..fem.reference_element import reference_tables, gauss_legendre_01
 from .optical import AbsorptionRangesHelper
@@ -213,13 +213,18 @@ class PDDSystem(_SystemBase):
                     continue
                 d = pa.facet_dofs(p, facets)                       # [n, 3]
                 val = bc.value
-                mag = val.magnitude if hasattr(val, 'magnitude') else val
-                if not as_expr(mag).is_zero():
-                    raise NotImplementedError(
-                        'non-zero essential flux BCs are not supported yet '
-                        '(all shipped examples use zerovec)')
+                # value of the BDM2 dofs (DirichletBC on the flux sub-space, spatial.py:296-304):
+                # the dof functional is v(x_k) . n with n the edge tangent (lower -> higher
+                # vertex) rotated clockwise, length-scaled; for a constant
+                # vector field all three dofs of a facet are vx t_y - vy t_x
+                unit = 'V/mesh_unit' if p == 0 else 'A/mesh_unit^2'
+                mag = val.m_as(unit) if hasattr(val, 'm_as') else val
+                vx, vy = vector_components(mag)
+                xf = mesh.coordinates[mesh.facet_vertices[facets]]  # [n, 2 vertices, 2]
+                t = xf[:, 1] - xf[:, 0]
+                g = vx * t[:, 1] - vy * t[:, 0]
                 bc_dofs.append(d.ravel())
-                bc_vals.append(np.zeros(d.size))
+                bc_vals.append(np.repeat(g, 3))
         if bc_dofs:
             dofs = np.concatenate(bc_dofs)
             vals = np.concatenate(bc_vals)
@@ -282,9 +287,47 @@ class PDDSystem(_SystemBase):
         return dict(cells=cells.astype(np.int32), inv=inv, w=w, c=c, va=va, vb=vb, l=l,
                     dof_a=pa.cell_dofs[c, lay['dg'][0][va]], dof_b=pa.cell_dofs[c, lay['dg'][0][vb]])
 
+    def natbc_spec(self):
+        """The natural boundary conditions as data for the exterior-facet kernel
+        (``sb_natbc_eval``; ``fem/spatial.py:237-273``): per 'poisson/phi' facet its cell and
+        local facet, the slots of its three integrals in the plan's natural-BC array, the
+        constant part ``c0`` of the BC value (floats and ``Constant`` leaves: the swept bias)
+        and the P2 nodal values ``p2`` of its cell-function part on the facet's cell.  The
+        integrals themselves are done by the backend (device kernel / oracle)."""
+        if not self._nat:
+            return None
+        if getattr(self, '_nat_static', None) is None:
+            inv = np.empty(len(self.pa.natbc_order), dtype=np.int32)
+            inv[self.pa.natbc_order] = np.arange(len(inv), dtype=np.int32)
+            cells = np.concatenate([c for _, _, c, _ in self._nat]).astype(np.int32)
+            local = np.concatenate([l for _, _, _, l in self._nat]).astype(np.int8)
+            self._nat_static = (cells, local, np.ascontiguousarray(inv))
+        cells, local, slot = self._nat_static
+        c0, p2 = [], []
+        for bc, facets, c, l in self._nat:
+            val = bc.value
+            mag = as_expr(val.m_as('V') if hasattr(val, 'm_as') else val)
+            k0 = mag.offset
+            acc = np.zeros((len(c), 6))
+            for a, leaf in mag.terms:
+                if hasattr(leaf, 'assign'):                       # Constant
+                    k0 += a * float(leaf)
+                elif hasattr(leaf, 'values') and not isinstance(leaf, ThermalEquilibriumU):
+                    v = np.asarray(leaf.values)[c]
+                    v6 = (np.repeat(v, 6, axis=1) if v.shape[1] == 1
+                          else p2_from_p1(v) if v.shape[1] == 3 else v)
+                    acc += a * v6
+                else:
+                    raise TypeError('unsupported leaf in a natural-BC value: %r' % (leaf,))
+            c0.append(np.full(len(c), k0))
+            p2.append(acc)
+        return dict(cell=cells, local=local, slot=slot, c0=np.concatenate(c0),
+                    p2=np.ascontiguousarray(np.concatenate(p2)))
+
     def natbc_values(self):
         """Integrals oint phi_bc psi_i . n ds for the three facet dofs of every
-        'poisson/phi' facet, in the order the plan was given."""
+        'poisson/phi' facet, in the order the plan was given (host evaluation; kept for
+        backends without an exterior-facet routine and as a cross-check in the tests)."""
         if not self._nat:
             return np.zeros(0)
         T = reference_tables()
@@ -430,7 +473,10 @@ class PDDSystem(_SystemBase):
     # -- hot-path forwards ------------------------------------------------------------
     def assemble(self):
         be = self.backend
-        be.set_natbc_values(self.natbc_values())
+        if hasattr(be, 'set_natbc'):
+            be.set_natbc(self.natbc_spec())          # exterior-facet integrals on the backend
+        else:
+            be.set_natbc_values(self.natbc_values())
         be.assemble()
 
     def rebase_w(self, band):

@@ -16,7 +16,7 @@ import logging
 
 import numpy as np
 
-from ..fem.expr import CellFunction, Constant, ThermalEquilibriumU, ZeroVec, p2_from_p1
+from ..fem.expr import CellFunction, Constant, ThermalEquilibriumU, UnitVec, ZeroVec, p2_from_p1
 from ..fem.spatial import Spatial
 from ..mesh import CellRegions
 from ..util import NameDict, SetattrInitMixin
@@ -42,13 +42,21 @@ class GetToSaveMixin(object):
 
 class MeshUtil(SetattrInitMixin):
     """The few ``mesh_util`` members user scripts touch (``fem/mesh_util1.py1``):
-    ``zerovec``, ``zero``, ``Constant``, ``unit_registry``."""
+    ``zerovec``, ``unitvec_x``, ``unitvec_y``, ``zero``, ``Constant``, ``unit_registry``."""
     mesh_data = None
     unit_registry = None
 
     @property
     def zerovec(self):
         return ZeroVec()
+
+    @property
+    def unitvec_x(self):
+        return UnitVec(0)
+
+    @property
+    def unitvec_y(self):
+        return UnitVec(1)
 
     @property
     def zero(self):

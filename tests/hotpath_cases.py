@@ -245,6 +245,40 @@ def newton_update_parity():
     assert out[4] > 0.0
 
 
+def natbc_eval_parity():
+    """a8: the exterior-facet kernel (sb_natbc_eval) against the oracle's physical-space
+    restatement of the `ds` integrals, on both contacts of a graded 2D mesh (both signs of
+    detJ, all three local facet numbers), constant + P2 boundary function."""
+    pa = syn.ib_problem(nx=7, ny=6, pattern='native')
+    plan = AssemblyPlan(pa)
+    T = plan.tensor
+    mesh = pa.mesh
+    facets = np.concatenate([pa.contacts['left'], pa.contacts['right'], pa.contacts['horiz']])
+    # the boundary of a product mesh only has local facets 0 and 2: add a few interior
+    # facets seen from the cell in which they are local facet 1 (the kernel integrates over
+    # whatever facet of whatever cell it is given, with that cell's outward normal)
+    inner = np.nonzero((mesh.facet_cells[:, 1] >= 0) & (mesh.facet_local[:, 0] == 1))[0][:7]
+    facets = np.concatenate([facets, inner])
+    cells = mesh.facet_cells[facets, 0].astype(np.int32)
+    local = mesh.facet_local[facets, 0].astype(np.int8)
+    assert set(local.tolist()) == {0, 1, 2}
+    rng = np.random.default_rng(11)
+    c0 = rng.standard_normal(len(facets))
+    p2 = rng.standard_normal((len(facets), 6))
+    slot = rng.permutation(3 * len(facets)).astype(np.int32)
+    out = torch.zeros(3 * len(facets), dtype=torch.float64, device=plan.device)
+    plan.natbc_eval(T(cells, torch.int32), T(local, torch.int8), T(slot, torch.int32), T(c0),
+                    T(p2), out)
+    ref = orc_mod.natural_bc_integrals(pa, cells, local, c0, p2).ravel()
+    got = out.cpu().numpy()[slot]
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    # constant-only and function-only variants (NULL pointers)
+    plan.natbc_eval(T(cells, torch.int32), T(local, torch.int8), T(slot, torch.int32), T(c0),
+                    None, out)
+    ref = orc_mod.natural_bc_integrals(pa, cells, local, c0, np.zeros_like(p2)).ravel()
+    assert np.abs(out.cpu().numpy()[slot] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
 def surface_flux_parity():
     pa = syn.pn_problem(nx=6, ny=5)
     st = syn.synthetic_state(pa)

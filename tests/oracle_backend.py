@@ -62,6 +62,15 @@ class OracleBackend(object):
     def set_natbc_values(self, v):
         self.natbc = np.asarray(v, dtype=np.float64)
 
+    def set_natbc(self, spec):
+        """Natural BCs as facet data: integrated by the oracle's own exterior-facet
+        restatement (``oracle.natural_bc_integrals``), not handed over as numbers."""
+        if spec is None:
+            self.natbc = np.zeros(0)
+            return
+        self.natbc = orc_mod.natural_bc_integrals(self.pa, spec['cell'], spec['local'],
+                                                  spec['c0'], spec['p2']).ravel()
+
     def assemble(self):
         self.vals, self.b = self.oracle.assemble(
             self.u, self.base_w, self.thmeq, self.phi_opt, self.bc_values, self.natbc)

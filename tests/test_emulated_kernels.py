@@ -54,6 +54,10 @@ def test_newton_update_emulated(emulated_lib):
     hc.newton_update_parity()
 
 
+def test_natbc_eval_emulated(emulated_lib):
+    hc.natbc_eval_parity()
+
+
 def test_surface_flux_emulated(emulated_lib):
     hc.surface_flux_parity()
 

@@ -96,6 +96,10 @@ def test_newton_update():
     hc.newton_update_parity()
 
 
+def test_natbc_eval():
+    hc.natbc_eval_parity()
+
+
 def test_surface_flux():
     hc.surface_flux_parity()
 

@@ -121,3 +121,72 @@ def test_2d_pn_diode_newton_solve_on_gpu_multifrontal():
             assert abs(j) < 1e-9 * abs(ref[0.3])
         else:
             assert abs(j - j0) <= 1e-6 * abs(j0), (v, j, j0)
+
+
+def test_nonzero_essential_flux_value_is_lowered_and_imposed():
+    """General essential BC values (fem/spatial.py:275-306; DirichletBC on the BDM sub-space):
+    E = 0.5 V/um * unitvec_y on the non-conductive sides of the diode's thermal-equilibrium
+    stage.  The lowered dof values follow FIAT's scaled-normal functionals, the solved field
+    carries them, and its boundary flux is the prescribed E . n times the length."""
+    from oracle_backend import OracleBackend
+    from oracle import oracle as orc_mod
+    from simudo_b200.example import pn_diode
+    from simudo_b200.example.pn_diode import (CellRegions, FacetRegions, ProblemData,
+                                              SimpleSiliconMaterial, topology_standard_contacts)
+    U, mesh_data = pn_diode.build(product2d_Ys=np.linspace(0.0, 0.2, 4))
+    R, F = CellRegions(), FacetRegions()
+    topology_standard_contacts(R, F)
+    R.Si = R.pSi | R.nSi
+    F.p_contact, F.n_contact = F.left_contact, F.right_contact
+
+    def create(goal, phi_cn=None):
+        root = ProblemData(goal=goal, mesh_data=mesh_data, unit_registry=U,
+                           backend_factory=OracleBackend)
+        pdd = root.pdd
+        pdd.easy_add_band(name='CB')
+        pdd.easy_add_band(name='VB')
+        sp = pdd.spatial
+        sp.add_rule('temperature', R.domain, U('300 K'))
+        sp.add_rule('poisson/static_rho', R.pSi, -1e18 * U('elementary_charge/cm^3'))
+        sp.add_rule('poisson/static_rho', R.nSi, +1e18 * U('elementary_charge/cm^3'))
+        SimpleSiliconMaterial(problem_data=root).register()
+        mu = pdd.mesh_util
+        if goal == 'thermal equilibrium':
+            sp.add_BC('poisson/phi', F.p_contact | F.n_contact, phi_cn)
+        zeroE = F.exterior - (F.p_contact | F.n_contact).both()
+        sp.add_BC('poisson/E', zeroE, U('V/um') * (0.5 * mu.unitvec_y))
+        return root
+    p0 = create('local charge neutrality')
+    p0.pdd.easy_auto_pre_solve()
+    p1 = create('thermal equilibrium', phi_cn=p0.pdd.poisson.phi)
+    p1.pdd.initialize_from(p0.pdd)
+    sysm = p1.pdd.system
+    pa, mesh = sysm.pa, sysm.mesh
+    # lowered values: horizontal facets run from the lower to the higher vertex id, i.e. in
+    # +x: n_scaled = (t_y, -t_x) = (0, -dx), so every dof is -0.5 dx
+    xy = mesh.coordinates[mesh.facet_vertices]
+    dx = {}
+    for f in mesh.boundary_facets():
+        if abs(xy[f, 0, 1] - xy[f, 1, 1]) < 1e-14:
+            dx[f] = abs(xy[f, 1, 0] - xy[f, 0, 0])
+    assert len(dx) == 2 * (len(np.unique(mesh.coordinates[:, 0])) - 1)
+    want = {}
+    for f, d in dx.items():
+        for dof in pa.facet_dofs(0, np.array([f]))[0]:
+            want[int(dof)] = -0.5 * d
+    got = dict(zip(pa.bc_dofs.tolist(), sysm.bc_values.tolist()))
+    assert set(want) == set(got)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-15
+    p1.pdd.easy_auto_pre_solve()
+    u = sysm.u_host()
+    for k in want:                                  # Newton's x0 lifting lands on the value
+        assert abs(u[k] - want[k]) <= 1e-12
+    # boundary flux of the solved E through the top side: E . n = +0.5 V/um, bottom: -0.5
+    ymid = xy[list(dx), :, 1].mean(axis=1)
+    fl = np.array(list(dx))
+    top, bottom = fl[ymid > 0.1], fl[ymid < 0.1]
+    Lx = mesh.coordinates[:, 0].max()
+    ft, _ = orc_mod.surface_flux(pa, u, 0, top)
+    fb, _ = orc_mod.surface_flux(pa, u, 0, bottom)
+    assert abs(ft - 0.5 * Lx) < 1e-12 and abs(fb + 0.5 * Lx) < 1e-12
