@@ -189,8 +189,11 @@ class Oracle(object):
 
     def to_scipy(self, vals):
         import scipy.sparse as sp
-        v = np.asarray(vals) if self._perm is None else np.asarray(vals)[self._perm]
-        return sp.csr_matrix((v, self._colidx_sorted, self._rowptr_csr), shape=(self.pa.N, self.pa.N))
+        # copies: scipy sorts the indices of a CSR matrix in place, which would silently
+        # permute the caller's value array of a layout with unsorted columns ('native')
+        v = np.array(vals, copy=True) if self._perm is None else np.asarray(vals)[self._perm]
+        return sp.csr_matrix((v, self._colidx_sorted.copy(), self._rowptr_csr.copy()),
+                             shape=(self.pa.N, self.pa.N))
 
 
 # ---------------------------------------------------------------------------

@@ -39,6 +39,9 @@ struct sb_band_solver {
   int32_t kl, ku, ldab;
   int32_t batch;
   int32_t n_refine;    /* iterative-refinement steps with double-double residual */
+  int32_t n_ruiz;      /* equilibration sweeps */
+  double* rmax;        /* [n * batch] scratch of the equilibration */
+  double* cmax;
   int64_t* rowptr;     /* device */
   int32_t* colidx;     /* device */
   int32_t* perm;       /* device: new index of each dof */
@@ -90,6 +93,43 @@ __global__ void k_band_colmax(int64_t n, const int64_t* rowptr, const int32_t* c
     const double s = rs[sys * n + r];
     for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
       atomic_max_pos_b(&cs[sys * n + colidx[k]], fabs(v[k]) * s);
+  }
+}
+
+/* Ruiz equilibration (iterated: r_i /= sqrt(max_j |a_ij|), c_j /= sqrt(max_i |a_ij|) of the
+ * current scaled matrix).  One row pass followed by one column pass is not enough for the
+ * Newton matrices of wide-gap devices: a continuity row mixes O(1) divergence entries with
+ * generation entries ~ carrier density (1e-26 um^-3 for minority carriers at a 2 eV gap), and
+ * the weakly determined minority quasi-Fermi modes then come out as noise of size 1e9 eV.
+ * A few sweeps balance rows and columns simultaneously -- the job MUMPS' MC64 scaling does in
+ * the reference (newton_solver.py:140-142, ICNTL(6) = 5, ICNTL(8) = 77).                    */
+__global__ void k_band_ones(int64_t total, double* rs, double* cs) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) { rs[i] = 1.0; cs[i] = 1.0; }
+}
+__global__ void k_band_ruiz_max(int64_t n, const int64_t* rowptr, const int32_t* colidx,
+                                const double* vals, int64_t vstride, const double* rs,
+                                const double* cs, double* rmax, double* cmax) {
+  const int64_t sys = blockIdx.y;
+  const double* v = vals + sys * vstride;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const double s = rs[sys * n + r];
+    double m = 0.0;
+    for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+      const double a = fabs(v[k]) * s * cs[sys * n + colidx[k]];
+      m = fmax(m, a);
+      atomic_max_pos_b(&cmax[sys * n + colidx[k]], a);
+    }
+    rmax[sys * n + r] = m;
+  }
+}
+__global__ void k_band_ruiz_apply(int64_t total, const double* rmax, const double* cmax,
+                                  double* rs, double* cs) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (rmax[i] > 0.0) rs[i] /= sqrt(rmax[i]);
+    if (cmax[i] > 0.0) cs[i] /= sqrt(cmax[i]);
   }
 }
 
@@ -365,6 +405,9 @@ extern "C" int sb_band_create(int64_t n, const int64_t* h_rowptr, const int32_t*
   if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->rs);
   if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->cs);
   if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->work);
+  if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->rmax);
+  if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->cmax);
+  s->n_ruiz = 8;
   if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->ipiv);
   if (rc == SB_OK) rc = balloc(s, (size_t)batch, &s->info);
   if (rc != SB_OK) { sb_band_destroy(s); return rc; }
@@ -415,9 +458,13 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
 #define GRID2(gx_, ny_) dim3((gx_), (ny_))
 #endif
 #ifndef SB_EMUL_BUILD
-  SBB_LAUNCH(k_band_rowscale, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, d_vals, vstride, s->rs, s->cs);
-  SBB_LAUNCH(k_band_colmax, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, s->colidx, d_vals, vstride, s->rs, s->cs);
-  SBB_LAUNCH(k_band_colscale, gx, 256, 0, st, n, s->cs, n * nsys);
+  SBB_LAUNCH(k_band_ones, gx, 256, 0, st, n * nsys, s->rs, s->cs);
+  for (int it = 0; it < s->n_ruiz; ++it) {
+    BTRY(cudaMemsetAsync(s->cmax, 0, (size_t)n * nsys * sizeof(double), st));
+    SBB_LAUNCH(k_band_ruiz_max, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, s->colidx, d_vals,
+               vstride, s->rs, s->cs, s->rmax, s->cmax);
+    SBB_LAUNCH(k_band_ruiz_apply, gx, 256, 0, st, n * nsys, s->rmax, s->cmax, s->rs, s->cs);
+  }
   SBB_LAUNCH(k_band_fill, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, s->colidx, s->perm, d_vals,
              vstride, d_b, n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work);
   SBB_LAUNCH(k_band_factor_solve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
@@ -435,9 +482,13 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
     snprintf(g_sb_err, sizeof g_sb_err, "emulation build solves one system at a time");
     return SB_ERR_UNSUPPORTED;
   }
-  SBB_LAUNCH(k_band_rowscale, 4u, 64, 0, st, n, s->rowptr, d_vals, vstride, s->rs, s->cs);
-  SBB_LAUNCH(k_band_colmax, 1u, 1, 0, st, n, s->rowptr, s->colidx, d_vals, vstride, s->rs, s->cs);
-  SBB_LAUNCH(k_band_colscale, 4u, 64, 0, st, n, s->cs, n * nsys);
+  SBB_LAUNCH(k_band_ones, 4u, 64, 0, st, n * nsys, s->rs, s->cs);
+  for (int it = 0; it < s->n_ruiz; ++it) {
+    BTRY(cudaMemsetAsync(s->cmax, 0, (size_t)n * nsys * sizeof(double), st));
+    SBB_LAUNCH(k_band_ruiz_max, 1u, 1, 0, st, n, s->rowptr, s->colidx, d_vals, vstride, s->rs,
+               s->cs, s->rmax, s->cmax);
+    SBB_LAUNCH(k_band_ruiz_apply, 4u, 64, 0, st, n * nsys, s->rmax, s->cmax, s->rs, s->cs);
+  }
   SBB_LAUNCH(k_band_fill, 4u, 64, 0, st, n, s->rowptr, s->colidx, s->perm, d_vals, vstride, d_b,
              n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work);
   SBB_LAUNCH(k_band_factor_solve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab,

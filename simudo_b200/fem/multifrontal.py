@@ -125,6 +125,7 @@ class MultifrontalSolver(object):
         self.pa = pa
         self.device = torch.device(device)
         self.n_refine = n_refine
+        self.n_ruiz = 8
         self.N = pa.N
         self._symbolic(pa, leaf_cells)
 
@@ -303,12 +304,19 @@ class MultifrontalSolver(object):
         """Numeric factorisation of the matrix with the stored values ``vals`` [nnz]."""
         N = self.N
         a = vals.abs()
-        rmax = torch.zeros(N, dtype=torch.float64, device=self.device)
-        rmax.scatter_reduce_(0, self.d_row, a, reduce='amax', include_self=True)
-        self.rs = 1.0 / torch.clamp(rmax, min=1e-300)
-        cmax = torch.zeros(N, dtype=torch.float64, device=self.device)
-        cmax.scatter_reduce_(0, self.d_col, a * self.rs[self.d_row], reduce='amax', include_self=True)
-        self.cs = 1.0 / torch.clamp(cmax, min=1e-300)
+        # Ruiz equilibration, a few sweeps (see csrc/band_solver.cu: k_band_ruiz_max): rows
+        # and columns balanced together; one row pass + one column pass leaves the minority
+        # quasi-Fermi modes of wide-gap devices unresolved
+        self.rs = torch.ones(N, dtype=torch.float64, device=self.device)
+        self.cs = torch.ones(N, dtype=torch.float64, device=self.device)
+        for _ in range(self.n_ruiz):
+            s = a * self.rs[self.d_row] * self.cs[self.d_col]
+            rmax = torch.zeros(N, dtype=torch.float64, device=self.device)
+            rmax.scatter_reduce_(0, self.d_row, s, reduce='amax', include_self=True)
+            cmax = torch.zeros(N, dtype=torch.float64, device=self.device)
+            cmax.scatter_reduce_(0, self.d_col, s, reduce='amax', include_self=True)
+            self.rs = self.rs / torch.sqrt(torch.where(rmax > 0, rmax, torch.ones_like(rmax)))
+            self.cs = self.cs / torch.sqrt(torch.where(cmax > 0, cmax, torch.ones_like(cmax)))
         self.fronts.zero_()
         self.fronts.index_add_(0, self.d_dest, vals * self.rs[self.d_row] * self.cs[self.d_col])
         for g in self.groups:

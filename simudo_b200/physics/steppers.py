@@ -42,7 +42,9 @@ class NonequilibriumCoupledStepper(AdaptiveStepper):
     def user_make_solver(self, solution):
         pdd = solution.pdd
         be_extra_careful = not self.get_last_successful(1)
-        solver = NewtonSolver.from_nice_obj(pdd)
+        # the reference hard-wires NewtonSolver (steppers.py:87); `newton_solver_class` lets a
+        # sweep choose one of its other solvers, e.g. NewtonSolverLogDamping
+        solver = (getattr(self, 'newton_solver_class', None) or NewtonSolver).from_nice_obj(pdd)
         solver.parameters.update(
             maximum_iterations=200 if be_extra_careful else 25,
             omega_cb=lambda s: 1.0,

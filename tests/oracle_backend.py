@@ -76,12 +76,20 @@ class OracleBackend(object):
             self.u, self.base_w, self.thmeq, self.phi_opt, self.bc_values, self.natbc)
 
     def solve(self):
-        A = self.oracle.to_scipy(self.vals).tocsc()
-        # equilibrate like the device solver; MUMPS scales too (newton_solver.py:140-142)
-        r = 1.0 / np.maximum(np.abs(A).max(axis=1).toarray().ravel(), 1e-300)
-        A = sp.diags(r) @ A
-        c = 1.0 / np.maximum(np.abs(A).max(axis=0).toarray().ravel(), 1e-300)
-        A = (A @ sp.diags(c)).tocsc()
+        A = self.oracle.to_scipy(self.vals).tocsr()
+        # equilibrate like the device solvers (Ruiz sweeps); MUMPS scales too (MC64,
+        # newton_solver.py:140-142)
+        n = A.shape[0]
+        r, c = np.ones(n), np.ones(n)
+        for _ in range(8):
+            rm = np.abs(A).max(axis=1).toarray().ravel()
+            cm = np.abs(A).max(axis=0).toarray().ravel()
+            rr = 1.0 / np.sqrt(np.where(rm > 0, rm, 1.0))
+            cc = 1.0 / np.sqrt(np.where(cm > 0, cm, 1.0))
+            A = (sp.diags(rr) @ A @ sp.diags(cc)).tocsr()
+            r *= rr
+            c *= cc
+        A = A.tocsc()
         lu = spla.splu(A)
         x = c * lu.solve(r * self.b)
         # two refinement steps with an extended-precision residual, like the device
