@@ -118,7 +118,7 @@ class MultifrontalSolver(object):
     """``solve(vals, b) -> x`` for the CSR Jacobian of ``pa`` (patterns with contiguous rows:
     'structural', 'native', 'dolfin')."""
 
-    def __init__(self, pa, device, leaf_cells=16, n_refine=2):
+    def __init__(self, pa, device, leaf_cells=16, n_refine=3):
         if pa.csr.pattern == 'bsr3':
             raise ValueError('the multifrontal solver takes a CSR value layout '
                              "('structural', 'native' or 'dolfin')")
