@@ -86,6 +86,10 @@ def parse_args():
     ap.add_argument('--no-solve', action='store_true',
                     help='skip the separately timed Newton linear solve (configs[2], 2D pn diode)')
     ap.add_argument('--no-weak', action='store_true', help='N > 1: skip the weak-scaling measurement')
+    ap.add_argument('--no-sweep', action='store_true',
+                    help='skip the J-V sweep ensemble (second half of the BASELINE metric)')
+    ap.add_argument('--sweep-members', type=int, default=8)
+    ap.add_argument('--sweep-bias-points', type=int, default=6)
     return ap.parse_args()
 
 
@@ -236,6 +240,19 @@ def solve_timing():
                 factor_ms=r['factor_ms'], solve_ms=r['solve_ms'], ms=r['factor_ms'] + r['solve_ms'],
                 assemble_ms=r['assemble_ms'], newton_wall_s=r['wall_s'],
                 J_mA_cm2=r['J_mA_cm2'], fronts=r.get('fronts'))
+
+
+def sweep_timing(args, dist):
+    """J-V sweep wall time (BASELINE metric, second half; configs[4] at reduced size): an
+    ensemble of four-layer IB cells (device-parameter variants, fourlayer.py:233-284), each a
+    light ramp + bias continuation with self-consistent optics, dealt to the ranks, up to 8
+    chains in flight per GPU (threads + streams), no data-path collective.  The same members
+    at every N, so wall_s(1) / wall_s(N) is the sweep's strong scaling."""
+    from simudo_b200.example import ibsc_ensemble
+    try:
+        return ibsc_ensemble.run(args.sweep_members, args.sweep_bias_points, in_flight=8, dist=dist)
+    except Exception as e:                      # a failed chain must not lose the assembly numbers
+        return dict(error='%s: %s' % (type(e).__name__, e))
 
 
 def run_b200(args):
@@ -419,6 +436,9 @@ def run_b200(args):
         del vals
         torch.cuda.empty_cache()
         solve = solve_timing()
+    sweep = None
+    if not args.no_sweep:
+        sweep = sweep_timing(args, dist if world > 1 else None)
     if rank == 0:
         pattern_txt = {'structural': 'structural non-zeros of the dolfin cell blocks, CSR, ascending columns',
                        'native': 'structural non-zeros of the dolfin cell blocks, CSR, columns in emission order',
@@ -477,6 +497,8 @@ def run_b200(args):
             line['cpu_baseline'] = cpu
         if solve is not None:
             line['solve'] = solve
+        if sweep is not None:
+            line['sweep'] = sweep
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

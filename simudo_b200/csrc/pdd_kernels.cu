@@ -1196,14 +1196,28 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
 
 /* The tables are shared __constant__ state: plans of one device must be used from one
  * stream at a time (the copy is stream-ordered on the caller's stream).              */
+static SbTables g_bound_tables[SB_MAX_DEVICES];
+static sb_model g_bound_model[SB_MAX_DEVICES];
+static bool g_bound_valid[SB_MAX_DEVICES] = {false};
+
 static int bind_tables(sb_plan* pl, cudaStream_t s) {
   const int slot = current_device_slot();
   if (g_tables_owner[slot] == pl) return SB_OK;
+  /* another plan with the same tables and model (the members of a sweep ensemble): nothing to
+     copy, and no kernel of a concurrent stream ever sees the constants change */
+  if (g_bound_valid[slot] && memcmp(&g_bound_tables[slot], &pl->tables, sizeof(SbTables)) == 0 &&
+      memcmp(&g_bound_model[slot], &pl->model, sizeof(sb_model)) == 0) {
+    g_tables_owner[slot] = pl;
+    return SB_OK;
+  }
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_T, &pl->tables, sizeof(SbTables), 0,
                                    cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_M, &pl->model, sizeof(sb_model), 0,
                                    cudaMemcpyHostToDevice, s));
   g_tables_owner[slot] = pl;
+  g_bound_tables[slot] = pl->tables;
+  g_bound_model[slot] = pl->model;
+  g_bound_valid[slot] = true;
   return SB_OK;
 }
 

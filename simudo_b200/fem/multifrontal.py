@@ -125,7 +125,7 @@ class MultifrontalSolver(object):
         self.pa = pa
         self.device = torch.device(device)
         self.n_refine = n_refine
-        self.n_ruiz = 8
+        self.n_ruiz = 5          # sweeps over all non-zeros: the cost of the scaling grows with this
         self.N = pa.N
         self._symbolic(pa, leaf_cells)
 
@@ -326,7 +326,9 @@ class MultifrontalSolver(object):
             if ne == 0:
                 S = F
             else:
-                LU, piv = torch.linalg.lu_factor(F[:, :ne, :ne])
+                # _ex: no host synchronisation for the error check (a singular front shows up
+                # as a non-finite solution, checked once per solve)
+                LU, piv, _ = torch.linalg.lu_factor_ex(F[:, :ne, :ne], check_errors=False)
                 g['LU'], g['piv'] = LU, piv
                 if nb:
                     X = torch.linalg.lu_solve(LU, piv, F[:, :ne, ne:])

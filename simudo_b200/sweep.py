@@ -16,15 +16,39 @@ from .parallel import shard_round_robin
 __all__ = ['run_ensemble']
 
 
-def run_ensemble(members, run_member, dist=None):
+def _run_in_flight(items, fn, in_flight):
+    """Run ``fn(item)`` for every item with up to ``in_flight`` of them at a time, each in its
+    own thread and CUDA stream: one continuation chain is a sequence of small launches with a
+    host decision after each Newton iteration, so a single chain leaves the GPU mostly idle;
+    several chains interleave (ctypes and torch release the GIL while the device works)."""
+    if in_flight <= 1 or len(items) <= 1:
+        return [fn(x) for x in items]
+    import concurrent.futures as cf
+    import torch
+
+    def worker(x):
+        if torch.cuda.is_available():
+            with torch.cuda.stream(torch.cuda.Stream()):
+                r = fn(x)
+                torch.cuda.current_stream().synchronize()
+                return r
+        return fn(x)
+    with cf.ThreadPoolExecutor(max_workers=in_flight) as ex:
+        return list(ex.map(worker, items))
+
+
+def run_ensemble(members, run_member, dist=None, in_flight=1):
     """``members``: list of parameter dicts; ``run_member(params) -> result``
-    (e.g. a list of (V, J)).  Returns ``(results, timings)`` on every rank:
+    (e.g. a list of (V, J)).  Members are dealt round-robin to the ranks (one process per
+    GPU); a rank keeps ``in_flight`` of its members going at once (BASELINE config 5: 8
+    devices per GPU in flight).  Returns ``(results, timings)`` on every rank:
     ``results[i]`` is member i's result, ``timings[r]`` the wall time of rank r."""
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     mine = shard_round_robin(len(members), rank, world)
     t0 = time.perf_counter()
-    local = {i: run_member(members[i]) for i in mine}
+    out = _run_in_flight([members[i] for i in mine], run_member, in_flight)
+    local = dict(zip(mine, out))
     dt = time.perf_counter() - t0
     if world == 1:
         return [local[i] for i in range(len(members))], [dt]
