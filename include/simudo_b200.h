@@ -178,6 +178,13 @@ int64_t sb_plan_nnz(const sb_plan* plan);
  * pattern, columns of a row in emission order), Dirichlet dofs on boundary facets only.
  * Any other numbering / pattern handed to sb_plan_create runs the generic kernels.      */
 int sb_plan_is_native(const sb_plan* plan);
+/* Which instance of the generation kernel (a6: electro_optical_process.py:141-157,294-312,
+ * 420-431,482-492,516-536) a native plan runs: 0 = the process list is interpreted per
+ * quadrature point; 1 = the list of the four-layer IB cell (bands CB, IB, VB; opt_ci, opt_iv,
+ * opt_cv, nr_top, nr_bottom: example/fourlayer/fourlayer.py:537-564) and 2 = the pn diode with
+ * SRH (example/pn_diode/pn_diode.py:161-164) are compiled as straight-line code.  Same
+ * arithmetic either way (SIMUDO_B200_GEN_INTERPRET=1 at plan creation forces 0).          */
+int sb_plan_generation_signature(const sb_plan* plan);
 /* materialise the CSR column indices (int32) on the device: for export/solvers */
 int sb_plan_column_indices(sb_plan* plan, int32_t* d_colidx, void* stream);
 

@@ -228,7 +228,7 @@ k_moments_nat(PlanDev pl, StateDev st, int nblk) {
 }
 
 /* ---- phase B, native: thread = cell ---------------------------------------------------- */
-template <int NB>
+template <int NB, class MV = sb_model>
 __global__ void __launch_bounds__(SB_TILE, SB_MB_GEN)
 k_generation_nat(PlanDev pl, StateDev st) {
   const int64_t c = (int64_t)blockIdx.x * SB_TILE + threadIdx.x;
@@ -257,8 +257,15 @@ k_generation_nat(PlanDev pl, StateDev st) {
   }
   if (!any_inside) return;                        /* nobody reads this cell's g moments */
   double mG[NB > 0 ? NB : 1][SB_NG];
-  sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k, st.thmeq ? st.thmeq + c * 6 : nullptr,
-                    st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG, true);
+  /* MV: the model's process list as a type (static lists, pdd_device.cuh) or the interpreter */
+  if constexpr (std::is_same<MV, sb_model>::value) {
+    sb_phaseB_all<NB>(c_T, c_M, tp, dgv, w0, inside_k, st.thmeq ? st.thmeq + c * 6 : nullptr,
+                      st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG, true);
+  } else {
+    const MV mv{c_M};
+    sb_phaseB_all<NB>(c_T, mv, tp, dgv, w0, inside_k, st.thmeq ? st.thmeq + c * 6 : nullptr,
+                      st.phi_opt ? st.phi_opt + c * 6 : nullptr, pl.n_cells * 6, mG, true);
+  }
   const int64_t nc = pl.n_cells;
 #pragma unroll
   for (int k = 0; k < NB; ++k) {
@@ -324,7 +331,8 @@ __device__ __forceinline__ void sb_nat_flux_part(
     const PlanDev& pl, const StateDev& st, double* __restrict__ vals, double* __restrict__ b,
     const SbNatMeta& meta, double* wst, double* stg, double* stg16, int lane, int64_t cc,
     bool active, bool bulk, int32_t finfo, const int32_t* fid, const SbCellGeom& g,
-    const double* fl, const double* sl, bool inside, int64_t g0, int64_t dof0, int grp) {
+    const double* fl, const double* sl, bool inside, int64_t g0, int64_t dof0, int grp,
+    double w0, const int32_t* nbr /* staged: base_w and the 3 neighbours of this cell */) {
   constexpr int P = NB + 1;
   constexpr int RDG = 12 + 3 * P;
   constexpr int RI = PS == 0 ? 15 : 18;
@@ -342,12 +350,11 @@ __device__ __forceinline__ void sb_nat_flux_part(
     if (inside) {
 #pragma unroll
       for (int e = 0; e < 21; ++e) W[e] = ob[(int64_t)(SB_NAT_W + e) * SB_NQS];
-      const double w0 = st.base_w[(int64_t)kb * nc + cc];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         if (f != grp) continue;
         if ((finfo >> (12 + 4 * f + kb)) & 1) {
-          const int64_t cn = pl.cell_neighbors[cc * 3 + f];
+          const int64_t cn = nbr[f];
           const double ref_out = (f == 1) ? -1.0 : 1.0;
           jumpf[f] = (st.base_w[(int64_t)kb * nc + cn] - w0) * ref_out * g.sdet;
         }
@@ -394,7 +401,7 @@ __device__ __forceinline__ void sb_nat_flux_part(
 #pragma unroll
       for (int t = 0; t < 6; ++t) S[t] = sa_base[(int64_t)(6 * grp + t) * SB_NQS];
       if (bits == 0) {                            /* interior facet, this cell is its first cell */
-        const int64_t cn = pl.cell_neighbors[cc * 3 + grp];
+        const int64_t cn = nbr[grp];
         const int f2 = (finfo >> (4 * grp + 2)) & 3;
         const double* sn = (PS == 0) ? natS0_ptr(pl, cn)
                                      : natA_ptr(pl, kb, cn) + (int64_t)SB_NAT_S * SB_NQS;
@@ -503,9 +510,103 @@ __device__ __forceinline__ void sb_nat_flux_part(
   }
 }
 
+/* ---- staged inputs of one 32-cell tile ---------------------------------------------------
+ * Everything whose address is a function of the cell index alone is copied global -> shared
+ * with cp.async TWO tiles ahead (no register is held while the copy is in flight); ONE tile
+ * ahead, when the facet ids and neighbours of that tile have landed, the lines the tile will
+ * load through them (facet dofs of u, facet row bases, neighbour base_w and (facet, facet)
+ * blocks) and the tile's own moment block are prefetched into L2.  The thread-per-cell
+ * kernel spent 62 % of its warp time on long-scoreboard stalls, four to five dependent DRAM
+ * round trips per tile (profiles/r2_s2_hot_lines.txt); now the chain is shared memory -> one
+ * round of L2 hits.                                                                        */
+#define SB_NIN_VERTS 0            /* double [32][6]                                        */
+#define SB_NIN_UCELL 1536         /* double [32][6]: DG + interior dofs of sub-problem PS  */
+#define SB_NIN_W0 3072            /* double [32]: base_w of band PS - 1                    */
+#define SB_NIN_FID 3328           /* int32 [32][3]                                         */
+#define SB_NIN_NBR 3712           /* int32 [32][3]                                         */
+#define SB_NIN_FINFO 4096         /* int32 [32]                                            */
+#define SB_NIN_SPECIAL 4224       /* int32 [32]                                            */
+#define SB_NIN_TAG 4352           /* int32 [32]                                            */
+#define SB_NIN_BYTES 4480
+#define SB_NIN_STAGES 3
+
+template <int P, int PS>
+__device__ __forceinline__ void sb_nat_fetch(const PlanDev& pl, const StateDev& st,
+                                             unsigned char* buf, int64_t tile, int tid) {
+  constexpr int kb = PS > 0 ? PS - 1 : 0;
+  const int64_t c0 = tile * 32, nc = pl.n_cells;
+  if (tid < 96) {                                 /* 3 pieces per cell */
+    const int i = tid / 3, part = tid - 3 * i;
+    const int64_t cs = c0 + i < nc ? c0 + i : nc - 1;      /* ragged last tile: a valid cell */
+    sb_cp_async16(buf + SB_NIN_VERTS + tid * 16, pl.cell_vertices + cs * 6 + part * 2);
+    sb_cp_async4(buf + SB_NIN_FID + tid * 4, pl.nat_fid + cs * 3 + part);
+    sb_cp_async4(buf + SB_NIN_NBR + tid * 4, pl.cell_neighbors + cs * 3 + part);
+    const int32_t* src = part == 0 ? pl.nat_finfo : (part == 1 ? pl.cell_special : pl.cell_tag);
+    sb_cp_async4(buf + SB_NIN_FINFO + part * 128 + i * 4, src + cs);
+  } else if (PS > 0) {
+    const int i = tid - 96;
+    const int64_t cs = c0 + i < nc ? c0 + i : nc - 1;
+    sb_cp_async8(buf + SB_NIN_W0 + i * 8, st.base_w + (int64_t)kb * nc + cs);
+  }
+  for (int q = tid; q < 192; q += SB_TILE) {
+    const int i = q / 6, k = q - 6 * i;
+    const int64_t cs = c0 + i < nc ? c0 + i : nc - 1;
+    sb_cp_async8(buf + SB_NIN_UCELL + q * 8, st.u + (int64_t)6 * P * cs + 6 * PS + k);
+  }
+}
+
+/* L2 prefetch of what tile `tile` (its staged inputs are in `in`) will load with plain loads */
+template <int NB, int PS>
+__device__ __forceinline__ void sb_nat_prefetch(const PlanDev& pl, const StateDev& st,
+                                                const unsigned char* in, int64_t tile,
+                                                int role, int lane) {
+  constexpr int P = NB + 1;
+  constexpr int kb = PS > 0 ? PS - 1 : 0;
+  const int64_t nc = pl.n_cells;
+#ifdef SB_EXP_NOPF_DEP
+  if (false) {
+#else
+  if (role < 3) {
+#endif
+    const int32_t fd = reinterpret_cast<const int32_t*>(in + SB_NIN_FID)[lane * 3 + role];
+    const int32_t cn = reinterpret_cast<const int32_t*>(in + SB_NIN_NBR)[lane * 3 + role];
+    const int32_t finfo = reinterpret_cast<const int32_t*>(in + SB_NIN_FINFO)[lane];
+    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * P * fd + 3 * PS;
+    sb_prefetch_l2(uf);
+    sb_prefetch_l2(uf + 2);                       /* 24 bytes may straddle a line */
+    sb_prefetch_l2(pl.nat_fbase + fd);
+    if (cn >= 0) {
+      if (PS > 0) sb_prefetch_l2(st.base_w + (int64_t)kb * nc + cn);
+      if (((finfo >> (4 * role)) & 3) == 0) {     /* this cell writes the shared block */
+        const int f2 = (finfo >> (4 * role + 2)) & 3;
+        const double* sn = (PS == 0) ? natS0_ptr(pl, cn)
+                                     : natA_ptr(pl, kb, cn) + (int64_t)SB_NAT_S * SB_NQS;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) sb_prefetch_l2(sn + (int64_t)(6 * f2 + t) * SB_NQS);
+      }
+    }
+#ifdef SB_EXP_NOPF_BULK
+  } else if (false) {
+#else
+  } else if (role == 3 && lane == 0) {            /* the tile's own moment blocks: contiguous */
+#endif
+    const int64_t c0 = tile * 32;
+    if (PS > 0) {
+      sb_prefetch_l2_bulk(natA_ptr(pl, kb, c0), SB_NAT_NA * 32 * 8);
+      sb_prefetch_l2_bulk(natG_ptr(pl, kb, c0), (9 + 6 * NB) * 32 * 8);
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < NB; ++kk)
+        sb_prefetch_l2_bulk(natA_ptr(pl, kk, c0) + (int64_t)SB_NAT_RX * SB_NQS,
+                            (SB_NRX + SB_NR) * 32 * 8);
+      sb_prefetch_l2_bulk(natS0_ptr(pl, c0), 18 * 32 * 8);
+    }
+  }
+}
+
 template <int NB, int PS, int LAY>
 __global__ void __launch_bounds__(SB_TILE, (LAY == 2 ? SB_MB_ROWS_BSR : SB_MB_ROWS))
-k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restrict__ b) {
+k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restrict__ b, int ntile) {
 #ifdef SB_EMUL_BUILD
   unsigned char* s_dyn = emul::dyn_smem();
 #else
@@ -526,26 +627,45 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   double* wst = reinterpret_cast<double*>(s_dyn) +
                 (LAY == 2 ? (size_t)warp * 32 * SB_NAT_FSTR : (size_t)warp * 32 * STR);
   SbNatMeta& meta = reinterpret_cast<SbNatMeta*>(s_dyn + sizeof(double) * 32 * STR * (SB_TILE / 32))[warp];
+  unsigned char* s_in = s_dyn + (LAY == 2 ? sizeof(double) * 32 * (3 * SB_NAT_FSTR + STR)
+                                          : (sizeof(double) * 32 * STR + sizeof(SbNatMeta)) * (SB_TILE / 32));
   double* stg = wst + lane * lstr;                /* this lane's slot                   */
   double* stg16 = stg + (lane & 1);               /* 16-byte aligned (odd strides)      */
   const int64_t nc = pl.n_cells;
   /* a CTA = 32 cells x 4 warps; warp `role` 0..2 emits the rows of facet `role`, warp 3 the
      DG and interior rows: four short, independent instruction streams per cell tile
-     instead of one long one -- every warp issues all of its loads up front and pays one
-     memory latency, not one per row group                                              */
+     instead of one long one.  The CTA is persistent: tiles blockIdx.x, + gridDim.x, ... */
   const int role = warp;
-  /* (an L2 prefetch of the inputs of the tile 444 / 888 CTAs ahead was measured 5 % slower:
-     the row kernels are limited by memory throughput, not by the latency of the first loads) */
-  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t G = gridDim.x;
+  int64_t tile = blockIdx.x;
+  if (tile >= ntile) return;
+  sb_nat_fetch<P, PS>(pl, st, s_in, tile, threadIdx.x);
+  if (tile + G < ntile) sb_nat_fetch<P, PS>(pl, st, s_in + SB_NIN_BYTES, tile + G, threadIdx.x);
+  sb_cp_async_commit();
+  for (int it = 0; tile < ntile; tile += G, ++it) {
+  sb_cp_async_wait_all();                         /* tiles `tile` and `tile + G` have landed ... */
+  __syncthreads();                                /* ... for every thread; tile - G is consumed  */
+  const unsigned char* in = s_in + (it % SB_NIN_STAGES) * SB_NIN_BYTES;
+  if (tile + G < ntile) {
+    sb_nat_prefetch<NB, PS>(pl, st, s_in + ((it + 1) % SB_NIN_STAGES) * SB_NIN_BYTES, tile + G,
+                            role, lane);
+    if (tile + 2 * G < ntile)
+      sb_nat_fetch<P, PS>(pl, st, s_in + ((it + 2) % SB_NIN_STAGES) * SB_NIN_BYTES, tile + 2 * G,
+                          threadIdx.x);
+    sb_cp_async_commit();
+  }
+  const int64_t c = tile * 32 + lane;
   const int64_t cc = c < nc ? c : nc - 1;
-  const bool active = (c < nc) && (pl.cell_special[cc] < 0);
-  const int32_t finfo = pl.nat_finfo[cc];
+  const bool active = (c < nc) && (reinterpret_cast<const int32_t*>(in + SB_NIN_SPECIAL)[lane] < 0);
+  const int32_t finfo = reinterpret_cast<const int32_t*>(in + SB_NIN_FINFO)[lane];
   const bool inside = (PS == 0) ? true : (((finfo >> (24 + kb)) & 1) != 0);
+  const int32_t* nbr = reinterpret_cast<const int32_t*>(in + SB_NIN_NBR) + lane * 3;
+  const double w0c = reinterpret_cast<const double*>(in + SB_NIN_W0)[lane];
   int32_t fid[3];
 #pragma unroll
-  for (int f = 0; f < 3; ++f) fid[f] = pl.nat_fid[cc * 3 + f];
-  const SbCellGeom g = sb_geom(pl.cell_vertices + cc * 6);
-  const double* uc = st.u + (int64_t)6 * P * cc + 6 * PS;
+  for (int f = 0; f < 3; ++f) fid[f] = reinterpret_cast<const int32_t*>(in + SB_NIN_FID)[lane * 3 + f];
+  const SbCellGeom g = sb_geom(reinterpret_cast<const double*>(in + SB_NIN_VERTS) + lane * 6);
+  const double* uc = reinterpret_cast<const double*>(in + SB_NIN_UCELL) + lane * 6;
   double fl[12], sl[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { sl[i] = uc[i]; fl[9 + i] = uc[3 + i]; }
@@ -575,6 +695,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   if (role == 3) {
     const int ph = (int)(g0 & 1);
     double* sd = stg16 + ph;
+    sb_bulk_wait_read();                          /* the previous tile's copy has left the slot */
     /* staging index of (row i, position k of the row): see SB_NAT_IDX */
 #define SB_NAT_DGIDX(i, k) (LAY == 2 ? ((k) / 3) * 9 + 3 * (i) + (k) % 3 : (i) * RDG + (k))
     double F[3] = {0.0, 0.0, 0.0};
@@ -596,7 +717,8 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
 #pragma unroll
           for (int t = 0; t < SB_NR; ++t) mom[t] += o[(int64_t)(SB_NAT_R + t) * SB_NQS];
         }
-        const double* tp = pl.tag_params + (int64_t)pl.cell_tag[cc] * SB_TAG_STRIDE;
+        const double* tp = pl.tag_params +
+            (int64_t)reinterpret_cast<const int32_t*>(in + SB_NIN_TAG)[lane] * SB_TAG_STRIDE;
         mom[0] += tp[SB_TP_RHO_STATIC] / tp[SB_TP_EPS] * 0.70710678118654752440;
         coef = -g.adet;
       } else {
@@ -660,17 +782,43 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
    * (A per-lane branch between the two would keep both operand sets live: spills.)       */
   if (PS == 0) {
     sb_nat_flux_part<NB, PS, 0, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                finfo, fid, g, fl, sl, true, g0, dof0, role);
+                                finfo, fid, g, fl, sl, true, g0, dof0, role, w0c, nbr);
   } else {
     const bool any_in = __any_sync(0xffffffffu, inside && active);
     if (any_in)
       sb_nat_flux_part<NB, PS, 1, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                  finfo, fid, g, fl, sl, inside, g0, dof0, role);
+                                  finfo, fid, g, fl, sl, inside, g0, dof0, role, w0c, nbr);
     else
       sb_nat_flux_part<NB, PS, 2, LAY>(pl, st, vals, b, meta, wst, stg, stg16, lane, cc, active, bulk,
-                                  finfo, fid, g, fl, sl, false, g0, dof0, role);
+                                  finfo, fid, g, fl, sl, false, g0, dof0, role, w0c, nbr);
   }
+  }                                               /* tile loop */
   sb_bulk_wait_read();                            /* the slot may be reused once it was read */
+}
+
+/* Grid of a persistent row kernel: as many CTAs as are resident at once (occupancy x SMs of
+ * the current device; looked up once per kernel and device), capped by the number of tiles. */
+static unsigned nat_rows_grid(const void* fn, size_t smem, int ntile) {
+#ifdef SB_EMUL_BUILD
+  (void)fn; (void)smem;
+  return (unsigned)(ntile < 3 ? ntile : 3);       /* several tiles per CTA + a ragged tail */
+#else
+  struct Entry { const void* fn; int dev; int resident; };
+  static std::vector<Entry> cache;
+  static std::mutex mtx;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mtx);
+  for (const Entry& e : cache)
+    if (e.fn == fn && e.dev == dev) return (unsigned)(ntile < e.resident ? ntile : e.resident);
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SB_TILE, smem);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+  cache.push_back({fn, dev, resident});
+  return (unsigned)(ntile < resident ? ntile : resident);
+#endif
 }
 
 /* launch k_rows_nat<NB, PS> for PS = NB .. 0 */
@@ -678,15 +826,17 @@ template <int NB, int PS>
 struct NatRowsLauncher {
   static void go(const PlanDev& d, const StateDev& sd, double* vals, double* b, unsigned nblk,
                  cudaStream_t s) {
-    const size_t smem = (sizeof(double) * 32 * SB_NAT_STR(NB + 1) + sizeof(SbNatMeta)) * (SB_TILE / 32);
-    const unsigned ntile = (unsigned)((d.n_cells + 31) / 32);    /* 32 cells per CTA */
+    const size_t smem = (sizeof(double) * 32 * SB_NAT_STR(NB + 1) + sizeof(SbNatMeta)) * (SB_TILE / 32)
+                        + SB_NIN_STAGES * SB_NIN_BYTES;
+    const int ntile = (int)((d.n_cells + 31) / 32);               /* 32 cells per tile */
     if (d.native == 2) {
-      const size_t smem2 = sizeof(double) * 32 * (3 * SB_NAT_FSTR + SB_NAT_STR(NB + 1));
-      cudaFuncSetAttribute(k_rows_nat<NB, PS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      SB_LAUNCH((k_rows_nat<NB, PS, 2>), ntile, SB_TILE, smem2, s, d, sd, vals, b);
+      const size_t smem2 = sizeof(double) * 32 * (3 * SB_NAT_FSTR + SB_NAT_STR(NB + 1))
+                           + SB_NIN_STAGES * SB_NIN_BYTES;
+      const unsigned grid = nat_rows_grid((const void*)k_rows_nat<NB, PS, 2>, smem2, ntile);
+      SB_LAUNCH((k_rows_nat<NB, PS, 2>), grid, SB_TILE, smem2, s, d, sd, vals, b, ntile);
     } else {
-      cudaFuncSetAttribute(k_rows_nat<NB, PS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      SB_LAUNCH((k_rows_nat<NB, PS, 1>), ntile, SB_TILE, smem, s, d, sd, vals, b);
+      const unsigned grid = nat_rows_grid((const void*)k_rows_nat<NB, PS, 1>, smem, ntile);
+      SB_LAUNCH((k_rows_nat<NB, PS, 1>), grid, SB_TILE, smem, s, d, sd, vals, b, ntile);
     }
     NatRowsLauncher<NB, PS - 1>::go(d, sd, vals, b, nblk, s);
   }

@@ -422,6 +422,66 @@ SB_HD void sb_phaseA_band(const SbRule& R, bool do_rho_, bool do_dd_, const SbBa
  * is warp-uniform).  Dynamically indexed thread-local arrays put the first
  * version of this kernel at 5.6 GB of local-memory traffic per 320 k cells.
  * ------------------------------------------------------------------------- */
+/* ---- static process lists ---------------------------------------------------------------- *
+ * The process list of a model is data, but a handful of lists cover the shipped device models
+ * (four-layer IB cell: fourlayer.py:537-564; pn diode with SRH: pn_diode.py:161-164).  For
+ * those the generation kernel is instantiated with the list as a type: SbCList<...>::operator[]
+ * folds to a literal once the process loop is unrolled, so sb_pick / sb_bump / sb_gen_sign and
+ * the kind dispatch disappear and the processes of a point become one straight-line block
+ * (the interpreter was ~35 % of the kernel's issue slots, profiles/r2_s2_hot_lines.txt).
+ * Any other list runs the interpreter (MV = sb_model).                                      */
+template <int... V>
+struct SbCList {
+  SB_HD constexpr int operator[](int i) const {
+    constexpr int v[sizeof...(V)] = {V...};
+    return v[i];
+  }
+};
+template <class MV> struct SbModelTraits { static constexpr int unroll_procs = 1; };
+SB_HD const sb_model& sb_dyn(const sb_model& M) { return M; }
+/* four-layer IB cell: bands CB (-), IB (-), VB (+); opt_ci, opt_iv, opt_cv, nr_top, nr_bottom */
+struct SbSigIB5 {
+  const sb_model& dyn;
+  static constexpr int n_procs = 5, n_fields = 3;
+  SbCList<SB_BAND_NONDEGENERATE, SB_BAND_INTERMEDIATE, SB_BAND_NONDEGENERATE> band_kind;
+  SbCList<-1, -1, 1> band_sign;
+  SbCList<SB_PROC_RAD_IB, SB_PROC_RAD_IB, SB_PROC_RAD_BB, SB_PROC_SR_TRAP, SB_PROC_SR_TRAP> proc_kind;
+  SbCList<0, 1, 0, 0, 1> proc_dst;
+  SbCList<1, 2, 2, 1, 2> proc_src;
+  SbCList<1, 1, -1, 1, 1> proc_trap;
+  SbCList<1, 1, 1, 1, 1> proc_radiative;
+};
+/* pn diode: bands CB (-), VB (+); SRH */
+struct SbSigPnSRH {
+  const sb_model& dyn;
+  static constexpr int n_procs = 1, n_fields = 0;
+  SbCList<SB_BAND_NONDEGENERATE, SB_BAND_NONDEGENERATE> band_kind;
+  SbCList<-1, 1> band_sign;
+  SbCList<SB_PROC_SRH> proc_kind;
+  SbCList<0> proc_dst;
+  SbCList<1> proc_src;
+  SbCList<-1> proc_trap;
+  SbCList<1> proc_radiative;
+};
+template <> struct SbModelTraits<SbSigIB5> { static constexpr int unroll_procs = 8; };
+template <> struct SbModelTraits<SbSigPnSRH> { static constexpr int unroll_procs = 8; };
+SB_HD const sb_model& sb_dyn(const SbSigIB5& M) { return M.dyn; }
+SB_HD const sb_model& sb_dyn(const SbSigPnSRH& M) { return M.dyn; }
+/* host: does `m` have the list of signature S? */
+template <class S>
+static inline bool sb_sig_matches(const sb_model& m, int nb) {
+  const sb_model dummy = m;
+  const S sg{dummy};
+  if (m.n_bands != nb || m.n_procs != S::n_procs || m.n_fields != S::n_fields) return false;
+  for (int l = 0; l < nb; ++l)
+    if (m.band_kind[l] != sg.band_kind[l] || m.band_sign[l] != sg.band_sign[l]) return false;
+  for (int p = 0; p < S::n_procs; ++p)
+    if (m.proc_kind[p] != sg.proc_kind[p] || m.proc_dst[p] != sg.proc_dst[p] ||
+        m.proc_src[p] != sg.proc_src[p] || m.proc_trap[p] != sg.proc_trap[p] ||
+        (m.proc_radiative[p] != 0) != (sg.proc_radiative[p] != 0)) return false;
+  return true;
+}
+
 template <int NB>
 SB_HD double sb_pick(const double* a, int i) {
   double v = a[0];
@@ -444,7 +504,8 @@ struct SbBandsAtPoint {
   int trap;
 };
 
-SB_HD int sb_gen_sign(const sb_model& M, int p, int k) {
+template <class MV>
+SB_HD int sb_gen_sign(const MV& M, int p, int k) {
   if (k == M.proc_dst[p]) return +1;
   if (k == M.proc_src[p]) return -(M.band_sign[M.proc_dst[p]] * M.band_sign[M.proc_src[p]]);
   return 0;
@@ -452,8 +513,8 @@ SB_HD int sb_gen_sign(const sb_model& M, int p, int k) {
 
 /* Shockley-Read kernel G = expm1(x) u_R F c and its partials
  * (electro_optical_process.py:294-312), hand-derived.                     */
-template <int NB>
-SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff, double beta,
+template <int NB, class MV>
+SB_HD void sb_sr_trap(const MV& M, const double* tp, int p, double coeff, double beta,
                       const SbBandsAtPoint<NB>& B, double& g, double& dphi, double* dw) {
   const int IB = M.proc_trap[p];
   const int RB = (M.proc_dst[p] == IB) ? M.proc_src[p] : M.proc_dst[p];
@@ -480,8 +541,8 @@ SB_HD void sb_sr_trap(const sb_model& M, const double* tp, int p, double coeff, 
 /* One process at one point: G_p (positive = the destination band gains
  * carriers) and its partials w.r.t. phi and every w_l.  Band k then receives
  * sign(p, k) * G_p (TwoBandEOPMixin, electro_optical_process.py:193-205).    */
-template <int NB>
-SB_HD void sb_process_point(const sb_model& M, const double* tp, int p, double beta,
+template <int NB, class MV>
+SB_HD void sb_process_point(const MV& M, const double* tp, int p, double beta,
                             const SbBandsAtPoint<NB>& B, const double* phi_clip,
                             double& g, double& dphi, double* dw) {
   g = 0.0; dphi = 0.0;
@@ -536,9 +597,12 @@ SB_HD void sb_process_point(const sb_model& M, const double* tp, int p, double b
 }
 
 /* which processes need what, hoisted out of the point loop */
-SB_HD void sb_phaseB_scan(const sb_model& M, bool& need_u0, int& trap) {
+template <class MV>
+SB_HD void sb_phaseB_scan(const MV& M, bool& need_u0, int& trap) {
   need_u0 = false;
   trap = -1;
+  constexpr int unroll_procs = SbModelTraits<MV>::unroll_procs;
+#pragma unroll unroll_procs
   for (int p = 0; p < M.n_procs; ++p) {
     need_u0 = need_u0 || (M.proc_kind[p] == SB_PROC_SRH);
     if (trap < 0 && (M.proc_kind[p] == SB_PROC_SR_TRAP ||
@@ -550,8 +614,8 @@ SB_HD void sb_phaseB_scan(const sb_model& M, bool& need_u0, int& trap) {
 /* Point n of the g-rule: totals per band gk[k] = g_k, dphik[k] = dg_k/dphi,
  * dwk[k * NB + l] = dg_k/dw_l.  dgv[3 p + i]: P1 nodal values of (phi | delta_w_l);
  * w0[l]: base_w of the cell; K[l]: band constants.                                */
-template <int NB>
-SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* tp, int n,
+template <int NB, class MV>
+SB_HD void sb_phaseB_point(const SbTables& T, const MV& M, const double* tp, int n,
                            const double* dgv, const double* w0, const SbBandK* K,
                            bool need_u0, int trap, double beta_pt,
                            const double* thmeq6, const double* phi_opt, int64_t field_stride,
@@ -603,7 +667,8 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
 #pragma unroll
     for (int l = 0; l < NB; ++l) dwk[k * NB + l] = 0.0;
   }
-#pragma unroll 1
+  constexpr int unroll_procs = SbModelTraits<MV>::unroll_procs;
+#pragma unroll unroll_procs
   for (int p = 0; p < M.n_procs; ++p) {
     if (!((pmask >> p) & 1u)) continue;         /* process switched off in this cell's region */
     double g, dphi, dw[NB > 0 ? NB : 1];
@@ -624,8 +689,8 @@ SB_HD void sb_phaseB_point(const SbTables& T, const sb_model& M, const double* t
  * band's density and each process are evaluated once.  dgv[p][3]: P1 nodal
  * values of (phi | delta_w_l); w0[l]: base_w of the cell.
  * out mG[k][.]: [0..2] g (P1), [3..8] d/dphi (P2), [9+6l ..] d/dw_l (P2).       */
-template <int NB>
-SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
+template <int NB, class MV>
+SB_HD void sb_phaseB_all(const SbTables& T, const MV& M, const double* tp,
                          const double (*dgv)[3], const double* w0, const bool* inside,
                          const double* thmeq6, const double* phi_opt, int64_t field_stride,
                          double (*mG)[SB_NG], bool region_mask = false) {
@@ -645,6 +710,8 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   if (region_mask) {
     pmask = 0u;
     bool any_trap = false;
+    constexpr int unroll_procs = SbModelTraits<MV>::unroll_procs;
+#pragma unroll unroll_procs
     for (int p = 0; p < M.n_procs; ++p) {
       const double* pp = tp + SB_TP_PROC0 + 8 * p;
       bool on = (M.proc_kind[p] == SB_PROC_SRH) || pp[SB_TPP_P0] != 0.0;
@@ -660,7 +727,7 @@ SB_HD void sb_phaseB_all(const SbTables& T, const sb_model& M, const double* tp,
   }
   const double beta_pt = 1.0 / tp[SB_TP_KT];
 #pragma unroll
-  for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(M, tp, l);
+  for (int l = 0; l < NB; ++l) K[l] = sb_band_consts(sb_dyn(M), tp, l);
 #ifndef SB_GEN_UNROLL
 #define SB_GEN_UNROLL 1
 #endif
@@ -1199,6 +1266,59 @@ SB_HD void sb_bulk_store_owned(double* gdst, const double* stg, int phase, int n
 SB_HD void sb_bulk_wait_read() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+
+/* ---- asynchronous input staging of the persistent row kernels (native.inl) ---------------- *
+ * cp.async (LDGSTS): global -> shared copies that occupy no register while in flight, one
+ * group per cell tile; L2 prefetches for what the next tile will load with plain loads.    */
+SB_HD void sb_cp_async4(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+               :: "r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 4);
+#endif
+}
+SB_HD void sb_cp_async8(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+               :: "r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 8);
+#endif
+}
+SB_HD void sb_cp_async16(void* sdst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               :: "r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+#else
+  memcpy(sdst, gsrc, 16);
+#endif
+}
+SB_HD void sb_cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+SB_HD void sb_cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+SB_HD void sb_prefetch_l2(const void* g) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(g));
+#else
+  (void)g;
+#endif
+}
+/* one instruction for a contiguous block (1-D TMA prefetch): g 16-byte aligned, bytes % 16 == 0 */
+SB_HD void sb_prefetch_l2_bulk(const void* g, uint32_t bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(g), "r"(bytes) : "memory");
+#else
+  (void)g; (void)bytes;
 #endif
 }
 

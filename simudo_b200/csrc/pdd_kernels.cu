@@ -21,6 +21,8 @@
 #include <vector>
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <type_traits>
 
 #define SB_TILE 128                /* threads (= cells) per CTA */
 #include "pdd_device.cuh"
@@ -109,6 +111,7 @@ struct sb_plan {
   cudaEvent_t evs[3] = {nullptr, nullptr, nullptr};  /* after moments, generation, fast rows */
 #endif
   int profiling = 0;
+  int gen_sig = 0;               /* 0: interpret the process list; 1: SbSigIB5; 2: SbSigPnSRH */
 };
 
 struct StateDev {
@@ -983,6 +986,9 @@ extern "C" int64_t sb_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t sb_tables_size(void) { return (int64_t)sizeof(SbTables); }
 extern "C" int64_t sb_plan_nnz(const sb_plan* p) { return p ? p->d.nnz : -1; }
 extern "C" int sb_plan_is_native(const sb_plan* p) { return p ? p->d.native : 0; }
+extern "C" int sb_plan_generation_signature(const sb_plan* p) {
+  return (p && p->d.native) ? p->gen_sig : 0;
+}
 
 extern "C" void sb_plan_destroy(sb_plan* pl) {
   if (!pl) return;
@@ -1015,6 +1021,13 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   }
   sb_plan* pl = new sb_plan();
   pl->model = *model;
+  /* process list known as a type?  (static lists, pdd_device.cuh; SIMUDO_B200_GEN_INTERPRET=1
+     forces the interpreter: the parity tests run both) */
+  pl->gen_sig = 0;
+  if (!getenv("SIMUDO_B200_GEN_INTERPRET")) {
+    if (sb_sig_matches<SbSigIB5>(*model, 3)) pl->gen_sig = 1;
+    else if (sb_sig_matches<SbSigPnSRH>(*model, 2)) pl->gen_sig = 2;
+  }
   memcpy(&pl->tables, pr->h_tables, sizeof(SbTables));
   const int L = 15 * pr->P;
   const int64_t nc = pr->n_cells, N = pr->n_dofs;
@@ -1276,7 +1289,12 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
 #endif
 #define SB_NAT_CASE(NBV)                                                                      \
     case NBV:                                                                                 \
-      SB_LAUNCH(k_generation_nat<NBV>, nblk, SB_TILE, 0, s, d, sd);                           \
+      if (NBV == 3 && pl->gen_sig == 1)                                                       \
+        SB_LAUNCH((k_generation_nat<3, SbSigIB5>), nblk, SB_TILE, 0, s, d, sd);                \
+      else if (NBV == 2 && pl->gen_sig == 2)                                                  \
+        SB_LAUNCH((k_generation_nat<2, SbSigPnSRH>), nblk, SB_TILE, 0, s, d, sd);              \
+      else                                                                                    \
+        SB_LAUNCH(k_generation_nat<NBV>, nblk, SB_TILE, 0, s, d, sd);                         \
       rec_stage_event(pl, 1, s);                                                              \
       NatRowsLauncher<NBV, NBV>::go(d, sd, d_vals, d_b, nblk, s);                             \
       rec_stage_event(pl, 2, s);                                                              \

@@ -188,5 +188,9 @@ class AssemblyPlan(object):
         """True when the plan runs the closed-form kernels (csrc/native.inl)."""
         return bool(self.lib.sb_plan_is_native(self._h))
 
+    def generation_signature(self):
+        """0: the process list is interpreted; 1 / 2: compiled-in list (IB cell / pn + SRH)."""
+        return int(self.lib.sb_plan_generation_signature(self._h))
+
     def launch_count(self):
         return int(self.lib.sb_launch_count())

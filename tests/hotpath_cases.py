@@ -61,6 +61,38 @@ def assembly_parity(maker, nx, ny, numbering='b200', with_bcs=True, **kw):
     return pa, st, plan, vals, b, vals0, b0
 
 
+def generation_signature_matches_interpreter():
+    """The compiled-in process lists (sb_plan_generation_signature 1: IB cell, 2: pn + SRH)
+    against the oracle and against the interpreted list of the same model."""
+    import os
+    for maker, nx, ny, want in ((syn.ib_problem, 9, 4, 1), (syn.pn_problem, 9, 4, 2)):
+        pa = maker(nx=nx, ny=ny, pattern='bsr3')
+        st = syn.synthetic_state(pa)
+        vals0, b0 = _oracle(pa, st)
+        plan = AssemblyPlan(pa)
+        assert plan.is_native() and plan.generation_signature() == want
+        vals, b = (x.cpu().numpy() for x in run_plan(plan, st))
+        os.environ['SIMUDO_B200_GEN_INTERPRET'] = '1'
+        try:
+            plan_i = AssemblyPlan(pa)
+        finally:
+            del os.environ['SIMUDO_B200_GEN_INTERPRET']
+        assert plan_i.generation_signature() == 0
+        vals_i, b_i = (x.cpu().numpy() for x in run_plan(plan_i, st))
+        for v, bb in ((vals, b), (vals_i, b_i)):
+            assert row_scaled_error(pa, v, vals0) < A_TOL and vector_error(bb, b0) < B_TOL
+        assert row_scaled_error(pa, vals, vals_i) < 1e-13
+    # a list that is not compiled in (the IB cell without the band-to-band process) is interpreted
+    pa = syn.ib_problem(nx=6, ny=3, pattern='bsr3')
+    pa.model.n_procs = 2
+    plan = AssemblyPlan(pa)
+    assert plan.is_native() and plan.generation_signature() == 0
+    st = syn.synthetic_state(pa)
+    vals0, b0 = _oracle(pa, st)
+    vals, b = (x.cpu().numpy() for x in run_plan(plan, st))
+    assert row_scaled_error(pa, vals, vals0) < A_TOL and vector_error(b, b0) < B_TOL
+
+
 def assembly_parity_at_scale(nx, ny):
     """The benchmarked configuration (bench.py: IB cell, nx x ny points, BCs on) against the
     oracle: what small cases cannot see -- 64-bit value offsets past 2^31, full grids, the

@@ -17,9 +17,18 @@ from simudo_b200 import synthetic as syn
     (syn.ib_problem, 6, 3, 'b200', True, 'dolfin'),
     (syn.ib_problem, 5, 2, 'ufc', False, 'structural'),
     (syn.pn_problem, 34, 3, 'b200', True, 'structural'),   # > 1 CTA, ragged last CTA
+    # closed-form kernels (csrc/native.inl): CSR 'native' and block CSR 'bsr3'
+    (syn.ib_problem, 6, 3, 'b200', True, 'native'),
+    (syn.ib_problem, 6, 3, 'b200', True, 'bsr3'),
+    (syn.pn_problem, 36, 4, 'b200', True, 'bsr3'),         # several tiles, ragged last tile
+    (syn.ib_problem, 5, 2, 'b200', False, 'bsr3'),
 ])
 def test_assembly_parity_emulated(emulated_lib, maker, nx, ny, numbering, bcs, pattern):
     hc.assembly_parity(maker, nx, ny, numbering=numbering, with_bcs=bcs, pattern=pattern)
+
+
+def test_generation_signature_emulated(emulated_lib):
+    hc.generation_signature_matches_interpreter()
 
 
 def test_thermal_equilibrium_mode_emulated(emulated_lib):

@@ -64,6 +64,10 @@ def test_assembly_parity_at_bench_scale():
     assert cells > 2 * (n - 1) ** 2 - 1
 
 
+def test_generation_signature():
+    hc.generation_signature_matches_interpreter()
+
+
 def test_thermal_equilibrium_mode():
     hc.thermal_equilibrium_mode()
 
