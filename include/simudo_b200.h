@@ -237,6 +237,26 @@ int sb_surface_flux(sb_plan* plan, const double* d_u, int32_t p,
                     const int8_t* d_facet_local, const double* d_facet_sign,
                     double* d_out, void* stream);
 
+/* ---- point evaluation / line cuts ----------------------------------------
+ * Replaces Function_eval_many (simudo/fem/extra_bindings.py:27-75), the evaluator behind
+ * LineCutCsvPlot (simudo/io/csv.py:54-63): for every point the first cell containing it
+ * (here: the containing cell with the lowest index, found through a uniform bin grid built
+ * once per mesh), then the value of a sub-function there.  sub_problem p, what = 0: the DG1
+ * scalar (phi, delta_w_k) -> d_values[n]; what = 1: the BDM2 vector (E, j_k) -> d_values[n][2].
+ * A point outside the mesh is skipped like in the reference (its value slot is left
+ * untouched) and d_cell (optional, [n]) receives -1.
+ * h_cell_vertices: the array handed to sb_plan_create; nbx, nby <= 0: chosen automatically;
+ * h_dubiner_mono [6][6]: monomial matrix of the orthonormal Dubiner P2 basis
+ * (simudo_b200/fem/reference_element.py: _dubiner_p2_monomial_matrix).  The device tables
+ * of a locator are released with its plan.                                          */
+typedef struct sb_locator sb_locator;
+int  sb_locator_create(sb_plan* plan, const double* h_cell_vertices, int32_t nbx, int32_t nby,
+                       const double* h_dubiner_mono, sb_locator** out);
+void sb_locator_destroy(sb_locator* loc);
+int  sb_eval_points(sb_locator* loc, const double* d_u, int32_t sub_problem, int32_t what,
+                    int64_t n_points, const double* d_xy, double* d_values, int32_t* d_cell,
+                    void* stream);
+
 /* ---- Newton linear solve ------------------------------------------------------------
  * Replaces PETScLUSolver("mumps").solve(A, Qdu, b) (simudo/fem/newton_solver.py:
  * 124-181) for product meshes that are thin in y: banded LU with partial pivoting

@@ -20,7 +20,7 @@ _EMULATED = False
 
 EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_launch_count', 'sb_assemble', 'sb_plan_zero_values', 'sb_plan_nnz',
-            'sb_plan_is_native', 'sb_plan_generation_signature', 'sb_measure_fp64_peak',
+            'sb_plan_is_native', 'sb_plan_generation_signature', 'sb_locator_create', 'sb_locator_destroy', 'sb_eval_points', 'sb_measure_fp64_peak',
             'sb_plan_column_indices', 'sb_natbc_eval', 'sb_rebase_w', 'sb_newton_update', 'sb_newton_update_damped',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
             'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
@@ -75,6 +75,12 @@ def _declare(lib):
     lib.sb_plan_is_native.restype = C.c_int
     lib.sb_plan_generation_signature.argtypes = [vp]
     lib.sb_plan_generation_signature.restype = C.c_int
+    lib.sb_locator_create.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, C.POINTER(vp)]
+    lib.sb_locator_create.restype = C.c_int
+    lib.sb_locator_destroy.argtypes = [vp]
+    lib.sb_locator_destroy.restype = None
+    lib.sb_eval_points.argtypes = [vp, vp, C.c_int32, C.c_int32, i64, vp, vp, vp, vp]
+    lib.sb_eval_points.restype = C.c_int
     lib.sb_assemble.argtypes = [vp, C.POINTER(SbState), vp, vp, vp]
     lib.sb_assemble.restype = C.c_int
     lib.sb_plan_zero_values.argtypes = [vp, vp, vp]

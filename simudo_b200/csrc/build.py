@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, 'libsimudo_b200.so')
 SOURCES = ['pdd_kernels.cu', 'band_solver.cu']
-DEPS = SOURCES + ["native.inl", 'pdd_device.cuh', 'pdd_tables.h', 'optics.inl', 'lcn.inl', '../../include/simudo_b200.h']
+DEPS = SOURCES + ["native.inl", 'pdd_device.cuh', 'pdd_tables.h', 'optics.inl', 'lcn.inl', 'points.inl', '../../include/simudo_b200.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -6,8 +6,10 @@
  * simudo/fem/newton_solver.py:61-77; forms poisson_drift_diffusion1.py1:42-47,264-303),
  * for problems whose dof numbering and CSR layout are the library's own:
  *
- *   numbering 'b200'  cell c owns dofs 6P c + 6p + (0..2 DG1 | 3..5 interior BDM2); facet
- *                     f owns dofs 6P Nc + 3P f + 3p + k            (fem/dofmap.py)
+ *   numbering 'b200'  sub-problem major: cell c owns dofs 6 Nc p + 6 c + (0..2 DG1 | 3..5
+ *                     interior BDM2); facet f owns dofs 6P Nc + 3 Nf p + 3 f + k
+ *                     (fem/dofmap.py) -- with values stored in row order, everything the row
+ *                     kernel of sub-problem p writes is one dense range of vals
  *   pattern 'native'  structural non-zeros only, the columns of a row in the emission
  *                     order of these kernels (fem/dofmap.py: _native_ranks_of_row):
  *                       DG1 row        [BDM(p) 0..11 | DG(q) q = 0..P-1]
@@ -123,10 +125,11 @@ k_moments_nat(PlanDev pl, StateDev st, int nblk) {
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
   const SbBandK K = sb_band_consts(c_M, tp, k);
   const bool dd = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
-  const double* uc = st.u + (int64_t)6 * P * c;
+  const double* uc = st.u + (int64_t)6 * c;                       /* sub-problem 0 */
+  const double* uk = st.u + (int64_t)6 * nc * (1 + k) + 6 * c;     /* sub-problem 1 + k */
   double phi[3], dw[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { phi[i] = uc[i]; dw[i] = uc[6 * (1 + k) + i]; }
+  for (int i = 0; i < 3; ++i) { phi[i] = uc[i]; dw[i] = uk[i]; }
   const double w0 = st.base_w[(int64_t)k * nc + c];
   double gc[2][6];
   if (dd) {
@@ -138,8 +141,8 @@ k_moments_nat(PlanDev pl, StateDev st, int nblk) {
 #pragma unroll
     for (int m = 0; m < 12; ++m) {
       const double fm = (m < 9)
-          ? st.u[pl.nat_dofF0 + (int64_t)3 * P * pl.nat_fid[c * 3 + m / 3] + 3 * (1 + k) + m % 3]
-          : uc[6 * (1 + k) + 3 + (m - 9)];
+          ? st.u[pl.nat_dofF0 + (int64_t)3 * pl.nat_nf * (1 + k) + 3 * pl.nat_fid[c * 3 + m / 3] + m % 3]
+          : uk[3 + (m - 9)];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -235,7 +238,7 @@ k_generation_nat(PlanDev pl, StateDev st) {
   if (c >= pl.n_cells) return;
   constexpr int P = NB + 1;
   const double* tp = pl.tag_params + (int64_t)pl.cell_tag[c] * SB_TAG_STRIDE;
-  const double* uc = st.u + (int64_t)6 * P * c;
+  const double* uc = st.u + (int64_t)6 * c;
   double dgv[1 + SB_MAX_BANDS][3];
   double w0[SB_MAX_BANDS];
   bool inside_k[SB_MAX_BANDS];
@@ -252,7 +255,7 @@ k_generation_nat(PlanDev pl, StateDev st) {
       inside_k[k] = tp[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0;
       any_inside = any_inside || inside_k[k];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = uc[6 * (1 + k) + i];
+      for (int i = 0; i < 3; ++i) dgv[1 + k][i] = uc[(int64_t)6 * pl.n_cells * (1 + k) + i];
     }
   }
   if (!any_inside) return;                        /* nobody reads this cell's g moments */
@@ -284,10 +287,17 @@ k_generation_nat(PlanDev pl, StateDev st) {
  *   group 1..3: its run in the 3 rows of facet 0..2 (3 + RB entries when it is the facet's
  *            first cell, RB otherwise), staged [row][entry] and flushed by the warp with
  *            lane = entry: one store instruction covers up to two row runs.           */
+/* experiment switch (tools/build_variant.sh -DSB_EXP_NOLOAD): the row kernels without their
+   moment loads, to separate load time from compute and store time */
+#ifdef SB_EXP_NOLOAD
+#define SB_LDQ(x) (1.0 + 1e-3 * (double)lane)
+#else
+#define SB_LDQ(x) (x)
+#endif
 #define SB_NAT_FROW 18                              /* staging slots per facet row */
 #define SB_NAT_FSTR 57                              /* block CSR: staging doubles per lane of a facet warp */
 #ifndef SB_MB_ROWS_BSR
-#define SB_MB_ROWS_BSR 3                            /* CTAs per SM of the block-CSR row kernels */
+#define SB_MB_ROWS_BSR 2                            /* CTAs per SM of the block-CSR row kernels (255 registers: no spills; measured faster than 3 x 168) */
 #endif
 #define SB_NAT_STR(P) ((((3 * (12 + 3 * (P))) > 3 * SB_NAT_FROW ? (3 * (12 + 3 * (P))) : 3 * SB_NAT_FROW) + 2) | 1)
 
@@ -349,7 +359,7 @@ __device__ __forceinline__ void sb_nat_flux_part(
   if (MODE == 1) {
     if (inside) {
 #pragma unroll
-      for (int e = 0; e < 21; ++e) W[e] = ob[(int64_t)(SB_NAT_W + e) * SB_NQS];
+      for (int e = 0; e < 21; ++e) W[e] = SB_LDQ(ob[(int64_t)(SB_NAT_W + e) * SB_NQS]);
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
         if (f != grp) continue;
@@ -384,10 +394,8 @@ __device__ __forceinline__ void sb_nat_flux_part(
        its run in the facet's block row */
     int64_t g1 = g0 + 3 * RDG;
     if (BSR && facet) {
-      const bool bnd = bits & 1;
       const int32_t fd = grp == 0 ? fid[0] : (grp == 1 ? fid[1] : fid[2]);
-      const int rowoff = PS == 0 ? 0 : (bnd ? 45 + 3 * (PS - 1) * 18 : 81 + 3 * (PS - 1) * 33);
-      g1 = pl.nat_fbase[fd] + rowoff + ((bits & 2) ? 3 * (3 + RB) : 0);
+      g1 = pl.nat_fbase[(int64_t)PS * pl.nat_nf + fd] + ((bits & 2) ? 3 * (3 + RB) : 0);
     }
     const int ph = (int)(g1 & 1);
     /* 16-byte phase of the bulk copy; CSR facet runs are flushed by the warp instead */
@@ -399,19 +407,19 @@ __device__ __forceinline__ void sb_nat_flux_part(
     double S[6] = {0, 0, 0, 0, 0, 0}, D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (lead) {
 #pragma unroll
-      for (int t = 0; t < 6; ++t) S[t] = sa_base[(int64_t)(6 * grp + t) * SB_NQS];
+      for (int t = 0; t < 6; ++t) S[t] = SB_LDQ(sa_base[(int64_t)(6 * grp + t) * SB_NQS]);
       if (bits == 0) {                            /* interior facet, this cell is its first cell */
         const int64_t cn = nbr[grp];
         const int f2 = (finfo >> (4 * grp + 2)) & 3;
         const double* sn = (PS == 0) ? natS0_ptr(pl, cn)
                                      : natA_ptr(pl, kb, cn) + (int64_t)SB_NAT_S * SB_NQS;
 #pragma unroll
-        for (int t = 0; t < 6; ++t) S[t] += sn[(int64_t)(6 * f2 + t) * SB_NQS];
+        for (int t = 0; t < 6; ++t) S[t] += SB_LDQ(sn[(int64_t)(6 * f2 + t) * SB_NQS]);
       }
     }
     if (momdrv) {
 #pragma unroll
-      for (int t = 0; t < 9; ++t) D[t] = ob[(int64_t)(SB_NAT_D + 9 * grp + t) * SB_NQS];
+      for (int t = 0; t < 9; ++t) D[t] = SB_LDQ(ob[(int64_t)(SB_NAT_D + 9 * grp + t) * SB_NQS]);
     }
     double F[3] = {0.0, 0.0, 0.0};
     if (active) {
@@ -484,7 +492,7 @@ __device__ __forceinline__ void sb_nat_flux_part(
       if (b) {
         if (facet) {
           const int32_t fd = grp == 0 ? fid[0] : (grp == 1 ? fid[1] : fid[2]);
-          double* bd = b + pl.nat_dofF0 + (int64_t)3 * P * fd + 3 * PS;
+          double* bd = b + pl.nat_dofF0 + (int64_t)3 * pl.nat_nf * PS + 3 * fd;
 #pragma unroll
           for (int k = 0; k < 3; ++k) SB_ATOMIC_ADD(bd + k, F[k]);
         } else {
@@ -551,7 +559,7 @@ __device__ __forceinline__ void sb_nat_fetch(const PlanDev& pl, const StateDev& 
   for (int q = tid; q < 192; q += SB_TILE) {
     const int i = q / 6, k = q - 6 * i;
     const int64_t cs = c0 + i < nc ? c0 + i : nc - 1;
-    sb_cp_async8(buf + SB_NIN_UCELL + q * 8, st.u + (int64_t)6 * P * cs + 6 * PS + k);
+    sb_cp_async8(buf + SB_NIN_UCELL + q * 8, st.u + (int64_t)6 * nc * PS + 6 * cs + k);
   }
 }
 
@@ -571,10 +579,10 @@ __device__ __forceinline__ void sb_nat_prefetch(const PlanDev& pl, const StateDe
     const int32_t fd = reinterpret_cast<const int32_t*>(in + SB_NIN_FID)[lane * 3 + role];
     const int32_t cn = reinterpret_cast<const int32_t*>(in + SB_NIN_NBR)[lane * 3 + role];
     const int32_t finfo = reinterpret_cast<const int32_t*>(in + SB_NIN_FINFO)[lane];
-    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * P * fd + 3 * PS;
+    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * pl.nat_nf * PS + 3 * fd;
     sb_prefetch_l2(uf);
     sb_prefetch_l2(uf + 2);                       /* 24 bytes may straddle a line */
-    sb_prefetch_l2(pl.nat_fbase + fd);
+    sb_prefetch_l2(pl.nat_fbase + (int64_t)PS * pl.nat_nf + fd);
     if (cn >= 0) {
       if (PS > 0) sb_prefetch_l2(st.base_w + (int64_t)kb * nc + cn);
       if (((finfo >> (4 * role)) & 3) == 0) {     /* this cell writes the shared block */
@@ -617,8 +625,8 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   constexpr int RI = PS == 0 ? 15 : 18;           /* interior BDM row length            */
   constexpr int RB = PS == 0 ? 12 : 15;           /* a cell's run in a facet row        */
   constexpr int STR = SB_NAT_STR(P);              /* staging doubles per lane (odd)     */
-  constexpr int CB = 3 * RDG * P + 45 + 54 * (P - 1);   /* owned values per cell        */
-  constexpr int OFF_DG = PS == 0 ? 0 : (3 * RDG + 45) + (PS - 1) * (3 * RDG + 54);
+  constexpr int CBP = 3 * RDG + 3 * RI;           /* owned values per cell and sub-problem */
+  constexpr int OFF_DG = PS == 0 ? 0 : (3 * RDG + 45) + (PS - 1) * (3 * RDG + 54);   /* of the ones before */
   constexpr int kb = PS > 0 ? PS - 1 : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   /* staging: CSR: STR doubles per lane for every warp (+ flush metadata); block CSR: the
@@ -671,7 +679,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
   for (int i = 0; i < 3; ++i) { sl[i] = uc[i]; fl[9 + i] = uc[3 + i]; }
 #pragma unroll
   for (int f = 0; f < 3; ++f) {
-    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * P * fid[f] + 3 * PS;
+    const double* uf = st.u + pl.nat_dofF0 + (int64_t)3 * pl.nat_nf * PS + 3 * fid[f];
 #pragma unroll
     for (int k = 0; k < 3; ++k) fl[3 * f + k] = uf[k];
   }
@@ -682,13 +690,14 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
     const int bits = (finfo >> (4 * f)) & 3;
     const bool bnd = bits & 1, second = bits & 2;
     const int rl = bnd ? (PS == 0 ? 15 : 18) : (PS == 0 ? 27 : 33);
-    const int rowoff = PS == 0 ? 0 : (bnd ? 45 + 3 * (PS - 1) * 18 : 81 + 3 * (PS - 1) * 33);
-    meta.gb[f][lane] = pl.nat_fbase[fid[f]] + rowoff + (second ? 3 + RB : 0);
+    meta.gb[f][lane] = pl.nat_fbase[(int64_t)PS * pl.nat_nf + fid[f]] + (second ? 3 + RB : 0);
     const int n = (active && vals != nullptr) ? (second ? RB : RB + 3) : 0;
     meta.rn[f][lane] = rl | (n << 16);
   }
-  const int64_t g0 = cc * CB + OFF_DG;            /* vals index of the DG block          */
-  const int64_t dof0 = (int64_t)6 * P * cc + 6 * PS;
+  /* vals index of the cell's DG block: the owned rows of sub-problem PS are one dense array
+     [cell][3 RDG + 3 RI] */
+  const int64_t g0 = nc * OFF_DG + cc * CBP;
+  const int64_t dof0 = (int64_t)6 * nc * PS + 6 * cc;
   const bool bulk = active && vals != nullptr;
 
   /* ---- group 0: DG rows ----------------------------------------------------------- */
@@ -710,12 +719,12 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
           const double* o = natA_ptr(pl, kk, cc);
 #pragma unroll
           for (int t = 0; t < SB_NRX; ++t) {
-            const double v = o[(int64_t)(SB_NAT_RX + t) * SB_NQS];
+            const double v = SB_LDQ(o[(int64_t)(SB_NAT_RX + t) * SB_NQS]);
             mom[3 + t] += v;
             mom[3 + 6 * (1 + kk) + t] = v;
           }
 #pragma unroll
-          for (int t = 0; t < SB_NR; ++t) mom[t] += o[(int64_t)(SB_NAT_R + t) * SB_NQS];
+          for (int t = 0; t < SB_NR; ++t) mom[t] += SB_LDQ(o[(int64_t)(SB_NAT_R + t) * SB_NQS]);
         }
         const double* tp = pl.tag_params +
             (int64_t)reinterpret_cast<const int32_t*>(in + SB_NIN_TAG)[lane] * SB_TAG_STRIDE;
@@ -724,7 +733,7 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
       } else {
         const double* og = natG_ptr(pl, kb, cc);
 #pragma unroll
-        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = og[(int64_t)t * SB_NQS];
+        for (int t = 0; t < 9 + 6 * NB; ++t) mom[t] = SB_LDQ(og[(int64_t)t * SB_NQS]);
         coef = -(double)c_M.band_sign[kb] * c_M.e_charge * g.adet;
       }
       if (active) {
@@ -853,7 +862,7 @@ struct NatRowsLauncher<NB, -1> {
  * within its triple.                                                                     */
 static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
                           std::vector<int32_t>& fid, std::vector<int32_t>& finfo,
-                          std::vector<int64_t>& fbase, int64_t* dofF0) {
+                          std::vector<int64_t>& fbase, int64_t* dofF0, int64_t* n_facets) {
   const int P = pr->P, L = 15 * P;
   const int64_t nc = pr->n_cells, N = pr->n_dofs;
   if (!model->bands_have_dofs || P < 2 || getenv("SIMUDO_B200_NO_NATIVE")) return false;
@@ -861,28 +870,27 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
   if (N <= F0 || (N - F0) % (3 * P) != 0) return false;
   const int64_t nf = (N - F0) / (3 * P);
   const int RDG = 12 + 3 * P;
-  const int64_t CB = (int64_t)3 * RDG * P + 45 + 54 * (P - 1);
   const int32_t* cd = pr->h_cell_dofs;
   const int64_t* rp = pr->h_rowptr;
   fid.assign((size_t)nc * 3, -1);
   finfo.assign((size_t)nc, 0);
-  fbase.assign((size_t)nf, -1);
-  /* dof numbering */
+  fbase.assign((size_t)nf * P, -1);
+  /* dof numbering: sub-problem major (fem/dofmap.py 'b200') */
   for (int64_t c = 0; c < nc; ++c) {
     const int32_t* d = cd + c * L;
     for (int f = 0; f < 3; ++f) {
       const int64_t q = (int64_t)d[3 + 3 * f] - F0;
-      if (q < 0 || q % (3 * P) != 0) return false;
-      fid[c * 3 + f] = (int32_t)(q / (3 * P));
+      if (q < 0 || q >= 3 * nf || q % 3 != 0) return false;
+      fid[c * 3 + f] = (int32_t)(q / 3);
     }
     for (int p = 0; p < P; ++p) {
       for (int i = 0; i < 3; ++i) {
-        if (d[15 * p + i] != 6 * P * c + 6 * p + i) return false;
-        if (d[15 * p + 12 + i] != 6 * P * c + 6 * p + 3 + i) return false;
+        if (d[15 * p + i] != 6 * nc * p + 6 * c + i) return false;
+        if (d[15 * p + 12 + i] != 6 * nc * p + 6 * c + 3 + i) return false;
       }
       for (int f = 0; f < 3; ++f)
         for (int k = 0; k < 3; ++k)
-          if (d[15 * p + 3 + 3 * f + k] != F0 + (int64_t)3 * P * fid[c * 3 + f] + 3 * p + k) return false;
+          if (d[15 * p + 3 + 3 * f + k] != F0 + 3 * nf * p + (int64_t)3 * fid[c * 3 + f] + k) return false;
     }
   }
   /* facet sides: first cell = lower index; neighbour's local facet */
@@ -906,30 +914,30 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
       if (tpc[SB_TP_BAND0 + 5 * k + SB_TPB_IN_SUBDOMAIN] != 0.0) info |= 1 << (24 + k);
     finfo[c] = info;
   }
-  /* row pointers */
-  for (int64_t c = 0; c < nc; ++c) {
-    int64_t off = c * CB;
+  /* row pointers: per sub-problem the owned rows [cell][3 DG rows | 3 interior rows], after all
+     of them per sub-problem the facet rows [facet][3 rows] */
+  {
+    int64_t off = 0;
     for (int p = 0; p < P; ++p) {
-      for (int i = 0; i < 3; ++i)
-        if (rp[6 * P * c + 6 * p + i] != off + (bsr ? 3 * i : RDG * i)) return false;
-      off += 3 * RDG;
       const int ri = p == 0 ? 15 : 18;
-      for (int i = 0; i < 3; ++i)
-        if (rp[6 * P * c + 6 * p + 3 + i] != off + (bsr ? 3 * i : ri * i)) return false;
-      off += 3 * ri;
+      for (int64_t c = 0; c < nc; ++c) {
+        for (int i = 0; i < 3; ++i)
+          if (rp[6 * nc * p + 6 * c + i] != off + (bsr ? 3 * i : RDG * i)) return false;
+        off += 3 * RDG;
+        for (int i = 0; i < 3; ++i)
+          if (rp[6 * nc * p + 6 * c + 3 + i] != off + (bsr ? 3 * i : ri * i)) return false;
+        off += 3 * ri;
+      }
     }
-    if (rp[6 * P * (c + 1)] != off) return false;
-  }
-  for (int64_t f = 0; f < nf; ++f) {
-    int64_t off = rp[F0 + 3 * P * f];
-    fbase[f] = off;
-    for (int p = 0; p < P; ++p) {
-      const int rl = fbnd[f] ? (p == 0 ? 15 : 18) : (p == 0 ? 27 : 33);
-      for (int k = 0; k < 3; ++k)
-        if (rp[F0 + 3 * P * f + 3 * p + k] != off + (bsr ? 3 * k : rl * k)) return false;
-      off += 3 * rl;
-    }
-    if (f + 1 < nf ? rp[F0 + 3 * P * (f + 1)] != off : rp[N] != off) return false;
+    for (int p = 0; p < P; ++p)
+      for (int64_t f = 0; f < nf; ++f) {
+        const int rl = fbnd[f] ? (p == 0 ? 15 : 18) : (p == 0 ? 27 : 33);
+        fbase[(size_t)p * nf + f] = off;
+        for (int k = 0; k < 3; ++k)
+          if (rp[F0 + 3 * nf * p + 3 * f + k] != off + (bsr ? 3 * k : rl * k)) return false;
+        off += 3 * rl;
+      }
+    if (rp[N] != off) return false;
   }
   /* rank patterns: once per (pattern id, side bits) */
   std::vector<uint8_t> checked((size_t)pr->n_patterns * 8, 0);
@@ -969,8 +977,9 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
   /* Dirichlet dofs: boundary facets only */
   for (int64_t i = 0; i < pr->n_bc; ++i) {
     const int64_t d = pr->h_bc_dofs[i];
-    if (d < F0 || !fbnd[(d - F0) / (3 * P)]) return false;
+    if (d < F0 || !fbnd[((d - F0) % (3 * nf)) / 3]) return false;
   }
   *dofF0 = F0;
+  *n_facets = nf;
   return true;
 }

@@ -95,8 +95,9 @@ struct PlanDev {
                                     facet's local number inside the neighbour; bits
                                     12 + 4f + k: base_w jump of band k on facet f ('+' side);
                                     bits 24 + k: cell inside the subdomain of band k */
-  const int64_t* nat_fbase;      /* [n_facets] vals index of the facet's row block */
+  const int64_t* nat_fbase;      /* [P][n_facets] vals index of the facet's 3 rows of sub-problem p */
   int64_t nat_dofF0;             /* first facet dof = 6 P n_cells             */
+  int64_t nat_nf;                /* number of facets                          */
 };
 
 struct sb_plan {
@@ -1105,19 +1106,20 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   pl->n_bc = pr->n_bc; pl->n_natbc = pr->n_natbc;
   UP(cell_special, special.data(), nc);
   /* closed-form layout?  (native.inl): 1 = CSR 'native', 2 = block CSR 'bsr3' */
-  d.native = 0; d.nat_fid = nullptr; d.nat_finfo = nullptr; d.nat_fbase = nullptr; d.nat_dofF0 = 0;
+  d.native = 0; d.nat_fid = nullptr; d.nat_finfo = nullptr; d.nat_fbase = nullptr; d.nat_dofF0 = 0; d.nat_nf = 0;
   {
     std::vector<int32_t> fid, finfo;
     std::vector<int64_t> fbase;
-    int64_t F0 = 0;
+    int64_t F0 = 0, nfac = 0;
     int kind = 0;
-    if (rc == SB_OK && detect_native(model, pr, false, fid, finfo, fbase, &F0)) kind = 1;
-    else if (rc == SB_OK && detect_native(model, pr, true, fid, finfo, fbase, &F0)) kind = 2;
+    if (rc == SB_OK && detect_native(model, pr, false, fid, finfo, fbase, &F0, &nfac)) kind = 1;
+    else if (rc == SB_OK && detect_native(model, pr, true, fid, finfo, fbase, &F0, &nfac)) kind = 2;
     if (kind) {
       UP(nat_fid, fid.data(), fid.size());
       UP(nat_finfo, finfo.data(), finfo.size());
       UP(nat_fbase, fbase.data(), fbase.size());
       d.nat_dofF0 = F0;
+      d.nat_nf = nfac;
       d.native = kind;
     }
   }
@@ -1565,5 +1567,6 @@ extern "C" int sb_surface_flux(sb_plan* pl, const double* d_u, int32_t p, int64_
   return SB_OK;
 }
 
+#include "points.inl"
 #include "optics.inl"
 #include "lcn.inl"

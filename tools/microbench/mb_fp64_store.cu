@@ -119,9 +119,11 @@ __global__ void k_store_bulk(double* out, int64_t ncell, int stride) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+static int g_gap = -1;     // >= 0: doubles left unwritten between two runs (0 = dense output)
 template <int RL, int NR>
 static void run_store(int64_t ncell) {
-  const int stride = RL + (RL > 60 ? 55 : 17) + ((RL & 1) ? 0 : 1);   // odd+even mix of phases                      // gaps between runs (other cells' columns)
+  const int stride = g_gap >= 0 ? RL + g_gap
+                                : RL + (RL > 60 ? 55 : 17) + ((RL & 1) ? 0 : 1);   // gaps between runs (other cells' columns)
   const size_t n = (size_t)ncell * NR * stride + 8;
   double* d; CK(cudaMalloc(&d, n * 8)); CK(cudaMemset(d, 0, n * 8));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -169,5 +171,11 @@ int main() {
   run_store<54, 12>(1000000);
   run_store<72, 4>(1000000);        // DG block
   run_store<126, 4>(1000000);       // owned block per sub-problem
+  // the same runs with no gaps (what a sub-problem-major layout gives one launch), and with
+  // the 3 : 1 gaps of the cell-major layout (a launch writes 1/4 of every cell's block)
+  g_gap = 0;
+  run_store<45, 12>(1000000); run_store<72, 4>(1000000); run_store<126, 4>(1000000);
+  g_gap = 369;
+  run_store<126, 4>(1000000);
   return 0;
 }
