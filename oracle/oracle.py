@@ -282,3 +282,38 @@ def surface_flux(pa, u, p, facets):
     sgn = ref_out[l] * np.sign(det[c])
     flux = (u[d] @ np.array([2 / 3, -1 / 3, 2 / 3])) * sgn
     return flux.sum(), mesh.facet_lengths()[facets].sum()
+
+
+def eval_points(pa, u, p, points, vector=False):
+    """Point evaluation of sub-function ``p`` (Function_eval_many,
+    simudo/fem/extra_bindings.py:27-75): brute-force search for the containing cell with the
+    lowest index, then DG1 barycentric interpolation, or the BDM2 basis tabulated from its
+    symbolic definition (fiat_like.tabulate_bdm2) pushed forward by the contravariant Piola
+    map.  Returns (values [n] or [n, 2], cells [n]); points outside the mesh: NaN, -1."""
+    from . import fiat_like
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
+    xv = np.asarray(pa.cell_vertices, dtype=np.float64).reshape(-1, 3, 2)
+    v0 = xv[:, 0, :]
+    J = np.stack([xv[:, 1, :] - v0, xv[:, 2, :] - v0], axis=2)          # [c, xy, XY]
+    det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
+    vals = np.full((len(pts), 2) if vector else (len(pts),), np.nan)
+    cells = np.full(len(pts), -1, dtype=np.int64)
+    cd = np.asarray(pa.cell_dofs, dtype=np.int64)
+    tol = 1e-12
+    for i, (x, y) in enumerate(pts):
+        dx, dy = x - v0[:, 0], y - v0[:, 1]
+        X = (J[:, 1, 1] * dx - J[:, 0, 1] * dy) / det
+        Y = (J[:, 0, 0] * dy - J[:, 1, 0] * dx) / det
+        hit = np.nonzero((X >= -tol) & (Y >= -tol) & (X + Y <= 1 + tol))[0]
+        if not len(hit):
+            continue
+        c = hit[0]
+        cells[i] = c
+        ref = np.array([[X[c], Y[c]]])
+        if not vector:
+            vals[i] = fiat_like.tabulate_p1(ref)[0] @ u[cd[c, 15 * p:15 * p + 3]]
+        else:
+            bv, _ = fiat_like.tabulate_bdm2(ref)                          # [1, 12, 2]
+            hat = u[cd[c, 15 * p + 3:15 * p + 15]] @ bv[0]
+            vals[i] = J[c] @ hat / det[c]
+    return vals, cells

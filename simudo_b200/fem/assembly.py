@@ -9,6 +9,7 @@ provider; every kernel is in ``csrc/``):
 ``rebase_w``        a9       (``mixedqfl_do_rebase_w``, poisson_drift_diffusion1.py1:339-383)
 ``newton_update``   a11      (newton_solver.py:79-122, 306-317, 533-547)
 ``surface_flux``    terminal current (io/output_writer.py:174-231)
+``eval_points``     point evaluation / line cuts (fem/extra_bindings.py:27-75, io/csv.py:54-63)
 """
 import ctypes as C
 
@@ -73,6 +74,13 @@ class AssemblyPlan(object):
 
     def __del__(self):
         h = getattr(self, '_h', None)
+        loc = getattr(self, '_locator', None)
+        if loc:
+            try:
+                self.lib.sb_locator_destroy(loc)
+            except Exception:
+                pass
+            self._locator = None
         if h:
             try:
                 self.lib.sb_plan_destroy(h)
@@ -168,6 +176,30 @@ class AssemblyPlan(object):
             self._h, _p(u), p, int(facet_cell.numel()), _p(facet_cell),
             _p(facet_local), _p(facet_sign), _p(out), self._stream(stream)))
         return out
+
+    def eval_points(self, u, sub_problem, points, vector=False, out=None, stream=None,
+                    return_cells=False):
+        """Values of a sub-function at ``points`` [n, 2] (device tensor or array):
+        ``vector=False`` the DG1 scalar of ``sub_problem`` -> [n]; ``vector=True`` its BDM2
+        vector -> [n, 2].  Points outside the mesh keep the value of ``out`` (NaN when ``out``
+        is not given) -- ``Function_eval_many`` skips them (extra_bindings.py:62-64)."""
+        if getattr(self, '_locator', None) is None:
+            from .reference_element import _dubiner_p2_monomial_matrix
+            mono = np.ascontiguousarray(_dubiner_p2_monomial_matrix(), dtype=np.float64)
+            cv = np.ascontiguousarray(self.pa.cell_vertices, dtype=np.float64)
+            h = C.c_void_p()
+            _lib.check(self.lib.sb_locator_create(self._h, _hp(cv), 0, 0, _hp(mono), C.byref(h)))
+            self._locator = h
+        xy = self.tensor(points).reshape(-1, 2)
+        n = xy.shape[0]
+        if out is None:
+            out = torch.full((n, 2) if vector else (n,), float('nan'), dtype=torch.float64,
+                             device=self.device)
+        cells = torch.empty(n, dtype=torch.int32, device=self.device) if return_cells else None
+        _lib.check(self.lib.sb_eval_points(self._locator, _p(u), int(sub_problem),
+                                           1 if vector else 0, n, _p(xy), _p(out), _p(cells),
+                                           self._stream(stream)))
+        return (out, cells) if return_cells else out
 
     def set_profiling(self, on=True):
         _lib.check(self.lib.sb_plan_set_profiling(self._h, 1 if on else 0))

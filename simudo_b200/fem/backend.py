@@ -161,6 +161,16 @@ class CudaBackend(object):
         return float(out[0]), float(out[1])
 
 
+    def eval_points(self, p, points, vector=False):
+        """Sub-function ``p`` of the current solution at ``points`` [n, 2] -> numpy."""
+        return self.plan.eval_points(self.u, p, points, vector=vector).cpu().numpy()
+
+    def locate_points(self, points):
+        """Index of the containing cell of every point (-1: outside the mesh) -> numpy."""
+        _, cells = self.plan.eval_points(self.u, 0, points, return_cells=True)
+        return cells.cpu().numpy().astype(np.int64)
+
+
 class CudaLCNBackend(object):
     """Device state + ``sb_lcn_iteration`` for the local-charge-neutrality stage
     (``LCNSystem``).  No CPU fallback."""

@@ -5,7 +5,8 @@ The part of ``simudo/io/output_writer.py`` on the J-V path:
 ``MetaCSVWriter`` (:113-135); ``MetaExtractorBandInfo`` (:144-152) and
 ``MetaExtractorIntegrals.add_surface_flux`` (:174-231) giving
 ``avg:current_<band>:<facet region>`` in mA/cm^2 and ``tot:current_...`` in
-mA.  Line cuts / XDMF / YAML+HDF5 are file formats outside the hot path.
+mA.  ``plot_1d`` writes the line cut of the unknowns (``io/csv.py``, :94-101); XDMF /
+YAML+HDF5 are file formats outside the hot path.
 """
 import csv
 import os
@@ -41,6 +42,7 @@ class OutputWriter(SetattrInitMixin):
     parameter_name = 'parameter'
     filename_prefix = 'output'
     meta_extractors = ()
+    line_cut_resolution = 5001
     _meta_csv = None
 
     def __init__(self, **kwargs):
@@ -59,6 +61,13 @@ class OutputWriter(SetattrInitMixin):
             extractor(solution=solution, parameter_value=parameter_value,
                       output_writer=self, meta=meta).call()
         self.rows.append(meta)
+        if self.plot_1d:
+            from .csv import LineCutCsvPlot, solution_line_cut
+            prefix = self.filename_prefix + '_{}={}'.format(
+                self.parameter_name, self.format_parameter(solution, parameter_value))
+            with LineCutCsvPlot(prefix + '.csv', None,
+                                resolution=self.line_cut_resolution) as plotter:
+                solution_line_cut(plotter, solution, 0)
         if self.plot_iv:
             if self._meta_csv is None:
                 self._meta_csv = MetaCSVWriter(

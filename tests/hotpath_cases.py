@@ -93,6 +93,34 @@ def generation_signature_matches_interpreter():
     assert row_scaled_error(pa, vals, vals0) < A_TOL and vector_error(b, b0) < B_TOL
 
 
+def eval_points_parity():
+    """sb_eval_points (Function_eval_many, extra_bindings.py:27-75) against the oracle's
+    brute-force restatement: interior points, points on cell edges and vertices, points
+    outside the mesh, the mid-line cut of LineCutCsvPlot (io/csv.py:30-41)."""
+    pa = syn.ib_problem(nx=11, ny=6, pattern='bsr3')
+    st = syn.synthetic_state(pa)
+    plan = AssemblyPlan(pa)
+    u = plan.tensor(st['u'])
+    rng = np.random.default_rng(7)
+    (x0, y0), (x1, y1) = pa.cell_vertices.reshape(-1, 2).min(0), pa.cell_vertices.reshape(-1, 2).max(0)
+    pts = np.column_stack([rng.uniform(x0, x1, 300), rng.uniform(y0, y1, 300)])
+    t = np.linspace(0, 1, 101)
+    cut = np.column_stack([x0 + t * (x1 - x0), np.full_like(t, 0.5 * (y0 + y1))])
+    verts = pa.cell_vertices.reshape(-1, 2)[::7]
+    outside = np.array([[x0 - 1.0, y0], [x1 + 1e-3, y1], [0.5 * (x0 + x1), y1 + 2.0]])
+    allp = np.concatenate([pts, cut, verts, outside])
+    for p in range(pa.P):
+        for vector in (False, True):
+            ref, cref = orc_mod.eval_points(pa, st['u'], p, allp, vector=vector)
+            got, cg = plan.eval_points(u, p, allp, vector=vector, return_cells=True)
+            got, cg = got.cpu().numpy(), cg.cpu().numpy()
+            assert (cg == cref).all()
+            assert (cg[-3:] == -1).all() and np.isnan(got[-3:]).all()
+            inside = cref >= 0
+            scale = np.abs(ref[inside]).max()
+            assert np.abs(got[inside] - ref[inside]).max() <= 1e-12 * scale
+
+
 def assembly_parity_at_scale(nx, ny):
     """The benchmarked configuration (bench.py: IB cell, nx x ny points, BCs on) against the
     oracle: what small cases cannot see -- 64-bit value offsets past 2^31, full grids, the

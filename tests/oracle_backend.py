@@ -41,6 +41,14 @@ class OracleBackend(object):
     def set_u(self, u):
         self.u = np.array(u, dtype=np.float64)
 
+    def eval_points(self, p, points, vector=False):
+        from oracle import oracle as _orc
+        return _orc.eval_points(self.pa, self.u, p, points, vector=vector)[0]
+
+    def locate_points(self, points):
+        from oracle import oracle as _orc
+        return _orc.eval_points(self.pa, self.u, 0, points)[1]
+
     def set_phi_opt(self, p):
         self.phi_opt = np.array(p, dtype=np.float64)
 

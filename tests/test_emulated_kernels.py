@@ -67,6 +67,10 @@ def test_natbc_eval_emulated(emulated_lib):
     hc.natbc_eval_parity()
 
 
+def test_eval_points_emulated(emulated_lib):
+    hc.eval_points_parity()
+
+
 def test_surface_flux_emulated(emulated_lib):
     hc.surface_flux_parity()
 

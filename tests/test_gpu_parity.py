@@ -104,6 +104,10 @@ def test_natbc_eval():
     hc.natbc_eval_parity()
 
 
+def test_eval_points():
+    hc.eval_points_parity()
+
+
 def test_surface_flux():
     hc.surface_flux_parity()
 

@@ -190,3 +190,28 @@ def test_nonzero_essential_flux_value_is_lowered_and_imposed():
     ft, _ = orc_mod.surface_flux(pa, u, 0, top)
     fb, _ = orc_mod.surface_flux(pa, u, 0, bottom)
     assert abs(ft - 0.5 * Lx) < 1e-12 and abs(fb + 0.5 * Lx) < 1e-12
+
+
+def test_line_cut_csv_of_the_converged_solution(oracle_sweep, tmp_path):
+    """``OutputWriter.plot_1d`` (simudo/io/output_writer.py:94-101, io/csv.py:21-77): the line
+    cut of the unknowns at the last bias point; phi drops by the applied bias + built-in
+    potential across the diode, j_tot is constant along x (steady state, 1D) and equals the
+    terminal current of the J-V table."""
+    from simudo_b200.io.csv import LineCutCsvPlot, solution_line_cut
+    jv, problem, stepper = oracle_sweep
+    prefix = str(tmp_path / 'cut.csv')
+    with LineCutCsvPlot(prefix, None, resolution=401) as plotter:
+        solution_line_cut(plotter, problem, 0)
+    with open(prefix + '.0') as f:
+        names = f.readline().strip().split(',')
+        data = np.array([[float(x) for x in line.split(',')] for line in f])
+    col = {n: data[:, i] for i, n in enumerate(names)}
+    assert data.shape[0] == 401 and names[:2] == ['coord_x', 'coord_y']
+    for k in ('phi', 'E_x', 'E_y', 'j_CB_x', 'j_VB_x', 'w_CB_delta', 'w_VB_base', 'qfl_CB', 'j_tot_x'):
+        assert k in col and np.isfinite(col[k]).all(), k
+    assert np.allclose(col['coord_y'], col['coord_y'][0])
+    # quasi-1D: no transverse field or current
+    assert np.abs(col["E_y"]).max() < 1e-4 * np.abs(col["E_x"]).max()
+    # steady state: total current constant along the device, equal to the terminal current
+    J = jv[-1][1]
+    assert np.abs(np.abs(col['j_tot_x']) - abs(J)).max() < 2e-3 * abs(J)
