@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -51,6 +52,10 @@ struct sb_band_solver {
   double* work;        /* [batch][n] permuted right-hand side / solution */
   int32_t* ipiv;       /* [batch][n] */
   int32_t* info;       /* [batch] first zero pivot + 1, 0 = ok */
+  double* rdiag;       /* [batch][n] reciprocal pivots (window kernels) */
+  double* arow;        /* [batch][n][kl + ku + 1] row-major copy of the scaled band, or null:
+                          the shared-memory window kernels are used when it exists */
+  size_t window_smem;
   std::vector<void*> allocs;
 };
 
@@ -143,10 +148,12 @@ __global__ void k_band_colscale(int64_t n, double* cs, int64_t total) {
 __global__ void k_band_fill(int64_t n, const int64_t* rowptr, const int32_t* colidx,
                             const int32_t* perm, const double* vals, int64_t vstride,
                             const double* b, int64_t bstride, const double* rs, const double* cs,
-                            double* ab, int32_t ldab, int32_t kv, double* work) {
+                            double* ab, int32_t ldab, int32_t kv, double* work,
+                            double* arow /* [n][kv + 1] row-major band copy, or null */, int32_t kl) {
   const int64_t sys = blockIdx.y;
   const double* v = vals + sys * vstride;
   double* A = ab + sys * n * ldab;
+  double* AR = arow ? arow + sys * n * (kv + 1) : nullptr;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
        r += (int64_t)gridDim.x * blockDim.x) {
     const double s = rs[sys * n + r];
@@ -154,7 +161,9 @@ __global__ void k_band_fill(int64_t n, const int64_t* rowptr, const int32_t* col
     for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k) {
       const int32_t c = colidx[k];
       const int64_t pc = perm[c];
-      A[pc * ldab + kv + pr - pc] = v[k] * s * cs[sys * n + c];
+      const double a = v[k] * s * cs[sys * n + c];
+      A[pc * ldab + kv + pr - pc] = a;
+      if (AR) AR[pr * (kv + 1) + (pc - pr + kl)] = a;
     }
     work[sys * n + pr] = b[sys * bstride + r] * s;
   }
@@ -284,6 +293,383 @@ k_band_resolve(int64_t n, int32_t kl, int32_t ku, int32_t ldab, const double* ab
 #undef ABE
 }
 
+/* ---- shared-memory window variants ----------------------------------------------------------
+ * The kernels above walk the band in global memory with one CTA-wide barrier per phase (about
+ * fifteen per column, 1024 threads): measured 224 ms per Newton solve of the quasi-1D IB cell
+ * (27 k unknowns, kl = ku = 62), i.e. the whole J-V sweep was waiting on it.  Same algorithm
+ * (gbtf2: partial pivoting inside the band, multipliers below the diagonal of AB, row
+ * interchanges in ipiv -- the factors are interchangeable), but
+ *  - the active (kl + 1) x (kv + 1) part of the band lives in shared memory as a ring in both
+ *    directions (one spare row and column slot, so the row entering at the next step is stored
+ *    while the current one is still read); it is fed from a row-major copy of the scaled band
+ *    (k_band_fill), SBB_STAGE rows at a time, and finished L columns / U rows stream out to AB;
+ *  - the pivot search is one warp with shuffles; a step has three barriers of a 256-thread CTA;
+ *  - the triangular solves (back substitution here, both sweeps in k_band_resolve_window) run
+ *    in ONE warp over blocks of SBB_TB columns that the whole CTA has loaded into shared memory
+ *    (coalesced, double-buffered): __syncwarp per column instead of __syncthreads.          */
+#ifdef SB_EMUL_BUILD
+#define SBB_WT 128
+static inline int sbb_shfl_down_i(int v, int o) { return (int)__shfl_down_sync(0xffffffffu, (double)v, o); }
+static inline double sbb_shfl_down_d(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+static inline int sbb_shfl_idx_i(int v, int src) {       /* broadcast of lane src (emulation: via the shuffle slots) */
+  auto& c = *emul::g_ctx;
+  const unsigned t = emul::t_tid;
+  c.shfl[t] = (double)v;
+  __syncwarp();
+  const int r = (int)c.shfl[(t / 32) * 32 + src];
+  __syncwarp();
+  return r;
+}
+#else
+#define SBB_WT 512
+__device__ __forceinline__ int sbb_shfl_down_i(int v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ double sbb_shfl_down_d(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ int sbb_shfl_idx_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#endif
+#define SBB_STAGE 16            /* rows of the row-major band staged per refill            */
+#define SBB_TB 32               /* columns per block of the triangular solves              */
+
+/* back substitution U x = y by warp 0 of the CTA (U: bandwidth kv above the diagonal, column j
+ * of U contiguous in AB); blk: shared memory [2][SBB_TB][kv + 1], ring: [kv + 1].           */
+__device__ void sbb_back_substitution(int64_t n, int kv, int ldab, const double* __restrict__ AB,
+                                      double* __restrict__ x, double* blk, double* ring,
+                                      double* xin /* [2][SBB_TB]: entries entering the ring */,
+                                      const double* __restrict__ rdiag /* 1 / U(j, j) */) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int RW = kv + 1;
+  const int64_t nblk = (n + SBB_TB - 1) / SBB_TB;
+  /* block q covers columns j in (hi - SBB_TB, hi], hi = n - 1 - q SBB_TB; column j stored as
+     blk[..][j_local][i] = U(j - i, j), i = 0 .. kv */
+  /* t0, tn: rank and number of the threads that take part in the load */
+  auto load_block = [&](int64_t q, double* dst, int t0, int tn) {
+    const int64_t hi = n - 1 - q * SBB_TB;
+    for (int e = t0; e < SBB_TB * RW; e += tn) {
+      const int jl = e / RW, i = e - jl * RW;
+      const int64_t j = hi - jl;
+      dst[e] = (j >= 0 && i <= j) ? (i == 0 ? rdiag[j] : AB[j * ldab + kv - i]) : 0.0;
+    }
+    /* the entry that enters the ring when column hi - jl retires (already final: y) */
+    for (int e = t0; e < SBB_TB; e += tn) {
+      const int64_t rin = hi - e - kv - 1;
+      xin[(q & 1) * SBB_TB + e] = rin >= 0 ? x[rin] : 0.0;
+    }
+  };
+  load_block(0, blk, tid, nt);
+  for (int e = tid; e < RW; e += nt) { const int64_t r = n - 1 - e; ring[e] = r >= 0 ? x[r] : 0.0; }
+  /* ring slot of row r: (n - 1 - r) mod RW */
+  __syncthreads();
+  int slot = 0;                                   /* slot of row j */
+  for (int64_t q = 0; q < nblk; ++q) {
+    double* cur = blk + (size_t)(q & 1) * SBB_TB * RW;
+    if (warp != 0) {
+      if (q + 1 < nblk) load_block(q + 1, blk + (size_t)((q + 1) & 1) * SBB_TB * RW, tid - 32, nt - 32);
+    } else {
+      const int64_t hi = n - 1 - q * SBB_TB;
+      for (int jl = 0; jl < SBB_TB; ++jl) {
+        const int64_t j = hi - jl;
+        if (j < 0) break;
+        const double* col = cur + jl * RW;
+        const double xj = ring[slot] * col[0];    /* col[0] = 1 / U(j, j) */
+        const int up = (int)(kv < j ? kv : j);
+        __syncwarp();                             /* every lane has read ring[slot] */
+        for (int i = 1 + lane; i <= up; i += 32) {
+          int sl = slot + i; if (sl >= RW) sl -= RW;
+          ring[sl] -= col[i] * xj;
+        }
+        if (lane == 0) {
+          x[j] = xj;
+          ring[slot] = xin[(q & 1) * SBB_TB + jl]; /* row j - kv - 1 enters: takes the slot of row j */
+        }
+        __syncwarp();
+        if (++slot >= RW) slot = 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+/* forward substitution with the stored multipliers and interchanges, same organisation;
+ * blk: [2][SBB_TB][kl + 1] (entry 0 unused), piv: int [2][SBB_TB], ring: [kl + 1]         */
+__device__ void sbb_forward_substitution(int64_t n, int kl, int kv, int ldab,
+                                         const double* __restrict__ AB, const int32_t* __restrict__ ipiv,
+                                         double* __restrict__ x, double* blk, int* piv, double* ring,
+                                         double* xin) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int RW = kl + 1;
+  const int64_t nblk = (n + SBB_TB - 1) / SBB_TB;
+  auto load_block = [&](int64_t q, double* dst, int* pdst, int t0, int tn) {
+    const int64_t lo = q * SBB_TB;
+    for (int e = t0; e < SBB_TB * RW; e += tn) {
+      const int jl = e / RW, i = e - jl * RW;
+      const int64_t j = lo + jl;
+      dst[e] = (j < n && i >= 1 && j + i < n) ? AB[j * ldab + kv + i] : 0.0;
+    }
+    for (int e = t0; e < SBB_TB; e += tn) {
+      pdst[e] = lo + e < n ? (int)(ipiv[lo + e] - (lo + e)) : 0;
+      const int64_t rin = lo + e + kl + 1;          /* untouched right-hand side entry */
+      xin[(q & 1) * SBB_TB + e] = rin < n ? x[rin] : 0.0;
+    }
+  };
+  load_block(0, blk, piv, tid, nt);
+  for (int e = tid; e < RW; e += nt) ring[e] = e < n ? x[e] : 0.0;      /* slot of row r: r mod RW */
+  __syncthreads();
+  int slot = 0;
+  for (int64_t q = 0; q < nblk; ++q) {
+    double* cur = blk + (size_t)(q & 1) * SBB_TB * RW;
+    int* pc = piv + (q & 1) * SBB_TB;
+    if (warp != 0) {
+      if (q + 1 < nblk)
+        load_block(q + 1, blk + (size_t)((q + 1) & 1) * SBB_TB * RW, piv + ((q + 1) & 1) * SBB_TB,
+                   tid - 32, nt - 32);
+    } else {
+      const int64_t lo = q * SBB_TB;
+      for (int jl = 0; jl < SBB_TB; ++jl) {
+        const int64_t j = lo + jl;
+        if (j >= n) break;
+        const double* col = cur + jl * RW;
+        const int jp = pc[jl];
+        if (jp != 0 && lane == 0) {
+          int sp = slot + jp; if (sp >= RW) sp -= RW;
+          const double t = ring[slot]; ring[slot] = ring[sp]; ring[sp] = t;
+        }
+        __syncwarp();
+        const double xj = ring[slot];
+        const int km = (int)(kl < n - 1 - j ? kl : n - 1 - j);
+        __syncwarp();                             /* every lane has read ring[slot] */
+        for (int i = 1 + lane; i <= km; i += 32) {
+          int sl = slot + i; if (sl >= RW) sl -= RW;
+          ring[sl] -= col[i] * xj;
+        }
+        if (lane == 0) {
+          x[j] = xj;
+          ring[slot] = xin[(q & 1) * SBB_TB + jl];
+        }
+        __syncwarp();
+        if (++slot >= RW) slot = 0;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t sbb_window_smem(int kl, int ku) {
+  const size_t kv = (size_t)kl + ku, WR = kl + 2, WC = kv + 2, LD = WR | 1;
+  const size_t fac = WC * LD + WR + (size_t)SBB_STAGE * (kv + 2);
+  const size_t tri = 2 * (size_t)SBB_TB * (kv + 1) + (kv + 1) + SBB_TB + 2 * SBB_TB;   /* ints as doubles */
+  return 8 * (fac > tri ? fac : tri) + 64;
+}
+
+__global__ void __launch_bounds__(SBB_WT)
+k_band_factor_window(int64_t n, int32_t kl, int32_t ku, int32_t ldab, const double* arow_all,
+                     double* ab_all, double* work_all, int32_t* ipiv_all, int32_t* info_all,
+                     double* rdiag_all) {
+#ifdef SB_EMUL_BUILD
+  double* sm = reinterpret_cast<double*>(emul::dyn_smem());
+#else
+  extern __shared__ __align__(16) double sm[];
+#endif
+  const int64_t sys = blockIdx.x;
+  const int kv = kl + ku, WR = kl + 2, WC = kv + 2, RS = kv + 2;
+  const int LD = WR | 1;     /* odd column stride of the window: accesses along a row (the
+                                interchange, the U row, the entering row) hit 32 banks */
+  double* AB = ab_all + sys * n * ldab;
+  const double* AR = arow_all + sys * n * (kv + 1);
+  double* x = work_all + sys * n;
+  int32_t* ipiv = ipiv_all + sys * n;
+  double* S = sm;                                 /* window [WC][LD]: S[(c mod WC) LD + (r mod WR)] */
+  double* xs = S + (size_t)WC * LD;               /* rhs of the window rows [WR]                     */
+  double* stage = xs + WR;                        /* [SBB_STAGE][kv + 2]: band row + its rhs         */
+  __shared__ int s_jp;
+  __shared__ double s_piv, s_rp, s_diag, s_xj, s_xold;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+#define ABE(i, j) AB[(int64_t)(j) * ldab + kv + (i) - (j)]
+  for (int e = tid; e < WC * LD + WR; e += nt) S[e] = 0.0;
+  __syncthreads();
+  /* rows 0 .. kl enter directly */
+  for (int64_t r = 0; r <= kl && r < n; ++r) {
+    for (int t = tid; t <= kv; t += nt) {
+      const int64_t c = r - kl + t;
+      if (c >= 0 && c < n) S[(int)(c % WC) * LD + (int)(r % WR)] = AR[r * (kv + 1) + t];
+    }
+    if (tid == 0) xs[r % WR] = x[r];
+  }
+  /* rows kl + 1 + [0, SBB_STAGE) wait in the staging area */
+  int64_t stage_row0 = kl + 1;
+  for (int e = tid; e < SBB_STAGE * RS; e += nt) {
+    const int q = e / RS, t = e - q * RS;
+    const int64_t r = stage_row0 + q;
+    stage[e] = r < n ? (t <= kv ? AR[r * (kv + 1) + t] : x[r]) : 0.0;
+  }
+  __syncthreads();
+  int jr = 0, jc = 0, ju = 0, info = 0;
+  double* abj = AB + kv;                          /* &ABE(j, j): ABE(j + i, j) = abj[i],
+                                                     ABE(j, j + t) = abj[t (ldab - 1)]      */
+  double* rdiag = rdiag_all + sys * n;            /* 1 / U(j, j) for the triangular solves   */
+  for (int64_t j = 0; j < n; ++j, abj += ldab) {
+    const int km = (int)((kl < n - 1 - j) ? kl : (n - 1 - j));
+    /* phase 1: pivot search over rows j .. j + km of column j, one warp with shuffles */
+    if (warp == 0) {
+      double best = -1.0; int bi = 0;
+      for (int i = lane; i <= km; i += 32) {
+        int rs = jr + i; if (rs >= WR) rs -= WR;
+        const double a = fabs(S[jc * LD + rs]);
+        if (a > best) { best = a; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = sbb_shfl_down_d(best, o);
+        const int oi = sbb_shfl_down_i(bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) {
+        int rsp0 = jr + bi; if (rsp0 >= WR) rsp0 -= WR;
+        const double pv = S[jc * LD + rsp0];
+        s_jp = bi;
+        s_piv = pv;
+        s_rp = 1.0 / pv;
+        s_diag = S[jc * LD + jr];
+        s_xj = xs[rsp0];
+        s_xold = xs[jr];
+        ipiv[j] = (int32_t)(j + bi);
+        rdiag[j] = s_rp;
+      }
+    }
+    __syncthreads();
+    const int jp = s_jp;
+    const double piv = s_piv;
+    {
+      const int64_t cand = j + ku + jp;
+      const int juc = (int)(cand < n - 1 ? cand : n - 1);
+      if (juc > ju) ju = juc;
+    }
+    const bool sing = (piv == 0.0);
+    if (sing && !info) info = (int)(j + 1);
+    int rsp = jr + jp; if (rsp >= WR) rsp -= WR;
+    /* phase 2: multipliers of column j + forward elimination of the rhs (threads over rows);
+       interchange of rows j and j + jp in the columns right of j (threads over columns) */
+    if (!sing) {
+      const double rp = s_rp, xjn = s_xj;
+      for (int i = 1 + tid; i <= km; i += nt) {
+        int rs = jr + i; if (rs >= WR) rs -= WR;
+        const double a = (i == jp) ? s_diag : S[jc * LD + rs];
+        const double l = a * rp;
+        S[jc * LD + rs] = l;
+        const double xi = (i == jp) ? s_xold : xs[rs];
+        xs[rs] = xi - l * xjn;
+      }
+      if (tid == 0) { S[jc * LD + jr] = piv; xs[jr] = xjn; }
+      if (jp != 0) {
+        /* the upper warps take the interchange: the lower ones are busy with the column */
+        for (int cc = nt - 1 - tid; cc < ju - (int)j; cc += nt) {
+          int cs = jc + 1 + cc; if (cs >= WC) cs -= WC;
+          const double t = S[cs * LD + jr];
+          S[cs * LD + jr] = S[cs * LD + rsp];
+          S[cs * LD + rsp] = t;
+        }
+      }
+    }
+    __syncthreads();
+    /* phase 3: trailing update; the finished L column and U row stream out; the row entering
+       at the next step goes to the spare row / column slots */
+    if (!sing) {
+      const int ncol = ju - (int)j;
+      /* a lane keeps the multipliers of its rows in registers (<= 4 rows: kl <= 128) and
+         streams over the columns of its warp */
+      const int nq = (km + 31) >> 5;
+      double lv[4]; int ro[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 1 + lane + 32 * q;
+        int rs = jr + (i <= km ? i : 0); if (rs >= WR) rs -= WR;
+        ro[q] = rs;
+        lv[q] = (q < nq && i <= km) ? S[jc * LD + rs] : 0.0;
+      }
+      /* 4 columns in flight per warp: the shared-memory round trips are the cost */
+      for (int c0 = warp * 4; c0 < ncol; c0 += nwarp * 4) {
+        double* colp[4]; double u[4]; double a[4][4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          int cs = jc + 1 + (c0 + m < ncol ? c0 + m : c0); if (cs >= WC) cs -= WC;
+          colp[m] = S + cs * LD;
+          u[m] = colp[m][jr];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) a[q][m] = colp[m][ro[q]];
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq && 1 + lane + 32 * q <= km) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              if (c0 + m < ncol) colp[m][ro[q]] = a[q][m] - lv[q] * u[m];
+          }
+      }
+    }
+    for (int i = 1 + tid; i <= km; i += nt) {
+      int rs = jr + i; if (rs >= WR) rs -= WR;
+      abj[i] = S[jc * LD + rs];
+    }
+    for (int t = tid; t <= kv && j + t < n; t += nt) {
+      int cs = jc + t; if (cs >= WC) cs -= WC;
+      abj[(int64_t)t * (ldab - 1)] = S[cs * LD + jr];
+    }
+    if (tid == 0) x[j] = xs[jr];
+    {
+      const int64_t r = j + kl + 1;               /* entering row; its columns are j + 1 .. j + kv + 1 */
+      int rspare = jr + kl + 1; if (rspare >= WR) rspare -= WR;
+      int cspare = jc + kv + 1; if (cspare >= WC) cspare -= WC;
+      const double* srow = stage + (int)(r - stage_row0) * RS;
+      /* the spare column slot held a retired column: clear it, then its corner arrives below */
+      for (int e = tid; e < WR; e += nt) if (e != rspare) S[cspare * LD + e] = 0.0;
+      for (int t = tid; t <= kv; t += nt) {
+        int cs = jc + 1 + t; if (cs >= WC) cs -= WC;
+        S[cs * LD + rspare] = (r < n && j + 1 + t < n) ? srow[t] : 0.0;
+      }
+      if (tid == 0) xs[rspare] = r < n ? srow[kv + 1] : 0.0;
+    }
+    __syncthreads();
+    if (j + kl + 1 - stage_row0 == SBB_STAGE - 1) {       /* staging area consumed: refill */
+      stage_row0 += SBB_STAGE;
+      for (int e = tid; e < SBB_STAGE * RS; e += nt) {
+        const int q = e / RS, t = e - q * RS;
+        const int64_t r = stage_row0 + q;
+        stage[e] = r < n ? (t <= kv ? AR[r * (kv + 1) + t] : x[r]) : 0.0;
+      }
+      __syncthreads();
+    }
+    if (++jr >= WR) jr = 0;
+    if (++jc >= WC) jc = 0;
+  }
+#undef ABE
+  if (tid == 0) info_all[sys] = info;
+  __syncthreads();
+  sbb_back_substitution(n, kv, ldab, AB, x, sm, sm + 2 * (size_t)SBB_TB * (kv + 1),
+                        sm + 2 * (size_t)SBB_TB * (kv + 1) + (kv + 1) + SBB_TB, rdiag);
+}
+
+/* forward + back substitution with the stored factors (iterative refinement) */
+__global__ void __launch_bounds__(SBB_WT)
+k_band_resolve_window(int64_t n, int32_t kl, int32_t ku, int32_t ldab, const double* ab_all,
+                      double* work_all, const int32_t* ipiv_all, const double* rdiag_all) {
+#ifdef SB_EMUL_BUILD
+  double* sm = reinterpret_cast<double*>(emul::dyn_smem());
+#else
+  extern __shared__ __align__(16) double sm[];
+#endif
+  const int64_t sys = blockIdx.x;
+  const int kv = kl + ku;
+  const double* AB = ab_all + sys * n * ldab;
+  double* x = work_all + sys * n;
+  double* ring = sm + 2 * (size_t)SBB_TB * (kv + 1);
+  double* xin = ring + (kv + 1) + SBB_TB;
+  sbb_forward_substitution(n, kl, kv, ldab, AB, ipiv_all + sys * n, x, sm,
+                           reinterpret_cast<int*>(ring + kv + 1), ring, xin);
+  __syncthreads();
+  sbb_back_substitution(n, kv, ldab, AB, x, sm, ring, xin, rdiag_all + sys * n);
+}
+
 /* r = b - A x with the row sums accumulated in double-double (error-free
  * products via FMA, TwoSum accumulation); r is written pre-scaled and permuted
  * into the solver's work vector: work[perm[row]] = rs[row] * r[row].
@@ -410,6 +796,22 @@ extern "C" int sb_band_create(int64_t n, const int64_t* h_rowptr, const int32_t*
   s->n_ruiz = 8;
   if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->ipiv);
   if (rc == SB_OK) rc = balloc(s, (size_t)batch, &s->info);
+  /* the window kernels need (kl + 2)(kl + ku + 2) doubles of shared memory (227 KB per CTA on
+     sm_100a); SIMUDO_B200_BAND_GLOBAL=1 keeps the global-memory kernels (tests compare both) */
+  s->arow = nullptr; s->rdiag = nullptr;
+  s->window_smem = sbb_window_smem((int)kl, (int)ku);
+  if (rc == SB_OK && s->window_smem <= 227 * 1024 && kl <= 128 && !getenv("SIMUDO_B200_BAND_GLOBAL")) {
+    rc = balloc(s, (size_t)(n * (kl + ku + 1) * batch), &s->arow);
+    if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->rdiag);
+#ifndef SB_EMUL_BUILD
+    if (rc == SB_OK) {
+      BTRY(cudaFuncSetAttribute(k_band_factor_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)s->window_smem));
+      BTRY(cudaFuncSetAttribute(k_band_resolve_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)s->window_smem));
+    }
+#endif
+  }
   if (rc != SB_OK) { sb_band_destroy(s); return rc; }
   cudaMemcpy(s->rowptr, h_rowptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
   cudaMemcpy(s->colidx, h_colidx, s->nnz * sizeof(int32_t), cudaMemcpyHostToDevice);
@@ -452,6 +854,8 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
   }
 #endif
   BTRY(cudaMemsetAsync(s->ab, 0, (size_t)s->ldab * n * nsys * sizeof(double), st));
+  if (s->arow)
+    BTRY(cudaMemsetAsync(s->arow, 0, (size_t)(s->kl + s->ku + 1) * n * nsys * sizeof(double), st));
 #ifdef SB_EMUL_BUILD
 #define GRID2(gx_, ny_) (gx_)
 #else
@@ -466,15 +870,23 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
     SBB_LAUNCH(k_band_ruiz_apply, gx, 256, 0, st, n * nsys, s->rmax, s->cmax, s->rs, s->cs);
   }
   SBB_LAUNCH(k_band_fill, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, s->colidx, s->perm, d_vals,
-             vstride, d_b, n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work);
-  SBB_LAUNCH(k_band_factor_solve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
-             s->ab, s->work, s->ipiv, s->info);
+             vstride, d_b, n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work, s->arow, s->kl);
+  if (s->arow)
+    SBB_LAUNCH(k_band_factor_window, (unsigned)nsys, SBB_WT, s->window_smem, st, n, s->kl, s->ku,
+               s->ldab, s->arow, s->ab, s->work, s->ipiv, s->info, s->rdiag);
+  else
+    SBB_LAUNCH(k_band_factor_solve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
+               s->ab, s->work, s->ipiv, s->info);
   SBB_LAUNCH(k_band_unpermute, GRID2(gx, nsys), 256, 0, st, n, s->perm, s->cs, s->work, d_x, n);
   for (int it = 0; it < s->n_refine; ++it) {
     SBB_LAUNCH(k_band_residual_dd, GRID2(gx, nsys), 256, 0, st, n, s->rowptr, s->colidx, s->perm,
                d_vals, vstride, d_b, d_x, n, s->rs, s->work);
-    SBB_LAUNCH(k_band_resolve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
-               s->ab, s->work, s->ipiv);
+    if (s->arow)
+      SBB_LAUNCH(k_band_resolve_window, (unsigned)nsys, SBB_WT, s->window_smem, st, n, s->kl, s->ku,
+                 s->ldab, s->ab, s->work, s->ipiv, s->rdiag);
+    else
+      SBB_LAUNCH(k_band_resolve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
+                 s->ab, s->work, s->ipiv);
     SBB_LAUNCH(k_band_accumulate, GRID2(gx, nsys), 256, 0, st, n, s->perm, s->cs, s->work, d_x, n);
   }
 #else
@@ -490,15 +902,23 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
     SBB_LAUNCH(k_band_ruiz_apply, 4u, 64, 0, st, n * nsys, s->rmax, s->cmax, s->rs, s->cs);
   }
   SBB_LAUNCH(k_band_fill, 4u, 64, 0, st, n, s->rowptr, s->colidx, s->perm, d_vals, vstride, d_b,
-             n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work);
-  SBB_LAUNCH(k_band_factor_solve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab,
-             s->work, s->ipiv, s->info);
+             n, s->rs, s->cs, s->ab, s->ldab, s->kl + s->ku, s->work, s->arow, s->kl);
+  if (s->arow)
+    SBB_LAUNCH(k_band_factor_window, 1u, SBB_WT, s->window_smem, st, n, s->kl, s->ku, s->ldab,
+               s->arow, s->ab, s->work, s->ipiv, s->info, s->rdiag);
+  else
+    SBB_LAUNCH(k_band_factor_solve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab,
+               s->work, s->ipiv, s->info);
   SBB_LAUNCH(k_band_unpermute, 4u, 64, 0, st, n, s->perm, s->cs, s->work, d_x, n);
   for (int it = 0; it < s->n_refine; ++it) {
     SBB_LAUNCH(k_band_residual_dd, 4u, 64, 0, st, n, s->rowptr, s->colidx, s->perm, d_vals,
                vstride, d_b, d_x, n, s->rs, s->work);
-    SBB_LAUNCH(k_band_resolve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab, s->work,
-               s->ipiv);
+    if (s->arow)
+      SBB_LAUNCH(k_band_resolve_window, 1u, SBB_WT, s->window_smem, st, n, s->kl, s->ku, s->ldab,
+                 s->ab, s->work, s->ipiv, s->rdiag);
+    else
+      SBB_LAUNCH(k_band_resolve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab, s->work,
+                 s->ipiv);
     SBB_LAUNCH(k_band_accumulate, 4u, 64, 0, st, n, s->perm, s->cs, s->work, d_x, n);
   }
 #endif

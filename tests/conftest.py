@@ -43,6 +43,7 @@ def build_emulation_library():
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'optics.inl'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'lcn.inl'),
             os.path.join(ROOT, 'simudo_b200', 'csrc', 'native.inl'),
+            os.path.join(ROOT, 'simudo_b200', 'csrc', 'points.inl'),
             os.path.join(ROOT, 'include', 'simudo_b200.h'),
             os.path.join(EMUL_DIR, 'cuda_emul.h')]
     if (not os.path.exists(EMUL_SO)

@@ -97,6 +97,10 @@ def test_band_solver_with_refinement_emulated(emulated_lib):
     assert np.abs(rs * r).max() < 1e-12 * np.abs(rs * b.numpy()).max() + 1e-20
 
 
+def test_band_window_kernels_emulated(emulated_lib):
+    hc.band_window_kernels_match_global_kernels()
+
+
 def test_optics_parity_emulated(emulated_lib):
     hc.optics_parity(nx=7, ny=3)
 

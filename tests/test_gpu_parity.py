@@ -104,6 +104,10 @@ def test_natbc_eval():
     hc.natbc_eval_parity()
 
 
+def test_band_window_kernels():
+    hc.band_window_kernels_match_global_kernels()
+
+
 def test_eval_points():
     hc.eval_points_parity()
 
