@@ -169,3 +169,102 @@ def test_multifrontal_solver_matches_sparse_lu_on_2d_meshes():
         x2 = mf.solve(torch.as_tensor(vals2), torch.as_tensor(b)).numpy()
         A2 = orc.to_scipy(vals2).tocsr()
         assert np.abs(r * (A2 @ x2 - b)).max() / np.abs(r * b).max() < 1e-11
+
+
+def test_oracle_manufactured_qfl_with_dg0_offsets_and_jump_term():
+    """The reference's own manufactured solution for exactly this discretisation
+    (simudo/trash/historical/qflop_test.py:11-68): mixed quasi-Fermi-level form in DG1 x BDM2
+    with a DG0 offset ``w0 = 1.0 if x > 0.5 else 0.3`` and the interior-facet jump term
+
+        v div c - v f + exp(w + w0) phi.c + div(phi) w - (w_BC - w0) phi.n ds
+                                                - (w0(-) - w0(+)) phi(+).n(+) dS = 0,
+
+    exact solution ``W = w + w0 = x^2 (1 - x)^2 / 10``, ``c = grad W exp(-W)``, ``f = div c``.
+    In the oracle this is one Boltzmann band with s = +1, kT = 1 eV, E = 0, mu N = dd_scale
+    (so 1/(mu u) = exp(chi)), an electrically dead Poisson block (eps -> inf, phi_bc = 0,
+    hence phi = 0) and no processes; the prescribed source f enters as a constant vector on
+    the band's DG1 rows (it does not depend on the unknowns).  Checks: Newton converges, the
+    smooth total W is recovered through the discontinuous offset (the jump term does its job),
+    O(h^2) convergence of W in DG1 and of the flux."""
+    import scipy.sparse.linalg as spla
+    import sympy as sp
+    from oracle import fiat_like as fl
+    from oracle.oracle import natural_bc_integrals
+    from simudo_b200.fem import model as M
+    from simudo_b200.fem.problem_arrays import ProblemArrays
+    from simudo_b200.mesh import Product2DMesh
+    X, Y = sp.symbols('x y')
+    Wx = X ** 2 * (1 - X) ** 2 / 10
+    cx = sp.diff(Wx, X) * sp.exp(-Wx)
+    f_ex = sp.lambdify((X, Y), sp.diff(cx, X), 'numpy')
+    W_ex = sp.lambdify((X, Y), Wx, 'numpy')
+    c_ex = sp.lambdify((X, Y), cx, 'numpy')
+    qp, qw = fl.default_triangle_scheme(8)                 # reference points / weights (5 x 5)
+    p1q = fl.tabulate_p1(qp)                               # [q, 3]
+    bdq, _ = fl.tabulate_bdm2(qp)                          # [q, 12, 2]
+    errs_w, errs_c = [], []
+    for nx in (8, 16, 32):
+        mesh = Product2DMesh(np.linspace(0, 1, nx + 1), np.linspace(0, 1, 4)).mesh
+        model = M.make_model([dict(kind=M.BAND_NONDEGENERATE, sign=+1)], [], n_tags=1)
+        tp = M.new_tag_params(1)
+        tp[0, M.TP_KT] = 1.0
+        tp[0, M.TP_EPS] = 1e30
+        o = M.TP_BAND0
+        tp[0, o + M.TPB_IN_SUBDOMAIN] = 1.0
+        tp[0, o + M.TPB_N] = 1.0
+        tp[0, o + M.TPB_E] = 0.0
+        tp[0, o + M.TPB_MOBILITY] = model.dd_scale        # cinv = dd_scale / (mob N) = 1
+        mesh.init()
+        jmask = np.full(mesh.num_facets, 1, dtype=np.uint8)
+        pa = ProblemArrays(mesh, np.zeros(mesh.num_cells, np.int32), model, tp,
+                           jump_facet_mask=jmask)
+        xv = pa.cell_vertices                               # [nc, 3, 2]
+        xc = xv.mean(axis=1)
+        base_w = np.where(xc[:, 0] > 0.5, 1.0, 0.3)[None, :]
+        lay = pa.layout()
+        # natural BC of the band on the whole boundary: - oint (W_ex - w0) xi.n ds
+        bf = mesh.boundary_facets()
+        bc = mesh.facet_cells[bf, 0]
+        bl = mesh.facet_local[bf, 0].astype(np.int64)
+        nodes = np.concatenate([xv, 0.5 * (xv[:, [1, 0, 0]] + xv[:, [2, 2, 1]])], axis=1)   # P2 nodes
+        p2 = W_ex(nodes[bc][:, :, 0], nodes[bc][:, :, 1])
+        integ = natural_bc_integrals(pa, bc, bl, -base_w[0, bc], p2)        # [nb, 3]
+        cells = np.repeat(bc, 3).astype(np.int32)
+        rows = lay['facet'][1][bl].ravel().astype(np.int32)
+        order = np.argsort(cells, kind='stable')
+        pa.natbc_order = np.arange(len(cells))
+        pa.natbc_cell = np.ascontiguousarray(cells[order])
+        pa.natbc_row = np.ascontiguousarray(rows[order])
+        natbc_values = (-integ.ravel())[order]
+        # source vector: int v_i f dx on the band's DG1 rows
+        J = np.stack([xv[:, 1] - xv[:, 0], xv[:, 2] - xv[:, 0]], axis=2)     # [nc, xy, XY]
+        det = np.abs(np.linalg.det(J))
+        xq = xv[:, 0][:, None, :] + np.einsum('cab,qb->cqa', J, qp)          # [nc, q, 2]
+        fq = f_ex(xq[:, :, 0], xq[:, :, 1])
+        src = np.zeros(pa.N)
+        dg = pa.cell_dofs[:, lay['dg'][1]]
+        src[dg] = np.einsum('cq,q,qi,c->ci', fq, qw, p1q, det)
+        orc = Oracle(pa)
+        u = np.zeros(pa.N)
+        for it in range(12):
+            vals, b = orc.assemble(u, base_w=base_w, natbc_values=natbc_values)
+            b = b - src
+            du = spla.spsolve(orc.to_scipy(vals).tocsc(), b)
+            u -= du
+            if np.abs(du).max() < 1e-13:
+                break
+        assert np.abs(du).max() < 1e-11, 'Newton did not converge'
+        # phi stays zero (dead Poisson block)
+        assert np.abs(u[pa.cell_dofs[:, lay['dg'][0]]]).max() < 1e-12
+        # total W = base_w + delta_w at the quadrature points vs exact, L2
+        Wq = base_w[0][:, None] + np.einsum('ci,qi->cq', u[dg], p1q)
+        errs_w.append(np.sqrt(np.einsum('cq,q,c->', (Wq - W_ex(xq[:, :, 0], xq[:, :, 1])) ** 2, qw, det)))
+        jh = np.einsum('cm,qma->cqa', u[pa.cell_dofs[:, lay['bdm'][1]]], bdq)
+        sdet = np.linalg.det(J)
+        jq = np.einsum('cab,cqb->cqa', J, jh) / sdet[:, None, None]
+        ec = (jq[:, :, 0] - c_ex(xq[:, :, 0], xq[:, :, 1])) ** 2 + jq[:, :, 1] ** 2
+        errs_c.append(np.sqrt(np.einsum('cq,q,c->', ec, qw, det)))
+        # the offsets differ by 0.7 across x = 0.5; the recovered W is smooth there
+        assert np.abs(Wq - W_ex(xq[:, :, 0], xq[:, :, 1])).max() < 2e-3
+    for e in (errs_w, errs_c):
+        assert e[1] < e[0] / 3.5 and e[2] < e[1] / 3.5, e       # second order (BDM2: >= 2)
