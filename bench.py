@@ -88,7 +88,7 @@ def parse_args():
     ap.add_argument('--no-weak', action='store_true', help='N > 1: skip the weak-scaling measurement')
     ap.add_argument('--no-sweep', action='store_true',
                     help='skip the J-V sweep ensemble (second half of the BASELINE metric)')
-    ap.add_argument('--sweep-members', type=int, default=8)
+    ap.add_argument('--sweep-members', type=int, default=8, help='sweep members per GPU')
     ap.add_argument('--sweep-bias-points', type=int, default=6)
     return ap.parse_args()
 
@@ -246,11 +246,19 @@ def sweep_timing(args, dist):
     """J-V sweep wall time (BASELINE metric, second half; configs[4] at reduced size): an
     ensemble of four-layer IB cells (device-parameter variants, fourlayer.py:233-284), each a
     light ramp + bias continuation with self-consistent optics, dealt to the ranks, up to 8
-    chains in flight per GPU (threads + streams), no data-path collective.  The same members
-    at every N, so wall_s(1) / wall_s(N) is the sweep's strong scaling."""
+    chains in flight per GPU (threads + streams), no data-path collective.  Weak scaling, as
+    BASELINE configs[4] is specified (64 devices on 8 GPUs = 8 per GPU): `--sweep-members`
+    members PER GPU, so N GPUs run 8 N members in about the wall time one GPU needs for 8 and
+    `bias_points_per_s` is the scaling number (one continuation chain is latency-bound: a fixed
+    set of 8 chains would not get faster on more GPUs)."""
     from simudo_b200.example import ibsc_ensemble
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     try:
-        return ibsc_ensemble.run(args.sweep_members, args.sweep_bias_points, in_flight=8, dist=dist)
+        r = ibsc_ensemble.run(args.sweep_members * world, args.sweep_bias_points, in_flight=8,
+                              dist=dist)
+        r['scaling'] = 'weak'
+        r['members_per_gpu'] = args.sweep_members
+        return r
     except Exception as e:                      # a failed chain must not lose the assembly numbers
         return dict(error='%s: %s' % (type(e).__name__, e))
 

@@ -53,6 +53,19 @@ struct sb_band_solver {
   int32_t* ipiv;       /* [batch][n] */
   int32_t* info;       /* [batch] first zero pivot + 1, 0 = ok */
   double* rdiag;       /* [batch][n] reciprocal pivots (window kernels) */
+#ifndef SB_EMUL_BUILD
+  cudaGraphExec_t gexec = nullptr;   /* the captured launch sequence of a solve ...         */
+  const double* g_vals = nullptr;    /* ... for exactly these arguments                      */
+  const double* g_b = nullptr;
+  double* g_x = nullptr;
+  int32_t g_nsys = 0, g_refine = -1;
+  int64_t g_vstride = 0;
+  const double* c_vals = nullptr;    /* arguments of the previous call (capture candidates)  */
+  const double* c_b = nullptr;
+  double* c_x = nullptr;
+  int32_t c_nsys = 0, c_refine = -1;
+  int64_t c_vstride = 0;
+#endif
   double* arow;        /* [batch][n][kl + ku + 1] row-major copy of the scaled band, or null:
                           the shared-memory window kernels are used when it exists */
   size_t window_smem;
@@ -753,6 +766,9 @@ static int balloc(sb_band_solver* s, size_t n, T** out) {
 
 extern "C" void sb_band_destroy(sb_band_solver* s) {
   if (!s) return;
+#ifndef SB_EMUL_BUILD
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
+#endif
   for (void* p : s->allocs) cudaFree(p);
   delete s;
 }
@@ -800,17 +816,30 @@ extern "C" int sb_band_create(int64_t n, const int64_t* h_rowptr, const int32_t*
      sm_100a); SIMUDO_B200_BAND_GLOBAL=1 keeps the global-memory kernels (tests compare both) */
   s->arow = nullptr; s->rdiag = nullptr;
   s->window_smem = sbb_window_smem((int)kl, (int)ku);
-  if (rc == SB_OK && s->window_smem <= 227 * 1024 && kl <= 128 && !getenv("SIMUDO_B200_BAND_GLOBAL")) {
+  size_t max_dyn = 227 * 1024;
+#ifndef SB_EMUL_BUILD
+  {
+    /* dynamic shared memory a launch of the window kernels may ask for on this device: the
+       opt-in maximum minus their static shared memory.  The attribute is per kernel, not per
+       solver, and solvers of different bandwidths (PDD system, CG2 optics matrices) coexist
+       in one process, possibly on several threads: opt in to the maximum once and for all */
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa1, fa2;
+    BTRY(cudaGetDevice(&dev));
+    BTRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    BTRY(cudaFuncGetAttributes(&fa1, k_band_factor_window));
+    BTRY(cudaFuncGetAttributes(&fa2, k_band_resolve_window));
+    const size_t st = fa1.sharedSizeBytes > fa2.sharedSizeBytes ? fa1.sharedSizeBytes : fa2.sharedSizeBytes;
+    max_dyn = (size_t)optin > st ? (size_t)optin - st : 0;
+    BTRY(cudaFuncSetAttribute(k_band_factor_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)optin - fa1.sharedSizeBytes)));
+    BTRY(cudaFuncSetAttribute(k_band_resolve_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)optin - fa2.sharedSizeBytes)));
+  }
+#endif
+  if (rc == SB_OK && s->window_smem <= max_dyn && kl <= 128 && !getenv("SIMUDO_B200_BAND_GLOBAL")) {
     rc = balloc(s, (size_t)(n * (kl + ku + 1) * batch), &s->arow);
     if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->rdiag);
-#ifndef SB_EMUL_BUILD
-    if (rc == SB_OK) {
-      BTRY(cudaFuncSetAttribute(k_band_factor_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)s->window_smem));
-      BTRY(cudaFuncSetAttribute(k_band_resolve_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)s->window_smem));
-    }
-#endif
   }
   if (rc != SB_OK) { sb_band_destroy(s); return rc; }
   cudaMemcpy(s->rowptr, h_rowptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
@@ -837,14 +866,9 @@ extern "C" int sb_band_info(const sb_band_solver* s, int64_t* n, int32_t* kl, in
 /* Solve A x = b for `nsys` <= batch systems sharing the sparsity pattern:
  * d_vals [nsys][vstride], d_b / d_x [nsys][n].  h_info (optional, host) receives the
  * LAPACK-style info per system (synchronises the stream when given).            */
-extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals,
-                             int64_t vstride, const double* d_b, double* d_x,
-                             int32_t* h_info, void* stream) {
-  if (!s || !d_vals || !d_b || !d_x || nsys <= 0 || nsys > s->batch) {
-    snprintf(g_sb_err, sizeof g_sb_err, "bad argument to sb_band_solve");
-    return SB_ERR_ARG;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
+/* the launch sequence of one solve (about 40 launches), enqueued on `st` */
+static int band_enqueue(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_t vstride,
+                        const double* d_b, double* d_x, cudaStream_t st) {
   const int64_t n = s->n;
   const unsigned gx = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
 #ifdef SB_EMUL_BUILD
@@ -923,6 +947,68 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
   }
 #endif
   BTRY(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals,
+                             int64_t vstride, const double* d_b, double* d_x,
+                             int32_t* h_info, void* stream) {
+  if (!s || !d_vals || !d_b || !d_x || nsys <= 0 || nsys > s->batch) {
+    snprintf(g_sb_err, sizeof g_sb_err, "bad argument to sb_band_solve");
+    return SB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+#ifndef SB_EMUL_BUILD
+  /* A Newton loop calls this with the same buffers every iteration: the ~40 launches of a
+     solve are captured once into a CUDA graph and replayed (one launch per solve; with eight
+     continuation chains in flight per GPU the launch rate of the process was the limit of a
+     J-V sweep).  The legacy default stream cannot be captured: direct launches there. */
+  const bool same = s->gexec && s->g_vals == d_vals && s->g_b == d_b && s->g_x == d_x &&
+                    s->g_nsys == nsys && s->g_vstride == vstride && s->g_refine == s->n_refine;
+  if (same) {
+    BTRY(cudaGraphLaunch(s->gexec, st));
+  } else {
+    if (s->gexec) { cudaGraphExecDestroy(s->gexec); s->gexec = nullptr; }
+    bool captured = false;
+    /* capture only what has been seen twice in a row: one-off argument sets are launched
+       directly (capturing + instantiating costs more than the launches) */
+    const bool again = s->c_vals == d_vals && s->c_b == d_b && s->c_x == d_x &&
+                       s->c_nsys == nsys && s->c_vstride == vstride && s->c_refine == s->n_refine;
+    s->c_vals = d_vals; s->c_b = d_b; s->c_x = d_x; s->c_nsys = nsys; s->c_vstride = vstride;
+    s->c_refine = s->n_refine;
+    if (again && st != nullptr && !getenv("SIMUDO_B200_NO_GRAPH") &&
+        cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rc = band_enqueue(s, nsys, d_vals, vstride, d_b, d_x, st);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc == SB_OK && e == cudaSuccess && g &&
+          cudaGraphInstantiate(&s->gexec, g, 0) == cudaSuccess) {
+        s->g_vals = d_vals; s->g_b = d_b; s->g_x = d_x; s->g_nsys = nsys;
+        s->g_vstride = vstride; s->g_refine = s->n_refine;
+        captured = true;
+      } else {
+        s->gexec = nullptr;
+      }
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();                         /* a failed capture leaves a sticky-free error */
+    } else {
+      cudaGetLastError();
+    }
+    if (captured) {
+      BTRY(cudaGraphLaunch(s->gexec, st));
+    } else {
+      const int rc = band_enqueue(s, nsys, d_vals, vstride, d_b, d_x, st);
+      if (rc != SB_OK) return rc;
+    }
+  }
+#else
+  {
+    const int rc = band_enqueue(s, nsys, d_vals, vstride, d_b, d_x, st);
+    if (rc != SB_OK) return rc;
+  }
+#endif
+  const int64_t n = s->n;
+  (void)n;
   if (h_info) {
 #ifndef SB_EMUL_BUILD
     BTRY(cudaMemcpyAsync(h_info, s->info, nsys * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -50,10 +50,14 @@ class OpticsPlan(object):
         self._h = h
         self._keep = (keep, tables)
         csr = (sp.n_dofs, sp.rowptr, sp.colidx, sp.x_major_permutation())
+        # one solver per system (mass projection, MSORTE) with fixed argument buffers: a solve
+        # whose arguments repeat is replayed as a captured CUDA graph (csrc/band_solver.cu)
         self.band = BandSolver(None, self.device, csr=csr)
+        self.band_mass = BandSolver(None, self.device, csr=csr)
         self.mass = plan.tensor(sp.mass_values())
-        self._vals = torch.zeros(sp.nnz, dtype=torch.float64, device=self.device)
-        self._rhs = torch.zeros(sp.n_dofs, dtype=torch.float64, device=self.device)
+        z = lambda n: torch.zeros(n, dtype=torch.float64, device=self.device)
+        self._vals, self._rhs = z(sp.nnz), z(sp.n_dofs)
+        self._arhs, self._alpha, self._phi = z(sp.n_dofs), z(sp.n_dofs), z(sp.n_dofs)
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -68,14 +72,14 @@ class OpticsPlan(object):
     def alpha_rhs(self, field, u, base_w):
         st = _lib.SbState()
         st.d_u, st.d_base_w = _p(u), _p(base_w)
-        rhs = torch.empty(self.space.n_dofs, dtype=torch.float64, device=self.device)
+        rhs = self._arhs
         _lib.check(self.lib.sb_optics_alpha_rhs(self._h, C.byref(st), int(field), _p(rhs),
                                                 self.plan._stream(None)))
         return rhs
 
     def project_alpha(self, field, u, base_w):
         """CG2 nodal values of the absorption coefficient of one field."""
-        return self.band.solve(self.mass, self.alpha_rhs(field, u, base_w))
+        return self.band_mass.solve(self.mass, self.alpha_rhs(field, u, base_w), x=self._alpha)
 
     def assemble(self, alpha, direction, bc_dofs, bc_vals):
         n_bc = 0 if bc_dofs is None else int(bc_dofs.numel())
@@ -96,5 +100,5 @@ class OpticsPlan(object):
         """Returns (Phi nodal [n_dofs], Phi per cell [Nc, 6])."""
         alpha = self.project_alpha(field, u, base_w)
         vals, rhs = self.assemble(alpha, direction, bc_dofs, bc_vals)
-        phi = self.band.solve(vals, rhs)
+        phi = self.band.solve(vals, rhs, x=self._phi).clone()    # the caller keeps it per field
         return phi, self.to_cells(phi, out)

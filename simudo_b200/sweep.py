@@ -26,9 +26,14 @@ def _run_in_flight(items, fn, in_flight):
     import concurrent.futures as cf
     import torch
 
+    # the current CUDA device is per thread and a new thread starts on device 0: hand the
+    # rank's device to its workers (otherwise every rank > 0 ran its chains on GPU 0)
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+
     def worker(x):
-        if torch.cuda.is_available():
-            with torch.cuda.stream(torch.cuda.Stream()):
+        if dev is not None:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
                 r = fn(x)
                 torch.cuda.current_stream().synchronize()
                 return r
