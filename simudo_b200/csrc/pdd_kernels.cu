@@ -21,6 +21,7 @@
 #include <vector>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <type_traits>
 
@@ -781,6 +782,33 @@ k_rows_staged(PlanDev pl, StateDev st, double* vals, double* b) {
   }
 }
 
+/* Opt a kernel in to `smem` bytes of dynamic shared memory on the current device, once:
+ * cudaFuncSetAttribute is not a cheap call -- it was made on every launch, and with several
+ * sweep chains in flight (one thread + stream each) it waited for the other chains' running
+ * kernels: 23 ms of host time per sb_assemble, 45 % of the wall time of an 8-chain ensemble
+ * (tools/prof_ensemble.py).  The attribute is per kernel and device: remembered per pair. */
+static void ensure_dynamic_smem(const void* fn, size_t smem) {
+#ifdef SB_EMUL_BUILD
+  (void)fn; (void)smem;
+#else
+  struct Entry { const void* fn; int dev; size_t smem; };
+  static std::vector<Entry> cache;
+  static std::mutex mtx;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mtx);
+  for (Entry& e : cache)
+    if (e.fn == fn && e.dev == dev) {
+      if (e.smem >= smem) return;
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e.smem = smem;
+      return;
+    }
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cache.push_back({fn, dev, smem});
+#endif
+}
+
 /* launch k_rows_fast<NB, PS> for PS = 0 .. NB */
 template <int NB, int PS>
 struct RowsLauncher {
@@ -789,9 +817,7 @@ struct RowsLauncher {
     if (d.stage_patk) {
       const size_t smem = (sizeof(double) * 32 * SB_STAGE_STRIDE + sizeof(SbWarpMeta))
                           * (SB_TILE / 32) + (size_t)SB_MAX_SMEM_PATTERNS * 15 * 32;
-      /* per device and cheap: set on every launch (a process may drive several GPUs) */
-      cudaFuncSetAttribute(k_rows_staged<NB, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
+      ensure_dynamic_smem((const void*)k_rows_staged<NB, PS>, smem);
       SB_LAUNCH((k_rows_staged<NB, PS>), nblk, SB_TILE, smem, s, d, sd, vals, b);
     } else
       SB_LAUNCH((k_rows_fast<NB, PS>), nblk, SB_TILE, 0, s, d, sd, vals, b);
@@ -1215,6 +1241,7 @@ static SbTables g_bound_tables[SB_MAX_DEVICES];
 static sb_model g_bound_model[SB_MAX_DEVICES];
 static bool g_bound_valid[SB_MAX_DEVICES] = {false};
 
+static std::atomic<int64_t> g_table_uploads{0}, g_table_upload_us{0};
 static int bind_tables(sb_plan* pl, cudaStream_t s) {
   const int slot = current_device_slot();
   if (g_tables_owner[slot] == pl) return SB_OK;
@@ -1225,10 +1252,18 @@ static int bind_tables(sb_plan* pl, cudaStream_t s) {
     g_tables_owner[slot] = pl;
     return SB_OK;
   }
+#ifndef SB_EMUL_BUILD
+  const auto t0_ = std::chrono::steady_clock::now();
+#endif
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_T, &pl->tables, sizeof(SbTables), 0,
                                    cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_M, &pl->model, sizeof(sb_model), 0,
                                    cudaMemcpyHostToDevice, s));
+#ifndef SB_EMUL_BUILD
+  g_table_uploads += 1;
+  g_table_upload_us += (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(
+      std::chrono::steady_clock::now() - t0_).count();
+#endif
   g_tables_owner[slot] = pl;
   g_bound_tables[slot] = pl->tables;
   g_bound_model[slot] = pl->model;
