@@ -482,6 +482,10 @@ class PDDSystem(_SystemBase):
     def rebase_w(self, band):
         be = self.backend
         o = self.ohmic[band] if self.ohmic else None
+        bobj = self.bands[band]
+        thr = tuple(getattr(bobj, 'mixedqfl_debug_fill_thresholds', (0.0, 0.0)))
+        if thr != (0.0, 0.0) or getattr(bobj, 'mixedqfl_debug_fill_with_zero_except_bc', False):
+            return self._rebase_w_flood_fill(band, o, thr, bobj)
         if o is None:
             be.rebase(band, None, None)
             return
@@ -492,6 +496,50 @@ class PDDSystem(_SystemBase):
                      + 4.0 * th[np.arange(len(o['c'])), mid]) / 6.0
             o['thm'] = np.bincount(o['inv'], weights=o['w'] * avg_f)
         be.rebase(band, o, o['thm'])
+
+    def _ohmic_bc_cell_values(self, band, o):
+        """(cells, values) next to the Ohmic contacts of ``band``: facet average of
+        u_to_w(u_bc) = e (phi_thmeq - phi) weighted per cell (``poisson_drift_diffusion1.py1:
+        362-367``, ``fem/spatial.py:185-235``) -- the host restatement of what ``sb_rebase_w``
+        receives as (bc_cells, bc_avg)."""
+        if o is None:
+            return (np.zeros(0, np.int64), np.zeros(0))
+        if 'thm' not in o:
+            th = self.thmeq_phi[o['c']]
+            mid = 3 + o['l']
+            ar = np.arange(len(o['c']))
+            avg_f = (th[ar, o['va']] + th[ar, o['vb']] + 4.0 * th[ar, mid]) / 6.0
+            o['thm'] = np.bincount(o['inv'], weights=o['w'] * avg_f)
+        phi = self.phi_nodal()[o['c']]
+        ar = np.arange(len(o['c']))
+        phi_f = 0.5 * (phi[ar, o['va']] + phi[ar, o['vb']])
+        phi_avg = np.bincount(o['inv'], weights=o['w'] * phi_f)
+        return (np.asarray(o['cells'], dtype=np.int64), o['thm'] - phi_avg)
+
+    def _rebase_w_flood_fill(self, band, o, thresholds, bobj):
+        """``mixedqfl_do_rebase_w`` with non-zero ``mixedqfl_debug_fill_thresholds``
+        (``poisson_drift_diffusion1.py1:339-383`` -> ``PartitionOffsets``,
+        ``fem/offset_partitioning.py:108-169``): offsets by flood fill on the host, delta_w
+        re-expressed so that base_w + delta_w is unchanged."""
+        from ..fem.offset_partitioning import partition_offsets
+        lay = self.pa.layout()
+        dg = self.pa.cell_dofs[:, lay['dg'][1 + band]]
+        u = np.array(self.u_host(), dtype=np.float64)
+        base = np.array(self.base_w_host(), dtype=np.float64)
+        w_avg = base[band] + u[dg].mean(axis=1)
+        bc = ((np.zeros(0, np.int64), np.zeros(0)))
+        if getattr(bobj, 'mixedqfl_debug_fill_from_boundary', True):
+            bc = self._ohmic_bc_cell_values(band, o)
+        new = partition_offsets(
+            w_avg, self.mesh.cell_to_cells_adjacency_via_facet(), thresholds, bc,
+            getattr(bobj, 'mixedqfl_debug_fill_with_zero_except_bc', False))
+        u[dg] += (base[band] - new)[:, None]
+        base[band] = new
+        self._base_w0 = base
+        self.set_u_host(u)
+        if self._backend is not None:
+            self._backend.set_state(self._u_host, self._base_w0 if self.full else None,
+                                    self.thmeq_phi if self.full else None, self.phi_opt)
 
     def terminal_current(self, band, facets):
         """(integral of j.n ds, total length) over exterior facets, form units."""

@@ -215,3 +215,32 @@ def test_line_cut_csv_of_the_converged_solution(oracle_sweep, tmp_path):
     # steady state: total current constant along the device, equal to the terminal current
     J = jv[-1][1]
     assert np.abs(np.abs(col['j_tot_x']) - abs(J)).max() < 2e-3 * abs(J)
+
+
+def test_rebasing_with_flood_fill_thresholds_preserves_the_quasi_fermi_level(oracle_sweep):
+    """``mixedqfl_debug_fill_thresholds`` != (0, 0) (``poisson_drift_diffusion1.py1:339-383``,
+    ``fem/offset_partitioning.py:108-169``): base_w becomes piecewise constant over regions,
+    delta_w absorbs the difference, w = base_w + delta_w is unchanged at every DG1 node."""
+    _, problem, _ = oracle_sweep
+    pdd = problem.pdd
+    sysm = pdd.system
+    band = pdd.bands['CB']
+    bi = band.index
+    lay = sysm.pa.layout()
+    dg = sysm.pa.cell_dofs[:, lay['dg'][1 + bi]]
+    saved = sysm.save()
+    try:
+        w_before = sysm.base_w_host()[bi][:, None] + sysm.u_host()[dg]
+        n_before = len(np.unique(np.round(sysm.base_w_host()[bi], 12)))
+        band.mixedqfl_debug_fill_thresholds = (5e-2, 0.0)
+        band.mixedqfl_do_rebase_w()
+        base = sysm.base_w_host()[bi]
+        w_after = base[:, None] + sysm.u_host()[dg]
+        assert np.abs(w_after - w_before).max() < 1e-12
+        assert len(np.unique(base)) < n_before / 4          # regions, not cells
+        # ... and the residual of the converged state is unchanged by the re-split
+        sysm.assemble()
+        assert np.abs(sysm.backend.get_b()).max() < 1e-6
+    finally:
+        del band.mixedqfl_debug_fill_thresholds
+        sysm.restore(saved)
