@@ -842,9 +842,14 @@ extern "C" int sb_band_create(int64_t n, const int64_t* h_rowptr, const int32_t*
     if (rc == SB_OK) rc = balloc(s, (size_t)(n * batch), &s->rdiag);
   }
   if (rc != SB_OK) { sb_band_destroy(s); return rc; }
-  cudaMemcpy(s->rowptr, h_rowptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice);
-  cudaMemcpy(s->colidx, h_colidx, s->nnz * sizeof(int32_t), cudaMemcpyHostToDevice);
-  cudaMemcpy(s->perm, h_perm, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (cudaMemcpy(s->rowptr, h_rowptr, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(s->colidx, h_colidx, s->nnz * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(s->perm, h_perm, n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    snprintf(g_sb_err, sizeof g_sb_err, "sb_band_create: upload of the sparsity structure failed: %s",
+             cudaGetErrorString(cudaGetLastError()));
+    sb_band_destroy(s);
+    return SB_ERR_CUDA;
+  }
   *out = s;
   return SB_OK;
 }
