@@ -244,3 +244,57 @@ def test_rebasing_with_flood_fill_thresholds_preserves_the_quasi_fermi_level(ora
     finally:
         del band.mixedqfl_debug_fill_thresholds
         sysm.restore(saved)
+
+
+def test_thermal_equilibrium_potential_against_the_depletion_approximation(oracle_sweep):
+    """The reference's depletion-approximation helper (``simudo/trash/deplapprox.py:6-78``):
+    ``V_bi = kT/q ln(n_n0 p_p0 / n_i^2)``, ``w_n,p = sqrt(2 eps V_bi / (q (N_D,A / N_A,D + 1)
+    N_D,A))`` and the piecewise-parabolic ``depl_V(x)``.  The thermal-equilibrium stage of the
+    tutorial diode (N_A = N_D = 1e18 cm^-3, silicon) must (1) drop exactly V_bi between the
+    neutral contacts -- an identity for Boltzmann statistics -- and (2) follow depl_V to the
+    accuracy of that approximation (a few kT: it neglects the carrier tails)."""
+    _, problem, _ = oracle_sweep
+    sysm = problem.pdd.system
+    U = problem.pdd.unit_registry
+    pa = sysm.pa
+    from simudo_b200.fem import model as M
+    tp = pa.tag_params
+    kT = tp[0, M.TP_KT]                                          # eV
+    eps = tp[0, M.TP_EPS]                                        # elementary charges / (V um)
+    NC = tp[0, M.TP_BAND0 + 0 * 5 + M.TPB_N]                     # 1 / um^3
+    NV = tp[0, M.TP_BAND0 + 1 * 5 + M.TPB_N]
+    Eg = tp[0, M.TP_BAND0 + 0 * 5 + M.TPB_E] - tp[0, M.TP_BAND0 + 1 * 5 + M.TPB_E]
+    ni2 = NC * NV * np.exp(-Eg / kT)
+    assert abs(eps / (11.7 * 55.26349406) - 1.0) < 1e-6          # 11.7 vacuum permittivities
+    q = 1.0                                                      # charge is counted in e
+    N_A = N_D = 1e18 * 1e-12                                     # 1 / um^3
+    n_n0 = 0.5 * (N_D + np.sqrt(N_D ** 2 + 4 * ni2))
+    p_p0 = 0.5 * (N_A + np.sqrt(N_A ** 2 + 4 * ni2))
+    V_bi = kT * np.log(n_n0 * p_p0 / ni2)                        # V (kT in eV)
+    w_n = np.sqrt(2 * V_bi * eps / (q * (N_D / N_A + 1) * N_D))
+    w_p = np.sqrt(2 * V_bi * eps / (q * (N_A / N_D + 1) * N_A))
+    # thermal-equilibrium potential at the cell vertices (P2 nodal values 0..2)
+    x = pa.cell_vertices[:, :, 0].ravel()
+    phi = sysm.thmeq_phi[:, :3].ravel()
+    order = np.argsort(x, kind='stable')
+    x, phi = x[order], phi[order]
+    x_pn = 0.5 * (x[0] + x[-1])
+    drop = abs(phi[-1] - phi[0])
+    assert abs(drop - V_bi) < 1e-6 * V_bi, (drop, V_bi)
+    assert 0.9 < V_bi < 1.0 and 0.02 < w_n < 0.03               # 0.956 V, 25 nm for 1e18 / 1e18
+
+    def depl_V(xx):
+        z_p, z_n = x_pn - w_p, x_pn + w_n
+        if xx < z_p:
+            return 0.0
+        V = q / eps * N_A * 0.5 * (min(x_pn, xx) - z_p) ** 2
+        if xx >= x_pn:
+            V += q / eps * N_D * 0.5 * ((x_pn - z_n) ** 2 - (z_n - min(xx, z_n)) ** 2)
+        return V
+    ref = np.array([depl_V(v) for v in x])
+    s = np.sign(phi[-1] - phi[0])
+    dev = np.abs(s * (phi - phi[0]) - ref).max()
+    assert dev < 3.0 * kT, (dev, kT)                             # measured ~1.3 kT
+    # the depletion region is where the potential varies: 10 % .. 90 % of V_bi within w_p + w_n
+    inside = (s * (phi - phi[0]) > 0.1 * V_bi) & (s * (phi - phi[0]) < 0.9 * V_bi)
+    assert x[inside].max() - x[inside].min() < w_n + w_p
