@@ -279,6 +279,12 @@ int  sb_band_set_refinement(sb_band_solver* s, int32_t steps);
  * 0 = ok, j+1 = zero pivot in column j (synchronises the stream when given).        */
 int  sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_vals, int64_t vstride,
                    const double* d_b, double* d_x, int32_t* h_info, void* stream);
+/* x = A^-1 b with the factors and scalings of the last sb_band_solve on this solver (no
+ * refinement): for matrices that do not change between solves, e.g. the CG2 mass matrix of
+ * OpticalField.update_input -> dolfin.project (simudo/physics/optical.py:260-274,
+ * simudo/fem/assign.py:12-47), which the reference refactors on every call.             */
+int  sb_band_solve_factored(sb_band_solver* s, int32_t nsys, const double* d_b, double* d_x,
+                            void* stream);
 
 /* r = b - A x with a compensated (double-double) row sum for a device CSR matrix: the
  * residual the refinement steps of the Newton linear solve need (a Newton row mixes entries

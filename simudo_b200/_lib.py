@@ -23,7 +23,7 @@ EXPORTED = ['sb_plan_create', 'sb_plan_destroy', 'sb_last_error', 'sb_version',
             'sb_plan_is_native', 'sb_plan_generation_signature', 'sb_locator_create', 'sb_locator_destroy', 'sb_eval_points', 'sb_measure_fp64_peak',
             'sb_plan_column_indices', 'sb_natbc_eval', 'sb_rebase_w', 'sb_newton_update', 'sb_newton_update_damped',
             'sb_surface_flux', 'sb_tables_size', 'sb_plan_set_profiling',
-            'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_destroy', 'sb_band_info',
+            'sb_plan_last_kernel_ms', 'sb_plan_last_stage_ms', 'sb_band_create', 'sb_band_solve_factored', 'sb_band_destroy', 'sb_band_info',
             'sb_band_solve', 'sb_band_set_refinement', 'sb_csr_residual_dd', 'sb_optics_create',
             'sb_optics_destroy', 'sb_optics_tables_size', 'sb_optics_alpha_rhs',
             'sb_optics_assemble', 'sb_optics_to_cells', 'sb_lcn_iteration']
@@ -111,6 +111,8 @@ def _declare(lib):
     lib.sb_band_info.restype = C.c_int
     lib.sb_band_solve.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp]
     lib.sb_band_solve.restype = C.c_int
+    lib.sb_band_solve_factored.argtypes = [vp, C.c_int32, vp, vp, vp]
+    lib.sb_band_solve_factored.restype = C.c_int
     lib.sb_csr_residual_dd.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp]
     lib.sb_csr_residual_dd.restype = C.c_int
     lib.sb_band_set_refinement.argtypes = [vp, i32]

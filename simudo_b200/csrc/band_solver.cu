@@ -53,6 +53,7 @@ struct sb_band_solver {
   int32_t* ipiv;       /* [batch][n] */
   int32_t* info;       /* [batch] first zero pivot + 1, 0 = ok */
   double* rdiag;       /* [batch][n] reciprocal pivots (window kernels) */
+  bool factored = false;   /* ab / ipiv / rs / cs hold the factors of a completed sb_band_solve */
 #ifndef SB_EMUL_BUILD
   cudaGraphExec_t gexec = nullptr;   /* the captured launch sequence of a solve ...         */
   const double* g_vals = nullptr;    /* ... for exactly these arguments                      */
@@ -180,6 +181,15 @@ __global__ void k_band_fill(int64_t n, const int64_t* rowptr, const int32_t* col
     }
     work[sys * n + pr] = b[sys * bstride + r] * s;
   }
+}
+
+/* permuted, row-scaled right-hand side into work (a solve with stored factors) */
+__global__ void k_band_rhs(int64_t n, const int32_t* perm, const double* b, int64_t bstride,
+                           const double* rs, double* work) {
+  const int64_t sys = blockIdx.y;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x)
+    work[sys * n + perm[r]] = b[sys * bstride + r] * rs[sys * n + r];
 }
 
 /* one CTA: gbtf2 + gbtrs on one system */
@@ -1014,6 +1024,7 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
 #endif
   const int64_t n = s->n;
   (void)n;
+  s->factored = true;
   if (h_info) {
 #ifndef SB_EMUL_BUILD
     BTRY(cudaMemcpyAsync(h_info, s->info, nsys * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1022,6 +1033,43 @@ extern "C" int sb_band_solve(sb_band_solver* s, int32_t nsys, const double* d_va
     memcpy(h_info, s->info, nsys * sizeof(int32_t));
 #endif
   }
+  return SB_OK;
+}
+
+/* x = A^-1 b with the factors (and scalings) of the last sb_band_solve: for a matrix that does
+ * not change between solves -- the CG2 mass matrix of the optical projection
+ * (dolfin.project, simudo/fem/assign.py:12-47, refactors it on every call).            */
+extern "C" int sb_band_solve_factored(sb_band_solver* s, int32_t nsys, const double* d_b,
+                                      double* d_x, void* stream) {
+  if (!s || !d_b || !d_x || nsys <= 0 || nsys > s->batch || !s->factored) {
+    snprintf(g_sb_err, sizeof g_sb_err, !s || s->factored ? "bad argument to sb_band_solve_factored"
+                                                          : "sb_band_solve_factored before sb_band_solve");
+    return SB_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = s->n;
+#ifdef SB_EMUL_BUILD
+  if (nsys != 1) return SB_ERR_UNSUPPORTED;
+  SBB_LAUNCH(k_band_rhs, 4u, 64, 0, st, n, s->perm, d_b, n, s->rs, s->work);
+  if (s->arow)
+    SBB_LAUNCH(k_band_resolve_window, 1u, SBB_WT, s->window_smem, st, n, s->kl, s->ku, s->ldab,
+               s->ab, s->work, s->ipiv, s->rdiag);
+  else
+    SBB_LAUNCH(k_band_resolve, 1u, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab, s->ab, s->work,
+               s->ipiv);
+  SBB_LAUNCH(k_band_unpermute, 4u, 64, 0, st, n, s->perm, s->cs, s->work, d_x, n);
+#else
+  const unsigned gx = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  SBB_LAUNCH(k_band_rhs, dim3(gx, nsys), 256, 0, st, n, s->perm, d_b, n, s->rs, s->work);
+  if (s->arow)
+    SBB_LAUNCH(k_band_resolve_window, (unsigned)nsys, SBB_WT, s->window_smem, st, n, s->kl, s->ku,
+               s->ldab, s->ab, s->work, s->ipiv, s->rdiag);
+  else
+    SBB_LAUNCH(k_band_resolve, (unsigned)nsys, SBB_THREADS, 0, st, n, s->kl, s->ku, s->ldab,
+               s->ab, s->work, s->ipiv);
+  SBB_LAUNCH(k_band_unpermute, dim3(gx, nsys), 256, 0, st, n, s->perm, s->cs, s->work, d_x, n);
+#endif
+  BTRY(cudaGetLastError());
   return SB_OK;
 }
 

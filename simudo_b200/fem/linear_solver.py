@@ -113,3 +113,18 @@ class BandSolver(object):
                 raise RuntimeError('simudo_b200: singular Jacobian in banded LU '
                                    '(zero pivot at column %d)' % (info[bad[0]] - 1))
         return x
+
+    def solve_factored(self, b, x=None, stream=None):
+        """x = A^{-1} b with the factors of the last ``solve`` (a matrix that does not change:
+        the CG2 mass matrix of the optical projection)."""
+        nsys = 1 if b.dim() == 1 else b.shape[0]
+        if x is None:
+            x = torch.empty_like(b)
+        st = None
+        if stream is not None:
+            st = C.c_void_p(stream.cuda_stream)
+        elif self.device.type == 'cuda':
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.sb_band_solve_factored(
+            self._h, nsys, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), st))
+        return x

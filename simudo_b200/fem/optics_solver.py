@@ -58,6 +58,7 @@ class OpticsPlan(object):
         z = lambda n: torch.zeros(n, dtype=torch.float64, device=self.device)
         self._vals, self._rhs = z(sp.nnz), z(sp.n_dofs)
         self._arhs, self._alpha, self._phi = z(sp.n_dofs), z(sp.n_dofs), z(sp.n_dofs)
+        self._mass_factored = False
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -79,7 +80,11 @@ class OpticsPlan(object):
 
     def project_alpha(self, field, u, base_w):
         """CG2 nodal values of the absorption coefficient of one field."""
-        return self.band_mass.solve(self.mass, self.alpha_rhs(field, u, base_w), x=self._alpha)
+        rhs = self.alpha_rhs(field, u, base_w)
+        if not self._mass_factored:                 # the mass matrix never changes: factor once
+            self._mass_factored = True
+            return self.band_mass.solve(self.mass, rhs, x=self._alpha)
+        return self.band_mass.solve_factored(rhs, x=self._alpha)
 
     def assemble(self, alpha, direction, bc_dofs, bc_vals):
         n_bc = 0 if bc_dofs is None else int(bc_dofs.numel())

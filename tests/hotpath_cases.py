@@ -137,6 +137,11 @@ def band_window_kernels_match_global_kernels():
                 os.environ.pop('SIMUDO_B200_BAND_GLOBAL', None)
             x[mode] = bs.solve(torch.as_tensor(A.data.copy(), device=dev),
                                torch.as_tensor(b, device=dev)).cpu().numpy()
+            # a second right-hand side through the stored factors (sb_band_solve_factored)
+            b2 = rng.normal(size=n)
+            x2 = bs.solve_factored(torch.as_tensor(b2, device=dev)).cpu().numpy()
+            xr2 = spla.spsolve(A.tocsc(), b2)
+            assert np.abs(x2 - xr2).max() <= 1e-8 * np.abs(xr2).max(), (mode, n, kl, ku)
             if mode == 'window':
                 bs_keep = bs
         if wide is None:
