@@ -644,21 +644,38 @@ k_rows_nat(PlanDev pl, StateDev st, double* __restrict__ vals, double* __restric
      DG and interior rows: four short, independent instruction streams per cell tile
      instead of one long one.  The CTA is persistent: tiles blockIdx.x, + gridDim.x, ... */
   const int role = warp;
-  const int64_t G = gridDim.x;
-  int64_t tile = blockIdx.x;
+  /* Tiles are handed out dynamically (one atomic per tile on a per-launch counter): CTAs that
+     start late -- the boundary-cell kernel runs beside the row kernels on a second stream --
+     take fewer tiles, and a small mesh (a strip of a decomposed mesh) does not end with some
+     CTAs one tile behind.  Thread 0 claims the tile of iteration it + 3 while the CTA works
+     on `it`; the claim travels through s_claim and the barrier at the top of the loop. */
+  __shared__ int s_claim[2];
+  int* ctr = pl.nat_tile_ctr + PS;
+  if (threadIdx.x == 0) {
+    s_claim[0] = atomicAdd(ctr, 1);
+    s_claim[1] = atomicAdd(ctr, 1);
+  }
+  __syncthreads();
+  int64_t tile = s_claim[0], tile1 = s_claim[1], tile2 = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) s_claim[0] = atomicAdd(ctr, 1);          /* for iteration 0: tile of it + 2 */
   if (tile >= ntile) return;
   sb_nat_fetch<P, PS>(pl, st, s_in, tile, threadIdx.x);
-  if (tile + G < ntile) sb_nat_fetch<P, PS>(pl, st, s_in + SB_NIN_BYTES, tile + G, threadIdx.x);
+  if (tile1 < ntile) sb_nat_fetch<P, PS>(pl, st, s_in + SB_NIN_BYTES, tile1, threadIdx.x);
   sb_cp_async_commit();
-  for (int it = 0; tile < ntile; tile += G, ++it) {
-  sb_cp_async_wait_all();                         /* tiles `tile` and `tile + G` have landed ... */
-  __syncthreads();                                /* ... for every thread; tile - G is consumed  */
+  for (int it = 0; tile < ntile; tile = tile1, tile1 = tile2, ++it) {
+  sb_cp_async_wait_all();                         /* tiles `tile` and `tile1` have landed ...    */
+  __syncthreads();                                /* ... for every thread; the previous tile is
+                                                     consumed; the claim of thread 0 is visible  */
+  tile2 = s_claim[it & 1];                        /* tile of iteration it + 2                    */
+  if (threadIdx.x == 0 && tile2 < ntile) s_claim[(it + 1) & 1] = atomicAdd(ctr, 1);
+  else if (threadIdx.x == 0) s_claim[(it + 1) & 1] = ntile;
   const unsigned char* in = s_in + (it % SB_NIN_STAGES) * SB_NIN_BYTES;
-  if (tile + G < ntile) {
-    sb_nat_prefetch<NB, PS>(pl, st, s_in + ((it + 1) % SB_NIN_STAGES) * SB_NIN_BYTES, tile + G,
+  if (tile1 < ntile) {
+    sb_nat_prefetch<NB, PS>(pl, st, s_in + ((it + 1) % SB_NIN_STAGES) * SB_NIN_BYTES, tile1,
                             role, lane);
-    if (tile + 2 * G < ntile)
-      sb_nat_fetch<P, PS>(pl, st, s_in + ((it + 2) % SB_NIN_STAGES) * SB_NIN_BYTES, tile + 2 * G,
+    if (tile2 < ntile)
+      sb_nat_fetch<P, PS>(pl, st, s_in + ((it + 2) % SB_NIN_STAGES) * SB_NIN_BYTES, tile2,
                           threadIdx.x);
     sb_cp_async_commit();
   }

@@ -99,6 +99,8 @@ struct PlanDev {
   const int64_t* nat_fbase;      /* [P][n_facets] vals index of the facet's 3 rows of sub-problem p */
   int64_t nat_dofF0;             /* first facet dof = 6 P n_cells             */
   int64_t nat_nf;                /* number of facets                          */
+  int* nat_tile_ctr;             /* [8] tile counters of the persistent row kernels, one per
+                                    sub-problem launch, zeroed once per pass     */
 };
 
 struct sb_plan {
@@ -113,6 +115,11 @@ struct sb_plan {
   cudaEvent_t evs[3] = {nullptr, nullptr, nullptr};  /* after moments, generation, fast rows */
 #endif
   int profiling = 0;
+#ifndef SB_EMUL_BUILD
+  /* the boundary-cell kernel runs beside the row kernels on a stream of its own */
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
   int gen_sig = 0;               /* 0: interpret the process list; 1: SbSigIB5; 2: SbSigPnSRH */
 };
 
@@ -1019,6 +1026,11 @@ extern "C" int sb_plan_generation_signature(const sb_plan* p) {
 
 extern "C" void sb_plan_destroy(sb_plan* pl) {
   if (!pl) return;
+#ifndef SB_EMUL_BUILD
+  if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+  if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+  if (pl->side) cudaStreamDestroy(pl->side);
+#endif
   for (void* p : pl->allocs) cudaFree(p);
 #ifndef SB_EMUL_BUILD
   if (pl->ev0) {
@@ -1229,6 +1241,9 @@ extern "C" int sb_plan_create(const sb_model* model, const sb_problem* pr, sb_pl
   /* native: tile-blocked by 32 cells (natQ_ptr) */
   if (rc == SB_OK) rc = upload<double>(pl, nullptr, (size_t)((nc + 31) / 32 * 32) * per_cell, &scr);
   d.scratch = const_cast<double*>(scr);
+  const int* ctr = nullptr;
+  if (rc == SB_OK) rc = upload<int>(pl, nullptr, 8, &ctr);
+  d.nat_tile_ctr = const_cast<int*>(ctr);
 #undef UP
   if (rc != SB_OK) { sb_plan_destroy(pl); return rc; }
   *out = pl;
@@ -1271,6 +1286,37 @@ static int bind_tables(sb_plan* pl, cudaStream_t s) {
   return SB_OK;
 }
 
+/* side stream of a plan: everything enqueued on `s` so far happens before what follows on the
+   returned stream; join_side_stream makes `s` wait for it again */
+static inline cudaStream_t fork_side_stream(sb_plan* pl, cudaStream_t s) {
+#ifdef SB_EMUL_BUILD
+  (void)pl;
+  return s;
+#else
+  if (getenv("SIMUDO_B200_NO_SIDE_STREAM")) return s;
+  if (!pl->side) {
+    if (cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      pl->side = nullptr;
+      return s;
+    }
+  }
+  cudaEventRecord(pl->ev_fork, s);
+  cudaStreamWaitEvent(pl->side, pl->ev_fork, 0);
+  return pl->side;
+#endif
+}
+static inline void join_side_stream(sb_plan* pl, cudaStream_t s) {
+#ifdef SB_EMUL_BUILD
+  (void)pl; (void)s;
+#else
+  if (!pl->side || getenv("SIMUDO_B200_NO_SIDE_STREAM")) return;
+  cudaEventRecord(pl->ev_join, pl->side);
+  cudaStreamWaitEvent(s, pl->ev_join, 0);
+#endif
+}
 static inline void rec_stage_event(sb_plan* pl, int i, cudaStream_t s) {
 #ifndef SB_EMUL_BUILD
   if (pl->profiling) cudaEventRecord(pl->evs[i], s);
@@ -1320,6 +1366,7 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
     /* closed-form path (native.inl): moments, generation, one row launch per sub-problem,
        boundary cells through the generic emitter; no slot is zeroed, no atomic on vals */
     const PlanDev& d = pl->d;
+    CUDA_TRY(cudaMemsetAsync(d.nat_tile_ctr, 0, 8 * sizeof(int), s));
     SB_LAUNCH(k_moments_nat, nblk * (unsigned)d.nb, SB_TILE, 0, s, d, sd, (int)nblk);
 #ifndef SB_EMUL_BUILD
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->evs[0], s));
@@ -1333,13 +1380,19 @@ extern "C" int sb_assemble(sb_plan* pl, const sb_state* st, double* d_vals, doub
       else                                                                                    \
         SB_LAUNCH(k_generation_nat<NBV>, nblk, SB_TILE, 0, s, d, sd);                         \
       rec_stage_event(pl, 1, s);                                                              \
-      NatRowsLauncher<NBV, NBV>::go(d, sd, d_vals, d_b, nblk, s);                             \
-      rec_stage_event(pl, 2, s);                                                              \
       if (d.n_special > 0) {                                                                  \
+        /* boundary cells (0.3 %): a latency-bound kernel of ~100 CTAs that touches no value   \
+           or residual slot the row kernels store to (facet residual rows: commutative         \
+           two-addend atomics) -- launched first, on the side stream, it runs beside them     \
+           instead of 0.15 ms after them */                                                   \
         const unsigned nsb = (unsigned)((d.n_special + SB_TILE - 1) / SB_TILE);               \
-        SB_LAUNCH(k_rows_special<NBV>, nsb * (unsigned)d.P, SB_TILE, 0, s, d, sd, d_vals,     \
+        cudaStream_t ss = fork_side_stream(pl, s);                                            \
+        SB_LAUNCH(k_rows_special<NBV>, nsb * (unsigned)d.P, SB_TILE, 0, ss, d, sd, d_vals,    \
                   d_b, (int)nsb);                                                             \
       }                                                                                       \
+      NatRowsLauncher<NBV, NBV>::go(d, sd, d_vals, d_b, nblk, s);                             \
+      rec_stage_event(pl, 2, s);                                                              \
+      if (d.n_special > 0) join_side_stream(pl, s);                                           \
       break;
 #ifdef SB_PROBE_NB          /* developer builds (tools/probe_build.sh): one band count only */
     switch (d.nb_dof) { default: SB_NAT_CASE(SB_PROBE_NB) }

@@ -105,6 +105,7 @@ static inline double atomicAdd(double* a, double v) {
   } while (!__atomic_compare_exchange_n(p, &old, des, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
   return od;
 }
+static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicMax(unsigned long long* a, unsigned long long v) {
   unsigned long long old = __atomic_load_n(a, __ATOMIC_RELAXED);
   while (old < v && !__atomic_compare_exchange_n(a, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
