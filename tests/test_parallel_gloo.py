@@ -145,19 +145,20 @@ def _dd_worker(rank, world, port, q, pattern):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('pattern', ['bsr3', 'native'])
-def test_strip_domain_decomposition_reproduces_single_domain_world2(emulated_lib, pattern):
-    """One IB mesh split into two y-strips (one ghost row of quads each, owner computes, ghost
-    update of u / base_w over gloo): the Jacobian and residual rows every rank owns are,
-    bit for bit, the rows of the single-domain assembly; together they are all rows."""
+@pytest.mark.parametrize('pattern,world', [('bsr3', 2), ('native', 2), ('bsr3', 4)])
+def test_strip_domain_decomposition_reproduces_single_domain_world2(emulated_lib, pattern, world):
+    """One IB mesh split into y-strips (one ghost row of quads per interior side, owner
+    computes, ghost update of u / base_w over gloo): the Jacobian and residual rows every rank
+    owns are, bit for bit, the rows of the single-domain assembly; together they are all rows.
+    world = 4 has middle ranks with two neighbours (what 6 of the 8 GPUs of a box are)."""
     from simudo_b200 import synthetic as syn
     from simudo_b200.fem.assembly import AssemblyPlan
     from simudo_b200.parallel import StripDecomposition
     from parity_util import run_plan
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (7 if pattern == 'native' else 0)
-    procs = [ctx.Process(target=_dd_worker, args=(r, 2, port, q, pattern)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if pattern == 'native' else 0) + 13 * world
+    procs = [ctx.Process(target=_dd_worker, args=(r, world, port, q, pattern)) for r in range(world)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=300) for _ in procs], key=lambda d: d['rank'])
@@ -182,4 +183,6 @@ def test_strip_domain_decomposition_reproduces_single_domain_world2(emulated_lib
         seen += len(o['v'])
     assert seen == g.csr.nnz                            # the owned rows are all rows, once
     assert sum(o['n_owned_cells'] for o in out) == g.n_cells
-    assert out[0]['bytes'] > 0 and out[1]['bytes'] > 0
+    assert all(o['bytes'] > 0 for o in out)
+    if world > 2:                                       # a middle rank talks to two neighbours
+        assert out[1]['bytes'] > out[0]['bytes']
