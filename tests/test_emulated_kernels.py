@@ -111,3 +111,20 @@ def test_lcn_iteration_parity_emulated(emulated_lib):
 
 def test_bulk_store_matches_entry_flush_emulated(emulated_lib):
     hc.bulk_store_matches_entry_flush()
+
+
+def test_band_solve_factored_needs_a_factorisation(emulated_lib):
+    """sb_band_solve_factored before any sb_band_solve is an argument error, not garbage."""
+    import numpy as np
+    import torch
+    from simudo_b200.fem.linear_solver import BandSolver
+    n = 6
+    rowptr = np.arange(n + 1, dtype=np.int64)
+    bs = BandSolver(None, 'cpu', csr=(n, rowptr, np.arange(n, dtype=np.int32),
+                                      np.arange(n, dtype=np.int32)))
+    with pytest.raises(RuntimeError):
+        bs.solve_factored(torch.ones(n, dtype=torch.float64))
+    x = bs.solve(torch.full((n,), 2.0, dtype=torch.float64), torch.ones(n, dtype=torch.float64))
+    assert np.allclose(x.numpy(), 0.5)
+    x2 = bs.solve_factored(torch.full((n,), 3.0, dtype=torch.float64))
+    assert np.allclose(x2.numpy(), 1.5)
