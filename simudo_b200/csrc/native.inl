@@ -26,8 +26,7 @@
  * moment scratch -- so no slot is zeroed and no atomic touches the Jacobian.
  *
  * sb_plan_create verifies the closed forms entry by entry (detect_native) and falls back
- * to the generic kernels otherwise ('ufc' numbering, dolfin / sorted patterns, Dirichlet
- * dofs on interior facets).
+ * to the generic kernels otherwise ('ufc' numbering, dolfin / sorted patterns).
  */
 
 /* moment scratch of the native path, [quantity][cell]:
@@ -991,10 +990,12 @@ static bool detect_native(const sb_model* model, const sb_problem* pr, bool bsr,
       }
     }
   }
-  /* Dirichlet dofs: boundary facets only */
+  /* Dirichlet dofs: facet dofs only (boundary facets, or interior ones such as the bounds of
+     an intermediate-band layer: both cells of such a facet go through k_rows_special, whose
+     emitter gives the shared block the identity entries of both cells) */
   for (int64_t i = 0; i < pr->n_bc; ++i) {
     const int64_t d = pr->h_bc_dofs[i];
-    if (d < F0 || !fbnd[((d - F0) % (3 * nf)) / 3]) return false;
+    if (d < F0) return false;
   }
   *dofF0 = F0;
   *n_facets = nf;

@@ -819,7 +819,13 @@ SB_HD void sb_emit(const SbIO& io, int64_t rowbase, int i, int j, double val, do
     if (io.nat) {
       const int bits = (io.finfo >> (4 * fi)) & 3;
       if (bits & 2) return;                                   /* the first cell writes it */
-      if (!(bits & 1)) val += io.snb[6 * fi + sb_sym3((i % 15 - 3) % 3, (j % 15 - 3) % 3)];
+      if (!(bits & 1)) {
+        /* the neighbour's share of the block: its cell block from the moment scratch -- unless
+           the pair involves a Dirichlet dof of this (interior) facet: the neighbour applies the
+           same element-wise rule, so its share is the identity entry */
+        if (SP && (sb_is_bc(io, i) || sb_is_bc(io, j))) val += (i == j) ? 1.0 : 0.0;
+        else val += io.snb[6 * fi + sb_sym3((i % 15 - 3) % 3, (j % 15 - 3) % 3)];
+      }
       *dst = val;
     } else {
       SB_ATOMIC_ADD(dst, val);

@@ -108,7 +108,7 @@ def pn_problem(nx=9, ny=2, length=0.5, height=1.0, numbering='b200', with_bcs=Tr
 
 
 def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
-               const_mobility=True, pattern='structural', strip=None):
+               const_mobility=True, pattern='structural', strip=None, ib_bounds_bc=False):
     """Four-layer FSF/p/IB/n intermediate-band cell (BASELINE config 2/4):
     CB, IB, VB; two Shockley-Read traps, radiative CV, radiative CI/IV with
     absorption, three optical fields."""
@@ -185,6 +185,17 @@ def ib_problem(nx=9, ny=2, height=1.0, numbering='b200', with_bcs=True,
     if with_bcs:
         _attach_bcs(pa, mesh, n_dof_bands=3, minority_left=[0], minority_right=[2],
                     extra_all=[1])
+        if ib_bounds_bc:
+            # IB/j = 0 on the bounds of the IB layer (fourlayer.py: spatial.add_BC('IB/j',
+            # F.nonconductive | F.IB_bounds, zj)): Dirichlet dofs on INTERIOR facets
+            fm = mesh.facet_midpoints()
+            fv = mesh.facet_vertices
+            vx = mesh.coordinates[fv][:, :, 0]
+            vertical = np.abs(vx[:, 0] - vx[:, 1]) < 1e-14
+            on_edge = vertical & ((np.abs(fm[:, 0] - edges[2]) < 1e-12) |
+                                  (np.abs(fm[:, 0] - edges[3]) < 1e-12))
+            extra = pa.facet_dofs(1 + IB, np.nonzero(on_edge)[0]).ravel()
+            pa.set_bc_dofs(np.unique(np.concatenate([pa.bc_dofs, extra])))
     pa.layer_edges = edges
     return pa
 

@@ -64,6 +64,29 @@ def test_assembly_parity_at_bench_scale():
     assert cells > 2 * (n - 1) ** 2 - 1
 
 
+@pytest.mark.parametrize('pattern', ['native', 'bsr3'])
+def test_interior_facet_dirichlet_dofs_on_the_closed_form_path(pattern):
+    """Dirichlet dofs on INTERIOR facets (IB/j = 0 on the bounds of the IB layer,
+    fourlayer.py's F.IB_bounds): both cells of such a facet are boundary cells; the shared
+    (facet, facet) block carries the identity entries of both (diagonal 2) and the
+    plan still runs the closed-form kernels."""
+    pa, st, plan, vals, b, vals0, b0 = hc.assembly_parity(
+        syn.ib_problem, 9, 4, pattern=pattern, ib_bounds_bc=True)
+    assert plan.is_native()
+    import numpy as np
+    interior_bc = [d for d in pa.bc_dofs if d >= 6 * pa.P * pa.n_cells]
+    fc = pa.mesh.facet_cells
+    nf = pa.mesh.num_facets
+    F0 = 6 * pa.P * pa.n_cells
+    on_interior = [d for d in interior_bc if fc[((d - F0) % (3 * nf)) // 3, 1] >= 0]
+    assert len(on_interior) >= 6
+    col, row = pa.csr.column_indices(want_rows=True)
+    for d in on_interior[:6]:
+        diag = vals[(row == d) & (col == d)]
+        assert len(diag) == 1 and diag[0] == 2.0
+        assert np.abs(vals[(row == d) & (col != d)]).max() == 0.0
+
+
 def test_generation_signature():
     hc.generation_signature_matches_interpreter()
 
