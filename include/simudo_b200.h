@@ -175,7 +175,7 @@ int sb_plan_zero_values(sb_plan* plan, double* d_vals, void* stream);
 int64_t sb_plan_nnz(const sb_plan* plan);
 /* 1 when the plan runs the closed-form kernels (csrc/native.inl): dof numbering 'b200' and
  * CSR pattern 'native' of simudo_b200/fem/dofmap.py (structural non-zeros of the dolfin
- * pattern, columns of a row in emission order), Dirichlet dofs on boundary facets only.
+ * pattern, columns of a row in emission order), Dirichlet dofs on facet dofs only (boundary or interior facets).
  * Any other numbering / pattern handed to sb_plan_create runs the generic kernels.      */
 int sb_plan_is_native(const sb_plan* plan);
 /* Which instance of the generation kernel (a6: electro_optical_process.py:141-157,294-312,
