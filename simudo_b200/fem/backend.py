@@ -9,6 +9,8 @@ The device copy of the solution is the single source of truth during
 ("data ownership").  No CPU fallback: constructing this
 backend without a CUDA device raises.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -16,6 +18,24 @@ from .assembly import AssemblyPlan
 from .linear_solver import BandSolver, make_solver
 
 __all__ = ['CudaBackend', 'CudaLCNBackend']
+
+
+def _nvtx(name):
+    """NVTX range around a device phase of the Newton loop when SIMUDO_B200_NVTX=1 (for
+    `ncu --nvtx --nvtx-include` / nsys timelines); a no-op otherwise."""
+    def deco(f):
+        if os.environ.get('SIMUDO_B200_NVTX') != '1':
+            return f
+
+        def g(*a, **k):
+            torch.cuda.nvtx.range_push('simudo_b200:' + name)
+            try:
+                return f(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        g.__name__, g.__doc__ = f.__name__, f.__doc__
+        return g
+    return deco
 
 
 class CudaBackend(object):
@@ -95,16 +115,19 @@ class CudaBackend(object):
             self.plan.natbc_eval(c['cell'], c['local'], c['slot'], c['c0'], c['p2'], self.natbc)
 
     # -- hot loop ----------------------------------------------------------------
+    @_nvtx('assemble')
     def assemble(self):
         self.plan.assemble(self.u, self.base_w, self.thmeq, self.phi_opt, self.bc_values,
                            self.natbc, self.vals, self.b)
 
+    @_nvtx('linear_solve')
     def solve(self):
         if self._solver is None:
             # symbolic phase once per lowered problem, reused by every Newton step
             self._solver = make_solver(self.pa, self.device)
         self._solver.solve(self.vals, self.b, self.du)
 
+    @_nvtx('newton_update')
     def newton_update(self, tol, omega, max_du, rel_tol, abs_tol, log_alpha=None):
         if not isinstance(tol, torch.Tensor):
             tol = self.T(tol)
@@ -115,6 +138,7 @@ class CudaBackend(object):
                     rel_du_norm=float(np.sqrt(out[2])) if out[5] > 0 else float('nan'),
                     combined_du_norm=float(out[3]), has_nans=bool(out[4] > 0))
 
+    @_nvtx('rebase_w')
     def rebase(self, band, ohmic, thm_avg):
         if ohmic is None:
             self.plan.rebase_w(self.u, self.base_w, band)
@@ -134,6 +158,7 @@ class CudaBackend(object):
         self.plan.rebase_w(self.u, self.base_w, band, cache['cells'], avg)
 
     # -- a10: optical sub-solves (physics/steppers.py:120-136) ------------------------
+    @_nvtx('optical_update')
     def optical_update(self, space, specs):
         """``specs``: [(field index, direction, bc_dofs, bc_values)]; solves every
         field for the current PDD state and writes its flux into ``phi_opt``."""
