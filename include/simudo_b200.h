@@ -168,7 +168,12 @@ int64_t sb_launch_count(void);
  * d_vals [nnz] (dolfin pattern; structural zeros are written once by
  * sb_plan_zero_values and never touched again), d_b [N].  Either may be NULL.
  * d_vals must be 16-byte aligned (bulk copies; SB_ERR_ARG otherwise) -- any cudaMalloc'ed
- * array is, a slice at an odd element offset is not.                              */
+ * array is, a slice at an odd element offset is not.
+ * Stream semantics: everything is ordered after the work already on `stream` and complete
+ * for what is enqueued on `stream` afterwards; internally the boundary-cell kernel runs on a
+ * side stream of the plan, forked and joined with events.  One pass of a plan at a time:
+ * do not call sb_assemble on the same plan from two streams concurrently (the plan owns the
+ * moment scratch and the tile counters); different plans are independent.          */
 int sb_assemble(sb_plan* plan, const sb_state* state,
                 double* d_vals, double* d_b, void* stream);
 int sb_plan_zero_values(sb_plan* plan, double* d_vals, void* stream);
