@@ -65,5 +65,30 @@ def main():
                   f, indent=1)
 
 
+def reference_parameter_fixture():
+    """Config 2 at the reference's own parameters and mesh (fourlayer_example.py:56-110): the
+    full light ramp + 26-point bias sweep through the oracle backend (7-8 minutes on 8 cores);
+    the efficiency of this J-V is the number the tutorial quotes (34.1 %, tutorial.rst:60)."""
+    import time
+    import numpy as np
+    from oracle_backend import OracleBackend
+    from simudo_b200.example import fourlayer
+    from simudo_b200.example.iv_analysis import IV_params, efficiency
+    V = [float(v) for v in np.linspace(0, 1.7, 26)]
+    t = time.time()
+    jv = [(float(v), float(j)) for v, j in fourlayer.run(P=dict(V_exts=V), backend_factory=OracleBackend)]
+    p = IV_params([j for _, j in jv], [v for v, _ in jv], -1.0)
+    with open(os.path.join(HERE, 'ib_cell_reference_parameters_oracle.json'), 'w') as f:
+        json.dump(dict(source='oracle backend, tests/golden/make_golden.py: fourlayer.run at the '
+                              'defaults of the reference example, 26 voltages 0 .. 1.7 V; %.0f s'
+                              % (time.time() - t),
+                       units=['V', 'mA/cm^2'], jv=jv, efficiency=efficiency(jv), voc=p.voc,
+                       jsc=p.isc, ff=p.ff, tutorial_efficiency=0.341,
+                       tutorial_source='doc/source/user/tutorial.rst:60'), f, indent=1)
+
+
 if __name__ == '__main__':
-    main()
+    if '--reference-parameters' in sys.argv:
+        reference_parameter_fixture()
+    else:
+        main()

@@ -129,3 +129,40 @@ def test_first_newton_step_at_reference_parameters_is_resolved(emulated_lib):
     for p in range(1, pa.P):
         assert np.abs(x[pa.cell_dofs[:, lay['dg'][p]]]).max() < 1e-6
     assert np.abs(x - be.du).max() <= 1e-6 * max(np.abs(be.du).max(), 1e-12) + 1e-12
+
+
+def test_reference_parameter_run_gives_the_tutorial_efficiency():
+    """Config 2 at the reference's own parameters and mesh (CB 2.0 eV, IB 1.2 eV, 279 x-points,
+    X = 100; ``fourlayer_example.py:56-110``): the J-V computed through the oracle backend
+    (fixture ``ib_cell_reference_parameters_oracle.json``, generated by
+    ``tests/golden/make_golden.py --reference-parameters``, 7-8 CPU minutes) analysed like
+    ``fourlayer_example.efficiency_analysis`` gives the efficiency the reference's tutorial
+    quotes for this example: 34.1 % (``doc/source/user/tutorial.rst:60``).  The only
+    reference-held end-to-end number of the IB / optics path."""
+    from simudo_b200.example.iv_analysis import IV_params, efficiency
+    with open(os.path.join(HERE, 'golden', 'ib_cell_reference_parameters_oracle.json')) as f:
+        fx = json.load(f)
+    jv = fx['jv']
+    assert len(jv) == 26 and jv[0][0] == 0.0 and abs(jv[-1][0] - 1.7) < 1e-12
+    eff = efficiency(jv, X=100.0, Ts=6000.0)
+    assert abs(eff - fx['efficiency']) < 1e-12
+    assert abs(eff - 0.341) < 1.5e-3, eff                    # 34.17 % vs "34.1 %"
+    p = IV_params([j for _, j in jv], [v for v, _ in jv], -1.0)
+    assert 1.5 < p.voc < 1.65 and 1.3 < p.mppv < p.voc
+    # photocurrent: 38.7 mA/cm^2 per sun at X = 100, flat up to ~1.3 V (the IB cell's plateau)
+    assert abs(p.isc / 100.0 + 38.74) < 0.05
+    j = np.array([b for _, b in jv])
+    assert (np.diff(j) > 0).all() and abs(j[19] / j[0] - 1.0) < 6e-3
+
+
+@pytest.mark.gpu
+def test_ib_cell_at_reference_parameters_on_gpu():
+    """The light ramp of the full-size four-layer cell at the reference's parameters on the
+    B200 (closed-form kernels: IB/j = 0 on the interior IB bounds included) reproduces the
+    oracle fixture's short-circuit current to 1e-6."""
+    from simudo_b200.example import fourlayer
+    with open(os.path.join(HERE, 'golden', 'ib_cell_reference_parameters_oracle.json')) as f:
+        fx = json.load(f)
+    jv = fourlayer.run(P=dict(V_exts=[0.0]))
+    assert abs(jv[0][0]) < 1e-15
+    assert abs(jv[0][1] / fx['jv'][0][1] - 1.0) < 1e-6, (jv[0][1], fx['jv'][0][1])
