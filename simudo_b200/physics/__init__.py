@@ -10,3 +10,4 @@ from .material import Material, SimpleSiliconMaterial, BadSimpleSiliconMaterial
 from .optical import Optical, OpticalField, AbsorptionRangesHelper
 from .steppers import (VoltageStepper, OpticalIntensityAdaptiveStepper,
                        NonequilibriumCoupledStepper, NewtonBailoutException)
+from .heterojunction import ThermionicHeterojunction

@@ -81,3 +81,12 @@ def test_first_failure_by_exception_propagates():
             raise RuntimeError('no device')
     with pytest.raises(RuntimeError):
         Boom(parameter_target_values=[1.0]).do_loop()
+
+
+def test_thermionic_heterojunction_fails_by_name():
+    # reference physics/heterojunction.py:11-135: same constructor; the facet term is not
+    # built on the device path and there is no CPU fallback, so register() must raise
+    from simudo_b200.physics import ThermionicHeterojunction
+    h = ThermionicHeterojunction(band=object(), boundary=object())
+    with pytest.raises(NotImplementedError, match='heterojunction'):
+        h.register()
